@@ -1,0 +1,93 @@
+"""ctypes loader for libcbops.so — the ONLY compute backend of this package.
+
+There is deliberately no CPU or PyTorch fallback: if the CUDA library is missing or a call fails,
+the operators raise (`CbopsError`).  `python -m contrastboundary_b200.build` builds the library.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcbops.so")
+
+
+class CbopsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CbopsError(
+                "contrastboundary_b200/libcbops.so is missing — build it with "
+                "`python -m contrastboundary_b200.build` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.cb_last_error_string.restype = C.c_char_p
+        _lib.cb_knn_workspace_bytes.restype = C.c_size_t
+        _lib.cb_knn_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        for name in ("cb_cbl_workspace_bytes",):
+            if hasattr(_lib, name):
+                getattr(_lib, name).restype = C.c_size_t
+    return _lib
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)"""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().cb_last_error_string()
+        raise CbopsError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise CbopsError("contrastboundary_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+def call(name, *args):
+    f = getattr(lib(), name)
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            conv.append(C.c_void_p(a.data_ptr()))
+        elif isinstance(a, float):
+            conv.append(C.c_float(a))
+        elif isinstance(a, int):
+            conv.append(C.c_int(a)) if abs(a) < 2 ** 31 else conv.append(C.c_size_t(a))
+        else:
+            conv.append(a)
+    check(f(*conv), name)
+
+
+class SizeT:
+    """wrap an int that must be passed as size_t"""
+    def __init__(self, v):
+        self.v = int(v)
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="default"):
+    """Cached, 256-byte aligned byte workspace per (device, stream, tag); grows monotonically."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream, tag)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t

@@ -1,0 +1,64 @@
+// common.cuh — shared helpers for libcbops (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/cbops.h"
+
+#define CB_FULL_MASK 0xffffffffu
+
+void cb_set_error(const char *fmt, ...);
+
+#define CB_REQUIRE(cond, code, ...)            \
+    do {                                       \
+        if (!(cond)) {                         \
+            cb_set_error(__VA_ARGS__);         \
+            return (code);                     \
+        }                                      \
+    } while (0)
+
+#define CB_CUDA_CHECK(what)                                                             \
+    do {                                                                                \
+        cudaError_t e__ = cudaPeekAtLastError();                                        \
+        if (e__ != cudaSuccess) {                                                       \
+            cb_set_error("%s: %s", what, cudaGetErrorString(e__));                      \
+            (void)cudaGetLastError();                                                   \
+            return CB_ECUDA;                                                            \
+        }                                                                               \
+    } while (0)
+
+static inline size_t cb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Squared distance exactly as the reference's SASS computes it (nvcc -fmad=true on
+// (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f)):  t = dx*dx; t = fma(dy,dy,t); t = fma(dz,dz,t)
+// (knnquery_cuda_kernel.cu:99, sampling_cuda_kernel.cu:54).
+__device__ __forceinline__ float cb_sqdist(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    float t = __fmul_rn(dx, dx);
+    t = __fmaf_rn(dy, dy, t);
+    t = __fmaf_rn(dz, dz, t);
+    return t;
+}
+
+// first i with q < offset[i]  (knnquery_cuda_kernel.cu:51-62), by binary search
+__device__ __forceinline__ int cb_scene_of(int q, const int *__restrict__ offset, int b)
+{
+    int lo = 0, hi = b - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (q < __ldg(offset + mid)) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ unsigned cb_f2ord(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float cb_ord2f(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}

@@ -1,0 +1,535 @@
+// knn.cu — a1: grid-hash K-nearest-neighbour query, bit-identical to the reference's brute-force
+// heap kernel (pytorch/lib/pointops/src/knnquery/knnquery_cuda_kernel.cu:65-119).
+//
+// Pipeline (all on the caller's stream, no host sync, no allocation):
+//   bbox -> trial grid (volume heuristic) -> occupancy + local-dimension estimate -> final cell
+//   size -> counting sort of the supports by cell (x-fastest cell order, so a row of cells is a
+//   contiguous point range) -> warp-per-query ring search with a register-resident sorted top-K
+//   -> exact replay of the reference heap for the few queries whose answer depends on it (ties).
+#include "knn.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+// ---------------------------------------------------------------------------------------------
+// error string
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void cb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *cb_last_error_string(void) { return g_err; }
+extern "C" int cb_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+static int cb_cell_cap(int n, int b) { return 16 * n + 4096 * b + 4096; }
+static int cb_trial_cap(int n, int b) { return 2 * n + 512 * b + 512; }
+
+size_t cb_grid_layout(int n, int m, int b, void *base, CbGridView *v)
+{
+    size_t off = 0;
+    char *p = (char *)base;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = cb_align_up(off + bytes, 256);
+        return p ? (void *)(p + o) : (void *)nullptr;
+    };
+    CbGridView t;
+    t.cell_cap = cb_cell_cap(n, b);
+    t.trial_cap = cb_trial_cap(n, b);
+    t.max_tiles = (t.cell_cap + 1 + CB_SCAN_TILE - 1) / CB_SCAN_TILE;
+    t.hdr = (CbGridHeader *)take(sizeof(CbGridHeader));
+    t.scenes = (CbScene *)take(sizeof(CbScene) * (size_t)b);
+    t.bbox = (unsigned *)take(sizeof(unsigned) * 6 * (size_t)b);
+    t.occ = (int *)take(sizeof(int) * 2 * (size_t)b);
+    t.tile_sums = (int *)take(sizeof(int) * (size_t)t.max_tiles);
+    t.cells = (int *)take(sizeof(int) * ((size_t)t.cell_cap + 1));
+    t.coarse = (int *)take(sizeof(int) * ((size_t)t.trial_cap + 1));
+    t.point_cell = (int *)take(sizeof(int) * (size_t)n);
+    t.point_rank = (int *)take(sizeof(int) * (size_t)n);
+    t.sorted = (float4 *)take(sizeof(float4) * (size_t)n);
+    t.flagged = (int *)take(sizeof(int) * (size_t)(m > 0 ? m : 1));
+    if (v) *v = t;
+    return off;
+}
+
+extern "C" size_t cb_knn_workspace_bytes(int n, int m, int b)
+{
+    if (n < 0 || m < 0 || b <= 0) return 0;
+    return cb_grid_layout(n, m, b, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid build kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bbox_init(unsigned *bbox, int *occ, int b, CbGridHeader *hdr, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b * 6) bbox[i] = (i % 6 < 3) ? 0xffffffffu : 0u;   // min slots / max slots
+    if (i < b * 2) occ[i] = 0;
+    if (i == 0) { hdr->total_cells = 0; hdr->flagged_count = 0; hdr->n = n; hdr->b = b; hdr->trial = 1; }
+}
+
+__global__ void k_bbox(const float *__restrict__ xyz, int n, const int *__restrict__ offset, int b, unsigned *bbox)
+{
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        const int ic = valid ? i : n - 1;
+        const int s = cb_scene_of(ic, offset, b);
+        const unsigned ux = cb_f2ord(__ldg(xyz + 3 * ic)), uy = cb_f2ord(__ldg(xyz + 3 * ic + 1)),
+                       uz = cb_f2ord(__ldg(xyz + 3 * ic + 2));
+        const int s0 = __shfl_sync(CB_FULL_MASK, s, 0);
+        if (__all_sync(CB_FULL_MASK, s == s0)) {
+            unsigned mnx = __reduce_min_sync(CB_FULL_MASK, ux), mny = __reduce_min_sync(CB_FULL_MASK, uy),
+                     mnz = __reduce_min_sync(CB_FULL_MASK, uz);
+            unsigned mxx = __reduce_max_sync(CB_FULL_MASK, ux), mxy = __reduce_max_sync(CB_FULL_MASK, uy),
+                     mxz = __reduce_max_sync(CB_FULL_MASK, uz);
+            if (lane == 0) {
+                unsigned *bb = bbox + 6 * s0;
+                atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMin(bb + 2, mnz);
+                atomicMax(bb + 3, mxx); atomicMax(bb + 4, mxy); atomicMax(bb + 5, mxz);
+            }
+        } else if (valid) {
+            unsigned *bb = bbox + 6 * s;
+            atomicMin(bb + 0, ux); atomicMin(bb + 1, uy); atomicMin(bb + 2, uz);
+            atomicMax(bb + 3, ux); atomicMax(bb + 4, uy); atomicMax(bb + 5, uz);
+        }
+    }
+}
+
+__device__ __forceinline__ float cb_target_occ(int nsample)
+{
+    // points per occupied cell that makes the 3x3x3 block hold the K nearest for most queries
+    return fminf(fmaxf(0.45f * (float)nsample, 2.0f), 48.0f);
+}
+
+// dims for cell size h; returns number of cells
+__device__ __forceinline__ long long cb_dims(float ex, float ey, float ez, float h, int *nx, int *ny, int *nz)
+{
+    const float inv = 1.0f / h;
+    *nx = (int)fminf(floorf(ex * inv), (float)(CB_GRID_MAX_DIM - 1)) + 1;
+    *ny = (int)fminf(floorf(ey * inv), (float)(CB_GRID_MAX_DIM - 1)) + 1;
+    *nz = (int)fminf(floorf(ez * inv), (float)(CB_GRID_MAX_DIM - 1)) + 1;
+    return (long long)*nx * *ny * *nz;
+}
+
+// phase 0: trial grid from the bbox-volume heuristic; phase 1: final grid from measured occupancy
+__global__ void k_params(CbGridHeader *hdr, CbScene *scenes, const unsigned *bbox, const int *occ,
+                         const int *__restrict__ offset, int b, int n, int nsample, int cap, int phase)
+{
+    const float target = cb_target_occ(nsample);
+    for (int s = threadIdx.x; s < b; s += blockDim.x) {
+        CbScene sc;
+        sc.start = s == 0 ? 0 : offset[s - 1];
+        sc.end = offset[s];
+        sc.pad = 0;
+        const int ns = sc.end - sc.start;
+        if (ns <= 0) {
+            sc.ox = sc.oy = sc.oz = 0.f; sc.h = 1.f; sc.inv_h = 1.f; sc.nx = sc.ny = sc.nz = 1; sc.cell_base = 0;
+            scenes[s] = sc;
+            continue;
+        }
+        const unsigned *bb = bbox + 6 * s;
+        sc.ox = cb_ord2f(bb[0]); sc.oy = cb_ord2f(bb[1]); sc.oz = cb_ord2f(bb[2]);
+        float ex = cb_ord2f(bb[3]) - sc.ox, ey = cb_ord2f(bb[4]) - sc.oy, ez = cb_ord2f(bb[5]) - sc.oz;
+        if (!(ex >= 0.f) || !(ey >= 0.f) || !(ez >= 0.f) || ex > 1e30f || ey > 1e30f || ez > 1e30f) { ex = ey = ez = 0.f; }
+        const float emax = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
+        float h;
+        if (phase == 0) {
+            const float vx = fmaxf(ex, 1e-3f * emax), vy = fmaxf(ey, 1e-3f * emax), vz = fmaxf(ez, 1e-3f * emax);
+            h = cbrtf(target * vx * vy * vz / (float)ns);
+        } else {
+            const CbScene old = scenes[s];
+            const float m1 = (float)max(occ[2 * s], 1), m2 = (float)max(occ[2 * s + 1], 1);
+            float dim = log2f(fmaxf(m1 / m2, 1.0f));
+            dim = fminf(fmaxf(dim, 1.5f), 3.0f);
+            const float o0 = (float)ns / m1;
+            h = old.h * powf(target / o0, 1.0f / dim);
+        }
+        h = fmaxf(h, emax / (float)(CB_GRID_MAX_DIM - 1));
+        h = fmaxf(h, 1e-20f);
+        // per-scene share of the cell budget
+        const long long budget = max((long long)((double)(cap - 64 * b - 1) * (double)ns / (double)max(n, 1)), 64LL);
+        int nx, ny, nz;
+        for (int it = 0; it < 400; it++) {
+            if (cb_dims(ex, ey, ez, h, &nx, &ny, &nz) <= budget) break;
+            h *= 1.1f;
+        }
+        cb_dims(ex, ey, ez, h, &nx, &ny, &nz);
+        sc.h = h; sc.inv_h = 1.0f / h; sc.nx = nx; sc.ny = ny; sc.nz = nz; sc.cell_base = 0;
+        scenes[s] = sc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int base = 0;
+        for (int s = 0; s < b; s++) {
+            scenes[s].cell_base = base;
+            const int ns = scenes[s].end - scenes[s].start;
+            if (ns > 0) base += scenes[s].nx * scenes[s].ny * scenes[s].nz;
+        }
+        hdr->total_cells = base;
+        hdr->trial = phase == 0;
+    }
+}
+
+// count points per cell.  trial: also measure occupied cells at h and 2h.
+__global__ void k_count(const float *__restrict__ xyz, int n, const int *__restrict__ offset, int b,
+                        const CbScene *__restrict__ scenes, int *cells, int *coarse, int *occ, int *point_cell,
+                        int *point_rank, int trial)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int s = cb_scene_of(i, offset, b);
+        const CbScene sc = scenes[s];
+        const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+        int cx = (int)floorf(cb_cellf(x, sc.ox, sc.inv_h)), cy = (int)floorf(cb_cellf(y, sc.oy, sc.inv_h)),
+            cz = (int)floorf(cb_cellf(z, sc.oz, sc.inv_h));
+        cx = min(max(cx, 0), sc.nx - 1); cy = min(max(cy, 0), sc.ny - 1); cz = min(max(cz, 0), sc.nz - 1);
+        const int cell = sc.cell_base + (cz * sc.ny + cy) * sc.nx + cx;
+        const int rank = atomicAdd(cells + cell, 1);
+        if (trial) {
+            if (rank == 0) atomicAdd(occ + 2 * s, 1);
+            const int hx = (sc.nx + 1) >> 1, hy = (sc.ny + 1) >> 1;
+            const int cc = sc.cell_base + ((cz >> 1) * hy + (cy >> 1)) * hx + (cx >> 1);
+            if (atomicExch(coarse + cc, 1) == 0) atomicAdd(occ + 2 * s + 1, 1);
+        } else {
+            point_cell[i] = cell;
+            point_rank[i] = rank;
+        }
+    }
+}
+
+// exclusive scan over cells[0 .. total_cells] (inclusive of the sentinel), in place, two kernels
+__global__ void __launch_bounds__(256) k_scan_tiles(int *cells, int *tile_sums, const CbGridHeader *hdr)
+{
+    const int total = hdr->total_cells + 1;
+    const int tile0 = blockIdx.x * CB_SCAN_TILE;
+    if (tile0 >= total) return;
+    __shared__ int warp_sums[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int v[8];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tile0 + t * 8 + k;
+        v[k] = i < total ? cells[i] : 0;
+        sum += v[k];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(CB_FULL_MASK, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < w; k++) woff += warp_sums[k];
+    int run = woff + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tile0 + t * 8 + k;
+        if (i < total) cells[i] = run;
+        run += v[k];
+    }
+    if (t == 255) tile_sums[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__(256) k_scan_add(int *cells, const int *tile_sums, const CbGridHeader *hdr)
+{
+    const int total = hdr->total_cells + 1;
+    const int tile0 = blockIdx.x * CB_SCAN_TILE;
+    if (tile0 >= total || blockIdx.x == 0) return;
+    __shared__ int red[256];
+    int acc = 0;
+    for (int k = threadIdx.x; k < blockIdx.x; k += 256) acc += tile_sums[k];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const int off = red[0];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tile0 + threadIdx.x * 8 + k;
+        if (i < total) cells[i] += off;
+    }
+}
+
+__global__ void k_fill(const float *__restrict__ xyz, int n, const int *__restrict__ cells,
+                       const int *__restrict__ point_cell, const int *__restrict__ point_rank, float4 *sorted)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pos = cells[point_cell[i]] + point_rank[i];
+        sorted[pos] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), __int_as_float(i));
+    }
+}
+
+// zero cells[0 .. total_cells] and the trial's coarse flags (sizes are device-known)
+__global__ void k_zero_cells(int *cells, int *coarse, const CbGridHeader *hdr, int zero_coarse)
+{
+    const int total = hdr->total_cells + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        cells[i] = 0;
+        if (zero_coarse) coarse[i] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// query kernel: one warp per query
+// ---------------------------------------------------------------------------------------------
+template <int KPL>
+__global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__restrict__ new_xyz,
+                                                   const int *__restrict__ new_offset, int b, int self_query,
+                                                   const CbScene *__restrict__ scenes, const int *__restrict__ cells,
+                                                   const float4 *__restrict__ sorted, int *__restrict__ idx,
+                                                   float *__restrict__ dist2, int sqrt_dist, CbGridHeader *hdr,
+                                                   int *flagged)
+{
+    __shared__ CbWarpScratch scratch[4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * 4 + wib;
+    if (w >= m) return;
+    int q = w;
+    float qx, qy, qz;
+    if (self_query) {   // walk queries in cell order: neighbouring warps touch the same cells
+        const float4 p = __ldg(sorted + w);
+        q = __float_as_int(p.w); qx = p.x; qy = p.y; qz = p.z;
+    } else {
+        qx = __ldg(new_xyz + 3 * q); qy = __ldg(new_xyz + 3 * q + 1); qz = __ldg(new_xyz + 3 * q + 2);
+    }
+    const int s = cb_scene_of(q, new_offset, b);
+    const CbScene sc = scenes[s];
+    CbTopK<KPL> tk;
+    tk.init(K, lane, sc.start);
+    bool ok = cb_grid_search<KPL>(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+    if (ok && tk.has_tie()) ok = false;
+    if (!ok) {
+        if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < KPL; j++) {
+        const int e = j * 32 + lane;
+        if (e < K) {
+            idx[(size_t)q * K + e] = tk.i[j];
+            dist2[(size_t)q * K + e] = sqrt_dist ? __fsqrt_rn(tk.d[j]) : tk.d[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact replay of the reference kernel for flagged queries: one block per flagged query, the
+// block evaluates distances in index order, thread 0 runs the reference's heap
+// (knnquery_cuda_kernel.cu:21-48,91-110) in shared memory.
+// ---------------------------------------------------------------------------------------------
+#define CB_REPLAY_THREADS 256
+__global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const float *__restrict__ xyz,
+                                                                 const float *__restrict__ new_xyz,
+                                                                 const int *__restrict__ offset,
+                                                                 const int *__restrict__ new_offset, int b,
+                                                                 int *__restrict__ idx, float *__restrict__ dist2,
+                                                                 int sqrt_dist, const CbGridHeader *hdr,
+                                                                 const int *__restrict__ flagged)
+{
+    extern __shared__ unsigned char smem_raw[];
+    float *hd = (float *)smem_raw;          // K
+    int *hi = (int *)(hd + K);              // K
+    float *cd = (float *)(hi + K);          // CB_REPLAY_THREADS
+    const int t = threadIdx.x;
+    const int count = hdr->flagged_count;
+    for (int f = blockIdx.x; f < count; f += gridDim.x) {
+        const int q = flagged[f];
+        const int s = cb_scene_of(q, new_offset, b);
+        const int start = s == 0 ? 0 : offset[s - 1], end = offset[s];
+        const float qx = new_xyz[3 * q], qy = new_xyz[3 * q + 1], qz = new_xyz[3 * q + 2];
+        for (int k = t; k < K; k += CB_REPLAY_THREADS) { hd[k] = 1e10f; hi[k] = start; }
+        __syncthreads();
+        for (int base = start; base < end; base += CB_REPLAY_THREADS) {
+            const int i = base + t;
+            float d = 3.0e38f;
+            if (i < end) d = cb_sqdist(qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+            cd[t] = d;
+            const int any = __syncthreads_or(i < end && d < hd[0]);
+            if (any) {
+                if (t == 0) {
+                    const int lim = min(CB_REPLAY_THREADS, end - base);
+                    for (int u = 0; u < lim; u++) {
+                        const float d2 = cd[u];
+                        if (d2 < hd[0]) {
+                            hd[0] = d2; hi[0] = base + u;
+                            int root = 0, child = 1;                       // reheap
+                            while (child < K) {
+                                if (child + 1 < K && hd[child + 1] > hd[child]) child++;
+                                if (hd[root] > hd[child]) break;
+                                float td = hd[root]; hd[root] = hd[child]; hd[child] = td;
+                                int ti = hi[root]; hi[root] = hi[child]; hi[child] = ti;
+                                root = child; child = root * 2 + 1;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (t == 0) {                                                       // heap_sort
+            for (int i = K - 1; i > 0; i--) {
+                float td = hd[0]; hd[0] = hd[i]; hd[i] = td;
+                int ti = hi[0]; hi[0] = hi[i]; hi[i] = ti;
+                int root = 0, child = 1;
+                while (child < i) {
+                    if (child + 1 < i && hd[child + 1] > hd[child]) child++;
+                    if (hd[root] > hd[child]) break;
+                    float t2 = hd[root]; hd[root] = hd[child]; hd[child] = t2;
+                    int t3 = hi[root]; hi[root] = hi[child]; hi[child] = t3;
+                    root = child; child = root * 2 + 1;
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = t; k < K; k += CB_REPLAY_THREADS) {
+            idx[(size_t)q * K + k] = hi[k];
+            dist2[(size_t)q * K + k] = sqrt_dist ? __fsqrt_rn(hd[k]) : hd[k];
+        }
+        __syncthreads();
+    }
+}
+
+// brute-force for every query (K > 256): flag all, then replay
+__global__ void k_flag_all(int m, CbGridHeader *hdr, int *flagged)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) flagged[i] = i;
+    if (i == 0) hdr->flagged_count = m;
+}
+
+__global__ void k_reset_flagged(CbGridHeader *hdr) { hdr->flagged_count = 0; }
+
+// ---------------------------------------------------------------------------------------------
+// host entry points
+// ---------------------------------------------------------------------------------------------
+static int grid_blocks(int n, int threads) { int g = (n + threads - 1) / threads; return g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g); }
+
+int cb_grid_build_impl(const float *xyz, int n, const int *offset, int b, int nsample_hint, const CbGridView &v,
+                           cudaStream_t st)
+{
+    const int ib = (b * 6 + 127) / 128;
+    k_bbox_init<<<ib, 128, 0, st>>>(v.bbox, v.occ, b, v.hdr, n);
+    if (n > 0) k_bbox<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.bbox);
+    // trial grid
+    k_params<<<1, 128, 0, st>>>(v.hdr, v.scenes, v.bbox, v.occ, offset, b, n, nsample_hint, v.trial_cap, 0);
+    k_zero_cells<<<148, 256, 0, st>>>(v.cells, v.coarse, v.hdr, 1);
+    if (n > 0) k_count<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.scenes, v.cells, v.coarse, v.occ,
+                                                             v.point_cell, v.point_rank, 1);
+    // final grid
+    k_params<<<1, 128, 0, st>>>(v.hdr, v.scenes, v.bbox, v.occ, offset, b, n, nsample_hint, v.cell_cap, 1);
+    k_zero_cells<<<148 * 2, 256, 0, st>>>(v.cells, v.coarse, v.hdr, 0);
+    if (n > 0) k_count<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.scenes, v.cells, v.coarse, v.occ,
+                                                             v.point_cell, v.point_rank, 0);
+    k_scan_tiles<<<v.max_tiles, 256, 0, st>>>(v.cells, v.tile_sums, v.hdr);
+    k_scan_add<<<v.max_tiles, 256, 0, st>>>(v.cells, v.tile_sums, v.hdr);
+    if (n > 0) k_fill<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, v.cells, v.point_cell, v.point_rank, v.sorted);
+    CB_CUDA_CHECK("cb_grid_build");
+    return CB_OK;
+}
+
+static int check_common(int m, int nsample, const void *xyz, int n, const void *offset, const void *new_offset, int b)
+{
+    CB_REQUIRE(m >= 0 && n >= 0 && b > 0, CB_EINVAL, "cb_knn: bad sizes m=%d n=%d b=%d", m, n, b);
+    CB_REQUIRE(nsample >= 1 && nsample <= CB_KNN_MAX_NSAMPLE, CB_EINVAL, "cb_knn: nsample=%d outside [1,%d]", nsample,
+               CB_KNN_MAX_NSAMPLE);
+    CB_REQUIRE((xyz || n == 0) && offset && new_offset, CB_EINVAL, "cb_knn: NULL pointer argument");
+    return CB_OK;
+}
+
+extern "C" int cb_grid_build(const float *xyz, int n, const int *offset, int b, int nsample_hint, void *grid,
+                             size_t grid_bytes, void *stream)
+{
+    CB_REQUIRE(n >= 0 && b > 0 && offset && grid && (xyz || n == 0), CB_EINVAL, "cb_grid_build: bad arguments");
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, 0, b, grid, &v);
+    CB_REQUIRE(grid_bytes >= need, CB_EWORKSPACE, "cb_grid_build: workspace %zu < %zu", grid_bytes, need);
+    CB_REQUIRE(((uintptr_t)grid & 255) == 0, CB_EINVAL, "cb_grid_build: workspace not 256-byte aligned");
+    if (nsample_hint < 1) nsample_hint = 16;
+    return cb_grid_build_impl(xyz, n, offset, b, nsample_hint, v, (cudaStream_t)stream);
+}
+
+void cb_knn_replay_launch(int K, int m, const float *xyz, const float *new_xyz, const int *offset,
+                          const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, const CbGridView &v,
+                          cudaStream_t st)
+{
+    const size_t smem = (size_t)K * 8 + CB_REPLAY_THREADS * 4;
+    const int rblocks = K <= 256 ? 148 : (m < 148 * 8 ? (m > 0 ? m : 1) : 148 * 8);
+    k_knn_replay<<<rblocks, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, dist2,
+                                                           sqrt_dist, v.hdr, v.flagged);
+}
+
+void cb_knn_reset_flagged(const CbGridView &v, cudaStream_t st) { k_reset_flagged<<<1, 1, 0, st>>>(v.hdr); }
+
+static int query_impl(int m, int K, const float *xyz, int n, const float *new_xyz, const int *offset,
+                      const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, const CbGridView &v,
+                      cudaStream_t st)
+{
+    if (m == 0) return CB_OK;
+    const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
+    const int blocks = (m + 3) / 4;
+    if (K <= 256) {
+        k_reset_flagged<<<1, 1, 0, st>>>(v.hdr);
+#define CB_LAUNCH_Q(KPL)                                                                                          \
+    k_knn_query<KPL><<<blocks, 128, 0, st>>>(m, K, new_xyz, new_offset, b, self_query, v.scenes, v.cells, v.sorted, \
+                                              idx, dist2, sqrt_dist, v.hdr, v.flagged)
+        if (K <= 32) CB_LAUNCH_Q(1);
+        else if (K <= 64) CB_LAUNCH_Q(2);
+        else if (K <= 128) CB_LAUNCH_Q(4);
+        else CB_LAUNCH_Q(8);
+#undef CB_LAUNCH_Q
+    } else {
+        k_flag_all<<<(m + 255) / 256, 256, 0, st>>>(m, v.hdr, v.flagged);
+    }
+    cb_knn_replay_launch(K, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, sqrt_dist, v, st);
+    CB_CUDA_CHECK("cb_knn_query");
+    return CB_OK;
+}
+
+extern "C" int cb_knn_query_grid(int m, int nsample, const float *xyz, int n, const float *new_xyz, const int *offset,
+                                 const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, void *grid,
+                                 size_t grid_bytes, void *stream)
+{
+    int rc = check_common(m, nsample, xyz, n, offset, new_offset, b);
+    if (rc) return rc;
+    CB_REQUIRE(grid && (idx || m == 0) && (dist2 || m == 0), CB_EINVAL, "cb_knn_query_grid: NULL pointer argument");
+    if (!new_xyz) new_xyz = xyz;
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, m, b, grid, &v);
+    CB_REQUIRE(grid_bytes >= need, CB_EWORKSPACE, "cb_knn_query_grid: workspace %zu < %zu", grid_bytes, need);
+    return query_impl(m, nsample, xyz, n, new_xyz, offset, new_offset, b, idx, dist2, sqrt_dist, v, (cudaStream_t)stream);
+}
+
+extern "C" int cb_knn_query(int m, int nsample, const float *xyz, int n, const float *new_xyz, const int *offset,
+                            const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, void *workspace,
+                            size_t workspace_bytes, void *stream)
+{
+    int rc = check_common(m, nsample, xyz, n, offset, new_offset, b);
+    if (rc) return rc;
+    CB_REQUIRE(workspace && (idx || m == 0) && (dist2 || m == 0), CB_EINVAL, "cb_knn_query: NULL pointer argument");
+    CB_REQUIRE(((uintptr_t)workspace & 255) == 0, CB_EINVAL, "cb_knn_query: workspace not 256-byte aligned");
+    if (!new_xyz) new_xyz = xyz;
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, m, b, workspace, &v);
+    CB_REQUIRE(workspace_bytes >= need, CB_EWORKSPACE, "cb_knn_query: workspace %zu < %zu", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nsample <= 256) {
+        rc = cb_grid_build_impl(xyz, n, offset, b, nsample, v, st);
+        if (rc) return rc;
+    } else {
+        k_bbox_init<<<1, 128, 0, st>>>(v.bbox, v.occ, 1, v.hdr, n);   // header only; brute force needs no grid
+    }
+    return query_impl(m, nsample, xyz, n, new_xyz, offset, new_offset, b, idx, dist2, sqrt_dist, v, st);
+}

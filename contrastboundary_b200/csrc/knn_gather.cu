@@ -1,0 +1,200 @@
+// knn_gather.cu — a1+a3 fused: grid KNN + neighbour-feature gather (the north-star kernel).
+// Reference path: knnquery then feat[idx.long()] (pytorch/lib/pointops/functions/pointops.py:88-94).
+//
+// One persistent warp per query stream: ring-search the K nearest (knn.cuh), then move the K
+// feature rows with the TMA engine — each lane that holds a neighbour index issues one
+// cp.async.bulk global->shared for its C-wide row (rows land back to back in a per-warp staging
+// slab), the warp waits on an mbarrier, and ONE cp.async.bulk shared->global writes the slab to
+// grouped[q, k0:k0+R, :], which is contiguous.  No feature byte passes through registers; the LSU
+// is left to the search.  The slab is reused only after cp.async.bulk.wait_group.read, which the
+// warp issues after the NEXT query's search, so stores drain under the search.
+//
+// Algorithmic HBM bytes per call: 12 n + 4 n c + 8 m K + 4 m K c  (SURVEY.md §8(d)).
+#include "knn.cuh"
+
+#define KG_WARPS 4
+#define KG_SLAB_BYTES 16384
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// rows per slab chunk: power of two <= 32 with R * row_bytes <= KG_SLAB_BYTES
+static int kg_rows_per_chunk(int c)
+{
+    int r = 32;
+    while (r > 1 && (size_t)r * c * 4 > KG_SLAB_BYTES) r >>= 1;
+    return r;
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int c, int R, const float *__restrict__ new_xyz,
+                                                              const float *__restrict__ feat,
+                                                              const int *__restrict__ new_offset, int b, int self_query,
+                                                              const CbScene *__restrict__ scenes,
+                                                              const int *__restrict__ cells,
+                                                              const float4 *__restrict__ sorted, int *__restrict__ idx,
+                                                              float *__restrict__ dist2, float *__restrict__ grouped,
+                                                              CbGridHeader *hdr, int *flagged)
+{
+    extern __shared__ __align__(128) unsigned char kg_smem[];
+    __shared__ CbWarpScratch scratch[KG_WARPS];
+    __shared__ __align__(8) unsigned long long bars[KG_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *slab = kg_smem + (size_t)wib * KG_SLAB_BYTES;
+    const unsigned slab_s = smem_u32(slab), bar_s = smem_u32(&bars[wib]);
+    if (lane == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned parity = 0;
+    const unsigned row_bytes = (unsigned)c * 4u;
+    const int total_warps = gridDim.x * KG_WARPS;
+    for (int w = blockIdx.x * KG_WARPS + wib; w < m; w += total_warps) {
+        int q = w;
+        float qx, qy, qz;
+        if (self_query) {
+            const float4 p = __ldg(sorted + w);
+            q = __float_as_int(p.w); qx = p.x; qy = p.y; qz = p.z;
+        } else {
+            qx = __ldg(new_xyz + 3 * q); qy = __ldg(new_xyz + 3 * q + 1); qz = __ldg(new_xyz + 3 * q + 2);
+        }
+        const int s = cb_scene_of(q, new_offset, b);
+        const CbScene sc = scenes[s];
+        CbTopK<KPL> tk;
+        tk.init(K, lane, sc.start);
+        bool ok = cb_grid_search<KPL>(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+        if (ok && tk.has_tie()) ok = false;
+        if (!ok) {   // exact replay + re-gather happen in follow-up kernels
+            if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < KPL; j++) {
+            const int e = j * 32 + lane;
+            if (e < K) {
+                idx[(size_t)q * K + e] = tk.i[j];
+                dist2[(size_t)q * K + e] = tk.d[j];
+            }
+        }
+        // gather: chunks of R rows; entry e of the chunk starting at e0 lives in lane (e & 31), reg (e >> 5)
+        for (int e0 = 0; e0 < K; e0 += R) {
+            const int rows = min(R, K - e0);
+            if (lane == 0) {
+                bulk_wait_read();                      // slab free (previous store has read it)
+                mbar_expect_tx(bar_s, (unsigned)rows * row_bytes);
+            }
+            __syncwarp();
+            const int j = e0 >> 5;
+            int my = 0;
+#pragma unroll
+            for (int jj = 0; jj < KPL; jj++)
+                if (jj == j) my = tk.i[jj];
+            const int rel = lane - (e0 & 31);
+            if (rel >= 0 && rel < rows)
+                bulk_g2s(slab_s + (unsigned)rel * row_bytes, feat + (size_t)my * c, row_bytes, bar_s);
+            mbar_wait(bar_s, parity);
+            parity ^= 1u;
+            if (lane == 0) bulk_s2g(grouped + ((size_t)q * K + e0) * c, slab_s, (unsigned)rows * row_bytes);
+            __syncwarp();
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+// generic gather of the rows of flagged queries (after the exact replay rewrote their idx)
+__global__ void k_regather_flagged(int K, int c, const float *__restrict__ feat, const int *__restrict__ idx,
+                                   float *__restrict__ grouped, const CbGridHeader *hdr, const int *__restrict__ flagged)
+{
+    const int count = hdr->flagged_count;
+    for (int f = blockIdx.x; f < count; f += gridDim.x) {
+        const int q = flagged[f];
+        for (int e = threadIdx.x; e < K * c; e += blockDim.x) {
+            const int k = e / c, ci = e - k * c;
+            grouped[((size_t)q * K + k) * c + ci] = __ldg(feat + (size_t)idx[(size_t)q * K + k] * c + ci);
+        }
+    }
+}
+
+extern "C" int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz, const float *feat,
+                             const int *offset, const int *new_offset, int b, int *idx, float *dist2, float *grouped,
+                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    CB_REQUIRE(m >= 0 && n >= 0 && b > 0 && c > 0, CB_EINVAL, "cb_knn_gather: bad sizes");
+    CB_REQUIRE(nsample >= 1 && nsample <= CB_KNN_MAX_NSAMPLE, CB_EINVAL, "cb_knn_gather: nsample=%d", nsample);
+    CB_REQUIRE((xyz || n == 0) && feat && offset && new_offset && workspace && idx && dist2 && grouped, CB_EINVAL,
+               "cb_knn_gather: NULL pointer");
+    CB_REQUIRE(((uintptr_t)workspace & 255) == 0, CB_EINVAL, "cb_knn_gather: workspace not 256-byte aligned");
+    if (!new_xyz) new_xyz = xyz;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tma_ok = (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 &&
+                        (size_t)c * 4 <= KG_SLAB_BYTES;
+    if (!tma_ok) {   // unfused composition with identical results
+        int rc = cb_knn_query(m, nsample, xyz, n, new_xyz, offset, new_offset, b, idx, dist2, 0, workspace,
+                              workspace_bytes, stream);
+        if (rc) return rc;
+        return cb_grouping_forward(m, nsample, c, feat, idx, grouped, stream);
+    }
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, m, b, workspace, &v);
+    CB_REQUIRE(workspace_bytes >= need, CB_EWORKSPACE, "cb_knn_gather: workspace %zu < %zu", workspace_bytes, need);
+    int rc = cb_grid_build_impl(xyz, n, offset, b, nsample, v, st);
+    if (rc) return rc;
+    if (m == 0) return CB_OK;
+    cb_knn_reset_flagged(v, st);
+    const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
+    const int R = kg_rows_per_chunk(c);
+    const size_t smem = (size_t)KG_WARPS * KG_SLAB_BYTES;
+    int blocks = 148 * 3;
+    if (blocks > (m + KG_WARPS - 1) / KG_WARPS) blocks = (m + KG_WARPS - 1) / KG_WARPS;
+#define KG_LAUNCH(KPL)                                                                                              \
+    do {                                                                                                            \
+        cudaFuncSetAttribute(k_knn_gather<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        k_knn_gather<KPL><<<blocks, KG_WARPS * 32, smem, st>>>(m, nsample, c, R, new_xyz, feat, new_offset, b,       \
+                                                               self_query, v.scenes, v.cells, v.sorted, idx, dist2, \
+                                                               grouped, v.hdr, v.flagged);                          \
+    } while (0)
+    if (nsample <= 32) KG_LAUNCH(1);
+    else if (nsample <= 64) KG_LAUNCH(2);
+    else if (nsample <= 128) KG_LAUNCH(4);
+    else KG_LAUNCH(8);
+#undef KG_LAUNCH
+    cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
+    k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
+    CB_CUDA_CHECK("cb_knn_gather");
+    return CB_OK;
+}

@@ -1,0 +1,328 @@
+"""Drop-in replacement for the reference's operator API
+`pytorch/lib/pointops/functions/pointops.py` (LiyaoTang/contrastBoundary): same names, positional
+signatures, dtypes (int32 indices, fp32) and return values, backed by libcbops.so (sm_100a CUDA
+behind the C ABI in include/cbops.h).  Usage in the reference's model code:
+
+    from contrastboundary_b200 import pointops          # instead of lib.pointops.functions
+
+Differences from the reference that are NOT observable in results:
+  * knnquery is a uniform-grid search (exact; bit-identical idx/dist to the brute-force heap kernel);
+  * all launches go to torch's CURRENT stream (the reference uses the legacy default stream);
+  * a small LRU cache returns the same (idx, dist) when the same (xyz, new_xyz, offsets, K) tensors
+    are queried again un-modified (the reference model repeats every search 2-3x per layer,
+    blocks.py:34-35); disable with `pointops.set_knn_cache(0)` or CB_KNN_CACHE=0.
+"""
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------------------------
+# furthestsampling  (reference pointops.py:10-27)
+# ------------------------------------------------------------------------------------------------
+def _max_scene_len(offset_cpu):
+    prev, n_max = 0, 0
+    for v in offset_cpu:
+        n_max = max(n_max, v - prev)
+        prev = v
+    return n_max
+
+
+class FurthestSampling(Function):
+    @staticmethod
+    def forward(ctx, xyz, offset, new_offset):
+        """
+        input: xyz: (n, 3), offset: (b), new_offset: (b)
+        output: idx: (m)
+        """
+        assert xyz.is_contiguous()
+        L.require_cuda(xyz, offset, new_offset)
+        n, b = xyz.shape[0], offset.shape[0]
+        off_cpu = offset.tolist()                       # the reference syncs here too (pointops.py:18-21)
+        m = int(new_offset[b - 1].item())
+        n_max = _max_scene_len(off_cpu)
+        idx = torch.zeros(m, dtype=torch.int32, device=xyz.device)
+        tmp = torch.full((n,), 1e10, dtype=torch.float32, device=xyz.device)
+        L.call("cb_furthest_sampling", b, n_max, xyz, offset.int(), new_offset.int(), tmp, idx, L.stream())
+        return idx
+
+
+def furthestsampling(xyz, offset, new_offset):
+    return FurthestSampling.apply(xyz, offset, new_offset)
+
+
+def furthestsampling_known(xyz, offset, new_offset, n_max, m):
+    """Same op when the host already knows n_max and m: no device->host sync."""
+    idx = torch.empty(m, dtype=torch.int32, device=xyz.device)
+    tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
+    L.call("cb_furthest_sampling", offset.shape[0], int(n_max), xyz, offset, new_offset, tmp, idx, L.stream())
+    return idx
+
+
+# ------------------------------------------------------------------------------------------------
+# knnquery  (reference pointops.py:30-45)
+# ------------------------------------------------------------------------------------------------
+_knn_cache = OrderedDict()
+_knn_cache_size = int(os.environ.get("CB_KNN_CACHE", "8"))
+
+
+def set_knn_cache(size):
+    global _knn_cache_size
+    _knn_cache_size = int(size)
+    _knn_cache.clear()
+
+
+def _tkey(t):
+    return (t.data_ptr(), t._version, tuple(t.shape), t.device.index)
+
+
+def knn_raw(nsample, xyz, new_xyz, offset, new_offset, sqrt_dist=True):
+    """(idx int32 (m,k), dist f32 (m,k)) straight from cb_knn_query (no cache)."""
+    L.require_cuda(xyz, new_xyz, offset, new_offset)
+    n, m, b = xyz.shape[0], new_xyz.shape[0], offset.shape[0]
+    dev = xyz.device
+    idx = torch.empty((m, nsample), dtype=torch.int32, device=dev)
+    dist = torch.empty((m, nsample), dtype=torch.float32, device=dev)
+    nbytes = L.lib().cb_knn_workspace_bytes(n, m, b)
+    ws = L.workspace(nbytes, dev, "knn")
+    f = L.lib().cb_knn_query
+    rc = f(C.c_int(m), C.c_int(int(nsample)), L.ptr(xyz), C.c_int(n), L.ptr(new_xyz), L.ptr(offset), L.ptr(new_offset),
+           C.c_int(b), L.ptr(idx), L.ptr(dist), C.c_int(1 if sqrt_dist else 0), L.ptr(ws), C.c_size_t(ws.numel()),
+           L.stream())
+    L.check(rc, "cb_knn_query")
+    return idx, dist
+
+
+class KNNQuery(Function):
+    @staticmethod
+    def forward(ctx, nsample, xyz, new_xyz, offset, new_offset):
+        """
+        input: xyz: (n, 3), new_xyz: (m, 3), offset: (b), new_offset: (b)
+        output: idx: (m, nsample), dist: (m, nsample)   [dist = sqrt(dist2), reference pointops.py:43]
+        """
+        if new_xyz is None:
+            new_xyz = xyz
+        assert xyz.is_contiguous() and new_xyz.is_contiguous()
+        nsample = int(nsample)
+        if offset.dtype != torch.int32:
+            offset = offset.int()
+        if new_offset.dtype != torch.int32:
+            new_offset = new_offset.int()
+        if _knn_cache_size > 0:
+            key = (nsample, _tkey(xyz), _tkey(new_xyz), _tkey(offset), _tkey(new_offset))
+            hit = _knn_cache.get(key)
+            if hit is not None:
+                _knn_cache.move_to_end(key)
+                idx, dist = hit[0].clone(), hit[1].clone()
+                ctx.mark_non_differentiable(idx, dist)
+                return idx, dist
+        idx, dist = knn_raw(nsample, xyz, new_xyz, offset, new_offset, True)
+        if _knn_cache_size > 0:
+            # hold the key tensors so their storage (and data_ptr) cannot be recycled while cached
+            _knn_cache[key] = (idx.clone(), dist.clone(), xyz, new_xyz, offset, new_offset)
+            while len(_knn_cache) > _knn_cache_size:
+                _knn_cache.popitem(last=False)
+        ctx.mark_non_differentiable(idx, dist)
+        return idx, dist
+
+
+def knnquery(nsample, xyz, new_xyz, offset, new_offset):
+    return KNNQuery.apply(nsample, xyz, new_xyz, offset, new_offset)
+
+
+# ------------------------------------------------------------------------------------------------
+# grouping  (reference pointops.py:48-76)
+# ------------------------------------------------------------------------------------------------
+class Grouping(Function):
+    @staticmethod
+    def forward(ctx, input, idx):
+        """
+        input: input: (n, c), idx : (m, nsample)
+        output: (m, nsample, c)
+        """
+        assert input.is_contiguous() and idx.is_contiguous()
+        L.require_cuda(input, idx)
+        m, nsample, n, c = idx.shape[0], idx.shape[1], input.shape[0], input.shape[1]
+        output = torch.empty((m, nsample, c), dtype=torch.float32, device=input.device)
+        L.call("cb_grouping_forward", m, nsample, c, input, idx, output, L.stream())
+        ctx.n = n
+        ctx.save_for_backward(idx)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        n = ctx.n
+        idx, = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        m, nsample, c = grad_output.shape
+        grad_input = torch.zeros((n, c), dtype=torch.float32, device=grad_output.device)
+        L.call("cb_grouping_backward", m, nsample, c, grad_output, idx, grad_input, L.stream())
+        return grad_input, None
+
+
+grouping = Grouping.apply
+
+
+def queryandgroup(nsample, xyz, new_xyz, feat, idx, offset, new_offset, use_xyz=True):
+    """
+    input: xyz: (n, 3), new_xyz: (m, 3), feat: (n, c), idx: (m, nsample), offset: (b), new_offset: (b)
+    output: new_feat: (m, nsample, c+3) (or (m, nsample, c) if not use_xyz)   [reference pointops.py:79-100]
+    """
+    if new_xyz is None:
+        new_xyz = xyz
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
+    if idx is None:
+        idx, _ = knnquery(nsample, xyz, new_xyz, offset, new_offset)  # (m, nsample)
+    grouped_feat = grouping(feat, idx)  # (m, nsample, c)
+    if use_xyz:
+        grouped_xyz = grouping(xyz, idx) - new_xyz.unsqueeze(1)  # (m, nsample, 3)
+        return torch.cat((grouped_xyz, grouped_feat), -1)  # (m, nsample, 3+c)
+    return grouped_feat
+
+
+# ------------------------------------------------------------------------------------------------
+# subtraction  (reference pointops.py:103-130)
+# ------------------------------------------------------------------------------------------------
+class Subtraction(Function):
+    @staticmethod
+    def forward(ctx, input1, input2, idx):
+        """
+        input: input1: (n, c), input2: (n, c), idx: (n, nsample)
+        output:  (n, nsample, c)
+        """
+        assert input1.is_contiguous() and input2.is_contiguous()
+        L.require_cuda(input1, input2, idx)
+        n, c = input1.shape
+        nsample = idx.shape[-1]
+        output = torch.empty((n, nsample, c), dtype=torch.float32, device=input1.device)
+        L.call("cb_subtraction_forward", n, nsample, c, input1, input2, idx.contiguous(), output, L.stream())
+        ctx.save_for_backward(idx)
+        ctx.n2 = input2.shape[0]
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        idx, = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        n, nsample, c = grad_output.shape
+        grad_input1 = torch.zeros((n, c), dtype=torch.float32, device=grad_output.device)
+        grad_input2 = torch.zeros((ctx.n2, c), dtype=torch.float32, device=grad_output.device)
+        L.call("cb_subtraction_backward", n, nsample, c, idx.contiguous(), grad_output, grad_input1, grad_input2, L.stream())
+        return grad_input1, grad_input2, None
+
+
+subtraction = Subtraction.apply
+
+
+# ------------------------------------------------------------------------------------------------
+# aggregation  (reference pointops.py:133-161)
+# ------------------------------------------------------------------------------------------------
+class Aggregation(Function):
+    @staticmethod
+    def forward(ctx, input, position, weight, idx):
+        """
+        input: input: (n, c), position: (n, nsample, c), weight : (n, nsample, c'), idx: (n, nsample)
+        output: (n, c)
+        """
+        assert input.is_contiguous() and position.is_contiguous() and weight.is_contiguous()
+        L.require_cuda(input, position, weight, idx)
+        n, nsample, c = position.shape
+        w_c = weight.shape[-1]
+        output = torch.empty((n, c), dtype=torch.float32, device=input.device)
+        L.call("cb_aggregation_forward", n, nsample, c, w_c, input, position, weight, idx.contiguous(), output, L.stream())
+        ctx.save_for_backward(input, position, weight, idx)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, position, weight, idx = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        n, nsample, c = position.shape
+        w_c = weight.shape[-1]
+        grad_input = torch.zeros_like(input)
+        grad_position = torch.empty_like(position)
+        grad_weight = torch.zeros_like(weight)
+        L.call("cb_aggregation_backward", n, nsample, c, w_c, input, position, weight, idx.contiguous(), grad_output,
+               grad_input, grad_position, grad_weight, L.stream())
+        return grad_input, grad_position, grad_weight, None
+
+
+aggregation = Aggregation.apply
+
+
+# ------------------------------------------------------------------------------------------------
+# interpolation  (reference pointops.py:164-214)
+# ------------------------------------------------------------------------------------------------
+def _interp_weights(xyz, new_xyz, offset, new_offset, k):
+    idx, dist = knnquery(k, xyz, new_xyz, offset, new_offset)  # (n, k), (n, k)
+    dist_recip = 1.0 / (dist + 1e-8)
+    norm = torch.sum(dist_recip, dim=1, keepdim=True)
+    weight = dist_recip / norm
+    return idx, weight
+
+
+class _InterpolationFn(Function):
+    @staticmethod
+    def forward(ctx, input, idx, weight):
+        n, k = idx.shape
+        m, c = input.shape
+        output = torch.empty((n, c), dtype=torch.float32, device=input.device)
+        L.call("cb_interpolation_forward", n, c, k, input, idx, weight, output, L.stream())
+        ctx.m = m
+        ctx.save_for_backward(idx, weight)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        idx, weight = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        n, c = grad_output.shape
+        k = idx.shape[1]
+        grad_input = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
+        L.call("cb_interpolation_backward", n, c, k, grad_output, idx, weight, grad_input, L.stream())
+        return grad_input, None, None
+
+
+def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
+    """
+    input: xyz: (m, 3), new_xyz: (n, 3), feat: (m, c), offset: (b), new_offset: (b)
+    output: (n, c)
+    """
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
+    L.require_cuda(xyz, new_xyz, feat)
+    idx, weight = _interp_weights(xyz, new_xyz, offset, new_offset, k)
+    return _InterpolationFn.apply(feat, idx.contiguous(), weight.contiguous())
+
+
+class Interpolation(Function):
+    """API twin of the reference's `Interpolation` (pointops.py:181-214)."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, input, offset, new_offset, k=3):
+        assert xyz.is_contiguous() and new_xyz.is_contiguous() and input.is_contiguous()
+        L.require_cuda(xyz, new_xyz, input)
+        idx, weight = _interp_weights(xyz, new_xyz, offset, new_offset, k)
+        n, c, m = new_xyz.shape[0], input.shape[1], input.shape[0]
+        output = torch.empty((n, c), dtype=torch.float32, device=input.device)
+        L.call("cb_interpolation_forward", n, c, k, input, idx, weight.contiguous(), output, L.stream())
+        ctx.m, ctx.k = m, k
+        ctx.save_for_backward(idx, weight)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        m, k = ctx.m, ctx.k
+        idx, weight = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        n, c = grad_output.shape
+        grad_input = torch.zeros((m, c), dtype=torch.float32, device=grad_output.device)
+        L.call("cb_interpolation_backward", n, c, k, grad_output, idx, weight.contiguous(), grad_input, L.stream())
+        return None, None, grad_input, None, None, None
+
+
+interpolation2 = Interpolation.apply

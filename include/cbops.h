@@ -1,0 +1,124 @@
+/*
+ * cbops.h — C ABI of libcbops.so, the B200-native (sm_100a) point-cloud operator stack that drops
+ * in behind the operator API of LiyaoTang/contrastBoundary.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: raw DEVICE pointers, ints, a cudaStream_t passed as `void *stream`
+ *     (NULL = legacy default stream).  No torch / ATen types.
+ *   - the CALLER allocates every output and every workspace (the reference does the same:
+ *     pytorch/lib/pointops/functions/pointops.py:21-22,40-41,57).  The library never allocates
+ *     device memory and never synchronises the stream.
+ *   - return value: 0 on success, negative CB_E* on failure; cb_last_error_string() gives detail.
+ *     (The reference launchers return void and never check cudaGetLastError.)
+ *   - `offset` / `new_offset` are int32 CUMULATIVE scene ends as in the reference
+ *     (pytorch/util/s3dis.py:117-126); `*_batches` / `*_lens` (TF-side ops) are per-scene LENGTHS
+ *     (tensorflow/ops/tf_custom_ops/tf_neighbors/tf_batch_neighbors.cpp:8-14).
+ *   - floats are fp32, indices int32, row-major contiguous.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference
+ * repo root).  INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef CBOPS_H_
+#define CBOPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK 0
+#define CB_EINVAL (-1)     /* bad argument (NULL pointer, negative size, unsupported K, ...) */
+#define CB_EWORKSPACE (-2) /* workspace too small */
+#define CB_ECUDA (-3)      /* a CUDA launch / runtime call failed */
+#define CB_EUNSUPPORTED (-4)
+
+#define CB_KNN_MAX_NSAMPLE 1024 /* same ceiling as the reference's best_dist[1024] (knnquery_cuda_kernel.cu:89-90) */
+
+int cb_version(void);
+const char *cb_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1  K-nearest-neighbour query            replaces knnquery_cuda_launcher
+ *     pytorch/lib/pointops/src/knnquery/knnquery_cuda_kernel.h:10-17 (kernel .cu:65-119)
+ *
+ * Uniform-grid search; results are bit-identical to the reference's brute-force heap kernel:
+ * idx (m,nsample) int32, dist2 (m,nsample) f32 = squared distance t=dx*dx; t=fma(dy,dy,t);
+ * t=fma(dz,dz,t) (the reference's SASS), ascending, short scenes padded with (scene_start, 1e10).
+ * Queries whose result depends on the reference's heap mechanics (exact d2 ties) are re-run
+ * through an exact replay of that heap.
+ *   n, b            number of support points / scenes (the reference launcher infers them)
+ *   new_xyz         may equal xyz (self query)
+ *   sqrt_dist       non-zero: write sqrtf(dist2) instead (what pointops.py:43 returns)
+ *   workspace       >= cb_knn_workspace_bytes(n, m, b) bytes, 256-byte aligned
+ * ---------------------------------------------------------------------------------------------- */
+size_t cb_knn_workspace_bytes(int n, int m, int b);
+int cb_knn_query(int m, int nsample, const float *xyz, int n, const float *new_xyz, const int *offset,
+                 const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
+/* Split form: build the search grid of a support set once, query it many times (different
+ * query sets / K).  `grid` is the workspace filled by cb_grid_build; nsample_hint tunes the cell
+ * size (use the K you will query most). */
+int cb_grid_build(const float *xyz, int n, const int *offset, int b, int nsample_hint, void *grid,
+                  size_t grid_bytes, void *stream);
+int cb_knn_query_grid(int m, int nsample, const float *xyz, int n, const float *new_xyz, const int *offset,
+                      const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, void *grid,
+                      size_t grid_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1+a3 fused KNN + neighbour-feature gather (the north-star kernel; reference = knnquery then
+ *     feat[idx.long()] in queryandgroup, pytorch/lib/pointops/functions/pointops.py:79-100)
+ * grouped (m,nsample,c) = feat[idx]; also writes idx and dist2 as cb_knn_query does.
+ * ---------------------------------------------------------------------------------------------- */
+int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz,
+                  const float *feat, const int *offset, const int *new_offset, int b, int *idx, float *dist2,
+                  float *grouped, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a2  farthest point sampling             replaces furthestsampling_cuda_launcher
+ *     pytorch/lib/pointops/src/sampling/sampling_cuda_kernel.h (kernel .cu:14-171)
+ * idx (new_offset[b-1]) int32, bit-identical to the reference including its tie rule
+ * (block of opt_n_threads(n_max) strided threads + lower-slot-wins tree).
+ * n_max = max scene length (host-known, as in the reference launcher); tmp (n) f32 scratch is the
+ * running min-distance buffer the reference also takes — on return it holds the same values.
+ * ---------------------------------------------------------------------------------------------- */
+int cb_furthest_sampling(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
+                         float *tmp, int *idx, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a3  grouping                            replaces grouping_{forward,backward}_cuda_launcher
+ *     pytorch/lib/pointops/src/grouping/grouping_cuda_kernel.h (.cu:5-25)
+ * forward: output(m,nsample,c) = input[idx];  backward: grad_input(n,c) += scatter(grad_output)
+ * (grad_input must be zero-filled by the caller, as pointops.py:72 does).
+ * ---------------------------------------------------------------------------------------------- */
+int cb_grouping_forward(int m, int nsample, int c, const float *input, const int *idx, float *output, void *stream);
+int cb_grouping_backward(int m, int nsample, int c, const float *grad_output, const int *idx, float *grad_input,
+                         void *stream);
+
+/* a4  subtraction   subtraction_{forward,backward}_cuda_launcher (subtraction_cuda_kernel.cu:5-30) */
+int cb_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2, const int *idx,
+                           float *output, void *stream);
+int cb_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output,
+                            float *grad_input1, float *grad_input2, void *stream);
+
+/* a4  aggregation   aggregation_{forward,backward}_cuda_launcher (aggregation_cuda_kernel.h:14-21, .cu:5-39)
+ * output(n,c) = sum_k (input[idx[n,k],c] + position[n,k,c]) * weight[n,k,c % w_c]  (output overwritten). */
+int cb_aggregation_forward(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                           const float *weight, const int *idx, float *output, void *stream);
+int cb_aggregation_backward(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                            const float *weight, const int *idx, const float *grad_output, float *grad_input,
+                            float *grad_position, float *grad_weight, void *stream);
+
+/* a6  interpolation  interpolation_{forward,backward}_cuda_launcher (interpolation_cuda_kernel.cu:5-33)
+ * output(n,c) = sum_i input[idx[n,i],c] * weight[n,i]  (output overwritten). */
+int cb_interpolation_forward(int n, int c, int k, const float *input, const int *idx, const float *weight,
+                             float *output, void *stream);
+int cb_interpolation_backward(int n, int c, int k, const float *grad_output, const int *idx, const float *weight,
+                              float *grad_input, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBOPS_H_ */

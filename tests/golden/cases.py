@@ -1,0 +1,108 @@
+"""Seeded inputs shared by the golden-vector generators and the parity tests."""
+import numpy as np
+
+from contrastboundary_b200 import synthetic as S
+
+
+def cumsum_i32(lens):
+    return np.cumsum(np.asarray(lens)).astype(np.int32)
+
+
+def scene_single():
+    """one 2048-point room"""
+    c, f, l = S.make_scene(2048, 11)
+    return c, cumsum_i32([2048])
+
+
+def scene_multi():
+    """three rooms of unequal length"""
+    lens = [700, 1500, 300]
+    pts = [S.make_scene(n, 20 + i)[0] for i, n in enumerate(lens)]
+    return np.concatenate(pts, 0), cumsum_i32(lens)
+
+
+def tie_lattice():
+    """integer lattice 10^3: every query has exact distance ties"""
+    g = np.stack(np.meshgrid(*[np.arange(10)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(5)
+    g = g[rng.permutation(len(g))]
+    return g, cumsum_i32([600, 400])
+
+
+def tie_duplicates():
+    rng = np.random.default_rng(6)
+    p = rng.random((300, 3)).astype(np.float32)
+    p = np.concatenate([p, p[:150], p[:50]], 0)
+    p = p[rng.permutation(len(p))]
+    return p, cumsum_i32([len(p)])
+
+
+def short_segments():
+    """scenes shorter than K, and a single-point scene"""
+    rng = np.random.default_rng(7)
+    p = rng.random((5 + 1 + 40, 3)).astype(np.float32)
+    return p, cumsum_i32([5, 1, 40])
+
+
+KNN_CASES = {
+    # name: (builder, K list, cross)   cross=True -> queries are every 4th support point of each scene
+    "single": (scene_single, [1, 3, 8, 16, 36], False),
+    "multi": (scene_multi, [16, 64], False),
+    "multi_cross": (scene_multi, [3, 16, 256], True),
+    "lattice": (tie_lattice, [8, 27], False),
+    "dups": (tie_duplicates, [4, 16], False),
+    "short": (short_segments, [8, 16], False),
+}
+
+
+def cross_queries(xyz, offset):
+    qs, lens, prev = [], [], 0
+    for e in offset:
+        sel = np.arange(prev, e, 4)
+        qs.append(xyz[sel])
+        lens.append(len(sel))
+        prev = e
+    return np.concatenate(qs, 0), cumsum_i32(lens)
+
+
+FPS_CASES = {
+    # name: (builder, stride)
+    "single": (scene_single, 4),
+    "multi": (scene_multi, 4),
+    "lattice": (tie_lattice, 4),
+    "dups": (tie_duplicates, 3),
+    "short": (short_segments, 2),
+}
+
+
+def fps_new_offset(offset, stride):
+    lens = np.diff(np.concatenate([[0], offset]))
+    return np.cumsum(lens // stride).astype(np.int32)
+
+
+def ops_inputs():
+    """random inputs for the K3-K6 stand-alone operators"""
+    rng = np.random.default_rng(3)
+    n, k, c, wc = 500, 8, 16, 4
+    inp = rng.standard_normal((n, c)).astype(np.float32)
+    inp2 = rng.standard_normal((n, c)).astype(np.float32)
+    pos = rng.standard_normal((n, k, c)).astype(np.float32)
+    w = rng.standard_normal((n, k, wc)).astype(np.float32)
+    idx = rng.integers(0, n, (n, k)).astype(np.int32)
+    go_nkc = rng.standard_normal((n, k, c)).astype(np.float32)
+    go_nc = rng.standard_normal((n, c)).astype(np.float32)
+    wk = rng.random((n, 3)).astype(np.float32)
+    return n, k, c, wc, inp, inp2, pos, w, idx, go_nkc, go_nc, wk
+
+
+# ---- TF-side (CPU reference) cases -------------------------------------------------------------
+def tf_config1():
+    """BASELINE config 1: one 4096-point scene, grid 0.08 then radius 0.1 on the subsample"""
+    c, f, l = S.make_scene(4096, 1000)
+    return c, f, l.astype(np.int32)
+
+
+def tf_sphere():
+    """a ~15000-point input 'sphere' (config 3 shape) and its 5 pyramid levels"""
+    c, f, l = S.make_scene(15000, 3000)
+    return c, f, l.astype(np.int32)

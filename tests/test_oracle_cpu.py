@@ -1,0 +1,175 @@
+"""CPU suite (-m "not gpu"): the oracle restatements against the reference-generated golden
+vectors, oracle self-consistency, and the C-ABI export check.  No GPU compute here."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import cases  # noqa: E402
+import oracle  # noqa: E402
+
+
+def rows_equal_mod_ties(a, b, queries, supports):
+    """radius-neighbour rows equal up to the order inside groups of EXACTLY equal fp32 distance
+    (the reference sorts with std::sort on distance only, nanoflann.hpp:1286-1287: tie order is
+    unspecified; e.g. a 2-point barycentre is equidistant from both points)."""
+    if a.shape != b.shape:
+        return False
+    if np.array_equal(a, b):
+        return True
+    if not np.array_equal(np.sort(a, 1), np.sort(b, 1)):
+        return False
+    sup = np.concatenate([supports, np.full((1, 3), 1e6, np.float32)], 0)   # shadow row
+
+    def dist(idx, q):
+        d = np.zeros(idx.shape, np.float32)
+        for t in range(3):
+            dd = (q[:, None, t] - sup[idx, t]).astype(np.float32)
+            d = (d + dd * dd).astype(np.float32)
+        return d
+    rows = np.unique(np.argwhere(a != b)[:, 0])
+    return np.array_equal(dist(a[rows], queries[rows]), dist(b[rows], queries[rows]))
+
+
+@pytest.fixture(scope="module")
+def tf_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "tfops_ref_cpu.npz"))
+
+
+def test_grid_subsampling_config1_matches_reference(tf_golden):
+    p, f, l = cases.tf_config1()
+    sp, sf, sl = oracle.grid_subsampling(p, f, l, 0.08)
+    assert np.array_equal(sp, tf_golden["c1/sub_points"])          # bit-exact, same (unordered_map) order
+    assert np.array_equal(sf, tf_golden["c1/sub_features"])
+    assert np.array_equal(sl, tf_golden["c1/sub_labels"])
+    lens = np.array([sp.shape[0]], np.int32)
+    nb = oracle.batch_neighbors(sp, sp, lens, lens, 0.1)
+    assert np.array_equal(nb, tf_golden["c1/neighbors"].astype(np.int32))
+    assert (nb[:, 0] == np.arange(sp.shape[0])).all()               # self first (distance 0)
+
+
+def test_pyramid_matches_reference(tf_golden):
+    p2 = cases.tf_config1()[0][:3000]
+    pts = np.concatenate([cases.tf_sphere()[0], p2], 0)
+    lens = np.array([15000, 3000], np.int32)
+    dl, r = 0.08, 0.1
+    for lvl in range(3):
+        g = lambda k: tf_golden[f"pyr/{lvl}/{k}"]  # noqa: E731
+        pool_pts, pool_lens = oracle.batch_grid_subsampling(pts, lens, dl)
+        assert np.array_equal(pool_pts, g("pool_pts")) and np.array_equal(pool_lens, g("pool_lens"))
+        if lvl < 2:   # brute-force oracle: keep the big level to one check
+            assert rows_equal_mod_ties(oracle.batch_neighbors(pool_pts, pts, pool_lens, lens, r), g("pools").astype(np.int32), pool_pts, pts)
+        if lvl > 0:
+            assert rows_equal_mod_ties(oracle.batch_neighbors(pts, pts, lens, lens, r), g("neighbors").astype(np.int32), pts, pts)
+            assert rows_equal_mod_ties(oracle.batch_neighbors(pts, pool_pts, lens, pool_lens, 2 * r), g("upsamples").astype(np.int32), pts, pool_pts)
+        pts, lens, dl, r = pool_pts, pool_lens, dl * 2, r * 2
+
+
+@pytest.mark.skipif(not oracle.have_ref_cpu(), reason="oracle/_ref not built (no /root/reference)")
+def test_restatement_vs_compiled_reference_random():
+    rng = np.random.default_rng(0)
+    for trial in range(3):
+        lens = rng.integers(50, 400, 3).astype(np.int32)
+        pts = (rng.random((int(lens.sum()), 3)) * rng.uniform(0.5, 2.0)).astype(np.float32)
+        dl = float(rng.uniform(0.05, 0.2))
+        a = oracle.batch_grid_subsampling(pts, lens, dl)
+        b = oracle.ref_batch_grid_subsampling(pts, lens, dl)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        na = oracle.batch_neighbors(a[0], pts, a[1], lens, 2 * dl)
+        nb = oracle.ref_batch_neighbors(a[0], pts, a[1], lens, 2 * dl)
+        assert rows_equal_mod_ties(na, nb, a[0], pts)
+        feats = rng.random((int(lens[0]), 4)).astype(np.float32)
+        labs = rng.integers(0, 5, (int(lens[0]), 2)).astype(np.int32)
+        ga = oracle.grid_subsampling(pts[:lens[0]], feats, labs, dl)
+        gb = oracle.ref_grid_subsampling(pts[:lens[0]], feats, labs, dl)
+        assert all(np.array_equal(x, y) for x, y in zip(ga, gb))
+
+
+def _naive_knn(xyz, q, off, qoff, k):
+    idx = np.zeros((q.shape[0], k), np.int64)
+    prev, qprev = 0, 0
+    for e, qe in zip(off, qoff):
+        d = ((q[qprev:qe, None, :].astype(np.float64) - xyz[None, prev:e, :].astype(np.float64)) ** 2).sum(-1)
+        idx[qprev:qe] = np.argsort(d, 1, kind="stable")[:, :k] + prev
+        prev, qprev = e, qe
+    return idx
+
+
+def test_oracle_knn_matches_naive_on_tie_free_data():
+    xyz, off = cases.scene_multi()
+    idx, d2 = oracle.knnquery(8, xyz, None, off, off)
+    assert (np.diff(d2, axis=1) >= 0).all()
+    assert (idx[:, 0] == np.arange(len(xyz))).all()                 # self at column 0
+    naive = _naive_knn(xyz, xyz, off, off, 8)
+    notie = ~(np.diff(d2, axis=1) == 0).any(1)
+    assert notie.mean() > 0.99
+    assert np.array_equal(idx[notie], naive[notie])
+
+
+def test_oracle_knn_short_segment_padding():
+    xyz, off = cases.short_segments()
+    idx, d2 = oracle.knnquery(8, xyz, None, off, off)
+    assert (idx[:5, 5:] == 0).all() and (d2[:5, 5:] == np.float32(1e10)).all()   # (start, 1e10) padding
+    assert (idx[5] == 5).all() and d2[5, 0] == 0 and (d2[5, 1:] == np.float32(1e10)).all()
+
+
+def test_oracle_fps_basic():
+    xyz, off = cases.scene_multi()
+    noff = cases.fps_new_offset(off, 4)
+    idx = oracle.furthestsampling(xyz, off, noff)
+    assert len(idx) == noff[-1] and idx[0] == 0
+    prev, nprev = 0, 0
+    for e, ne in zip(off, noff):
+        seg = idx[nprev:ne]
+        assert seg.min() >= prev and seg.max() < e and len(set(seg.tolist())) == len(seg)
+        assert seg[0] == prev
+        # second pick is the farthest from the first
+        d = ((xyz[prev:e] - xyz[prev]) ** 2).sum(1)
+        assert seg[1] == prev + int(np.argmax(d))
+        prev, nprev = e, ne
+
+
+def test_oracle_gather_ops_consistency():
+    n, k, c, wc, inp, inp2, pos, w, idx, go_nkc, go_nc, wk = cases.ops_inputs()
+    g = oracle.grouping_forward(inp, idx)
+    assert np.array_equal(g, inp[idx])
+    assert np.array_equal(oracle.subtraction_forward(inp, inp2, idx), inp[:, None] - inp2[idx])
+    agg = oracle.aggregation_forward(inp, pos, w, idx)
+    ref = ((inp[idx] + pos).reshape(n, k, c // wc, wc) * w[:, :, None, :]).sum(1).reshape(n, c)
+    assert np.allclose(agg, ref, rtol=1e-5, atol=1e-5)
+    gi = oracle.grouping_backward(go_nkc, idx, n)
+    chk = np.zeros((n, c), np.float64)
+    np.add.at(chk, idx.reshape(-1), go_nkc.reshape(-1, c))
+    assert np.allclose(gi, chk, rtol=1e-5, atol=1e-5)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cbops.h")).read()
+    names = sorted(set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    lib_path = os.path.join(ROOT, "contrastboundary_b200", "libcbops.so")
+    if not os.path.exists(lib_path):
+        from contrastboundary_b200 import build
+        build.build()
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.cb_version.restype = ctypes.c_int
+    assert lib.cb_version() >= 100
+    lib.cb_knn_workspace_bytes.restype = ctypes.c_size_t
+    lib.cb_knn_workspace_bytes.argtypes = [ctypes.c_int] * 3
+    assert lib.cb_knn_workspace_bytes(1000, 1000, 2) > 1000 * 16
+
+
+def test_product_has_no_cpu_fallback():
+    import torch
+    from contrastboundary_b200 import pointops, _lib
+    xyz = torch.rand(10, 3)
+    off = torch.tensor([10], dtype=torch.int32)
+    with pytest.raises(_lib.CbopsError):
+        pointops.knnquery(3, xyz, xyz, off, off)
