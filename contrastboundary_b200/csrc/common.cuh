@@ -30,13 +30,14 @@ void cb_set_error(const char *fmt, ...);
 static inline size_t cb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Squared distance exactly as the reference's SASS computes it (nvcc -fmad=true on
-// (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f)):  t = dx*dx; t = fma(dy,dy,t); t = fma(dz,dz,t)
-// (knnquery_cuda_kernel.cu:99, sampling_cuda_kernel.cu:54).
+// (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f)):  t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)
+// (knnquery_cuda_kernel.cu:99, sampling_cuda_kernel.cu:54; order read off the reference's sm_100a SASS
+// and pinned by tests/golden/pointops_ref_gpu.npz).
 __device__ __forceinline__ float cb_sqdist(float ax, float ay, float az, float bx, float by, float bz)
 {
     float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
-    float t = __fmul_rn(dx, dx);
-    t = __fmaf_rn(dy, dy, t);
+    float t = __fmul_rn(dy, dy);
+    t = __fmaf_rn(dx, dx, t);
     t = __fmaf_rn(dz, dz, t);
     return t;
 }

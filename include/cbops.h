@@ -44,7 +44,7 @@ const char *cb_last_error_string(void);
  *     pytorch/lib/pointops/src/knnquery/knnquery_cuda_kernel.h:10-17 (kernel .cu:65-119)
  *
  * Uniform-grid search; results are bit-identical to the reference's brute-force heap kernel:
- * idx (m,nsample) int32, dist2 (m,nsample) f32 = squared distance t=dx*dx; t=fma(dy,dy,t);
+ * idx (m,nsample) int32, dist2 (m,nsample) f32 = squared distance t=dy*dy; t=fma(dx,dx,t);
  * t=fma(dz,dz,t) (the reference's SASS), ascending, short scenes padded with (scene_start, 1e10).
  * Queries whose result depends on the reference's heap mechanics (exact d2 ties) are re-run
  * through an exact replay of that heap.

@@ -14,8 +14,10 @@
  * Every function cites the reference file:line it follows (paths relative to
  * pytorch/lib/pointops/src/).  Arithmetic notes:
  *   - the reference is compiled by nvcc with the default -fmad=true, so
- *     (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f) becomes  t = dx*dx; t = fma(dy,dy,t);
- *     t = fma(dz,dz,t)  (confirmed in SASS).  We spell that out with
+ *     (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f) becomes  t = dy*dy; t = fma(dx,dx,t);
+ *     t = fma(dz,dz,t)  — read off the sm_100a SASS of the reference kernels (FADD dy; FADD dx;
+ *     FMUL dy*dy; FADD dz; FFMA dx,dx; FFMA dz,dz) and confirmed bit-for-bit by the golden vectors
+ *     (SURVEY.md §A.1 guessed dx*dx first; the goldens showed 1-ulp differences).  We spell that out with
  *     fmaf() and compile with -ffp-contract=off so gcc adds no contraction of its own.
  */
 #include <math.h>
@@ -31,8 +33,8 @@
 static inline float sqdist_fmad(float ax, float ay, float az, float bx, float by, float bz)
 {
     float dx = ax - bx, dy = ay - by, dz = az - bz;
-    float t = dx * dx;
-    t = fmaf(dy, dy, t);
+    float t = dy * dy;
+    t = fmaf(dx, dx, t);
     t = fmaf(dz, dz, t);
     return t;
 }

@@ -126,7 +126,15 @@ def test_fps_matches_oracle_and_reference(name):
     assert np.array_equal(idx, oi), f"{name}: {np.flatnonzero(idx != oi)[:5]}"
     gp = os.path.join(ROOT, "tests", "golden", "pointops_ref_gpu.npz")
     if os.path.exists(gp):
-        assert np.array_equal(idx, np.load(gp)[f"fps/{name}/idx"])
+        gold = np.load(gp)
+        assert np.array_equal(idx, gold[f"fps/{name}/idx"])
+        # the running min-distance buffer the reference leaves behind, bit for bit
+        from contrastboundary_b200 import _lib as L
+        tmp = torch.full((len(xyz),), 1e10, dtype=torch.float32, device=DEV)
+        out = torch.zeros(int(noff[-1]), dtype=torch.int32, device=DEV)
+        lens = np.diff(np.concatenate([[0], off]))
+        L.call("cb_furthest_sampling", len(off), int(lens.max()), t(xyz), t(off), t(noff), tmp, out, L.stream())
+        assert np.array_equal(tmp.cpu().numpy().view(np.uint32), gold[f"fps/{name}/tmp"].view(np.uint32))
 
 
 @pytest.mark.parametrize("lens", [[40960, 40960, 30000, 40960], [10240, 10240, 7000], [2560, 640], [9000, 70000]])
