@@ -36,6 +36,12 @@ def lib():
     return _lib
 
 
+def launch_count():
+    f = lib().cb_launch_count
+    f.restype = C.c_ulonglong
+    return int(f())
+
+
 def ptr(t):
     """device pointer of a tensor (None -> NULL)"""
     if t is None:

@@ -8,6 +8,8 @@
 #define CB_FULL_MASK 0xffffffffu
 
 void cb_set_error(const char *fmt, ...);
+extern unsigned long long g_cb_launches;   // kernels launched by this library (host-side count)
+#define CB_COUNT(n) (g_cb_launches += (n))
 
 #define CB_REQUIRE(cond, code, ...)            \
     do {                                       \

@@ -180,6 +180,7 @@ extern "C" int cb_furthest_sampling(int b, int n_max, const float *xyz, const in
         (void)cudaGetLastError();
         return CB_ECUDA;
     }
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_furthest_sampling");
     return CB_OK;
 }

@@ -63,6 +63,7 @@ extern "C" int cb_grouping_forward(int m, int nsample, int c, const float *input
     const bool v4 = (c % 4 == 0) && (((uintptr_t)input | (uintptr_t)output) % 16 == 0);
     if (v4) k_grouping_fwd<4><<<nblocks(rows * (c / 4), 256), 256, 0, st>>>(rows, c / 4, input, idx, output);
     else k_grouping_fwd<1><<<nblocks(rows * c, 256), 256, 0, st>>>(rows, c, input, idx, output);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_grouping_forward");
     return CB_OK;
 }
@@ -78,6 +79,7 @@ extern "C" int cb_grouping_backward(int m, int nsample, int c, const float *grad
     const bool v4 = (c % 4 == 0) && (((uintptr_t)grad_input | (uintptr_t)grad_output) % 16 == 0);
     if (v4) k_grouping_bwd<4><<<nblocks(rows * (c / 4), 256), 256, 0, st>>>(rows, c / 4, grad_output, idx, grad_input);
     else k_grouping_bwd<1><<<nblocks(rows * c, 256), 256, 0, st>>>(rows, c, grad_output, idx, grad_input);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_grouping_backward");
     return CB_OK;
 }
@@ -119,6 +121,7 @@ extern "C" int cb_subtraction_forward(int n, int nsample, int c, const float *in
     if ((long long)n * nsample * c == 0) return CB_OK;
     CB_REQUIRE(input1 && input2 && idx && output, CB_EINVAL, "cb_subtraction_forward: NULL pointer");
     k_subtraction_fwd<<<nblocks((long long)n * nsample * c, 256), 256, 0, (cudaStream_t)stream>>>(n, nsample, c, input1, input2, idx, output);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_subtraction_forward");
     return CB_OK;
 }
@@ -130,6 +133,7 @@ extern "C" int cb_subtraction_backward(int n, int nsample, int c, const int *idx
     if ((long long)n * nsample * c == 0) return CB_OK;
     CB_REQUIRE(idx && grad_output && grad_input1 && grad_input2, CB_EINVAL, "cb_subtraction_backward: NULL pointer");
     k_subtraction_bwd<<<nblocks((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(n, nsample, c, idx, grad_output, grad_input1, grad_input2);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_subtraction_backward");
     return CB_OK;
 }
@@ -195,6 +199,7 @@ extern "C" int cb_aggregation_forward(int n, int nsample, int c, int w_c, const 
     if ((long long)n * c == 0) return CB_OK;
     CB_REQUIRE(input && position && weight && idx && output, CB_EINVAL, "cb_aggregation_forward: NULL pointer");
     k_aggregation_fwd<<<nblocks((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(n, nsample, c, w_c, input, position, weight, idx, output);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_aggregation_forward");
     return CB_OK;
 }
@@ -210,6 +215,7 @@ extern "C" int cb_aggregation_backward(int n, int nsample, int c, int w_c, const
     cudaStream_t st = (cudaStream_t)stream;
     k_aggregation_bwd_ip<<<nblocks((long long)n * nsample * c, 256), 256, 0, st>>>(n, nsample, c, w_c, weight, idx, grad_output, grad_input, grad_position);
     k_aggregation_bwd_w<<<nblocks((long long)n * nsample * w_c, 256), 256, 0, st>>>(n, nsample, c, w_c, input, position, idx, grad_output, grad_weight);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_aggregation_backward");
     return CB_OK;
 }
@@ -249,6 +255,7 @@ extern "C" int cb_interpolation_forward(int n, int c, int k, const float *input,
     if ((long long)n * c == 0) return CB_OK;
     CB_REQUIRE(input && idx && weight && output, CB_EINVAL, "cb_interpolation_forward: NULL pointer");
     k_interpolation_fwd<<<nblocks((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(n, c, k, input, idx, weight, output);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_interpolation_forward");
     return CB_OK;
 }
@@ -260,6 +267,7 @@ extern "C" int cb_interpolation_backward(int n, int c, int k, const float *grad_
     if ((long long)n * c == 0) return CB_OK;
     CB_REQUIRE(grad_output && idx && weight && grad_input, CB_EINVAL, "cb_interpolation_backward: NULL pointer");
     k_interpolation_bwd<<<nblocks((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(n, c, k, grad_output, idx, weight, grad_input);
+    CB_COUNT(1);
     CB_CUDA_CHECK("cb_interpolation_backward");
     return CB_OK;
 }

@@ -23,6 +23,8 @@ void cb_set_error(const char *fmt, ...)
 }
 extern "C" const char *cb_last_error_string(void) { return g_err; }
 extern "C" int cb_version(void) { return 100; }
+unsigned long long g_cb_launches = 0;
+extern "C" unsigned long long cb_launch_count(void) { return g_cb_launches; }
 
 // ---------------------------------------------------------------------------------------------
 // workspace layout
@@ -436,6 +438,7 @@ int cb_grid_build_impl(const float *xyz, int n, const int *offset, int b, int ns
     k_scan_tiles<<<v.max_tiles, 256, 0, st>>>(v.cells, v.tile_sums, v.hdr);
     k_scan_add<<<v.max_tiles, 256, 0, st>>>(v.cells, v.tile_sums, v.hdr);
     if (n > 0) k_fill<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, v.cells, v.point_cell, v.point_rank, v.sorted);
+    CB_COUNT(11);
     CB_CUDA_CHECK("cb_grid_build");
     return CB_OK;
 }
@@ -494,6 +497,7 @@ static int query_impl(int m, int K, const float *xyz, int n, const float *new_xy
         k_flag_all<<<(m + 255) / 256, 256, 0, st>>>(m, v.hdr, v.flagged);
     }
     cb_knn_replay_launch(K, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, sqrt_dist, v, st);
+    CB_COUNT(3);
     CB_CUDA_CHECK("cb_knn_query");
     return CB_OK;
 }

@@ -195,6 +195,7 @@ extern "C" int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n,
 #undef KG_LAUNCH
     cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
     k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
+    CB_COUNT(4);
     CB_CUDA_CHECK("cb_knn_gather");
     return CB_OK;
 }

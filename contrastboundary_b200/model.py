@@ -1,0 +1,420 @@
+"""Point-Transformer + Contrastive-Boundary-Learning network on the B200-native operator stack.
+
+Host-side mirror of the reference's model code (LiyaoTang/contrastBoundary, pytorch/model/
+{pointtransformer_seg,blocks,heads,basic_operators}.py): same architecture, same parameter /
+buffer names (a reference `state_dict` loads unchanged), same outputs — but organised around a
+`Geometry` object: everything that depends only on coordinates (farthest-point sampling, every
+neighbour search, interpolation weights) is computed ONCE per forward, up front, on a side stream,
+instead of being recomputed inside every layer (the reference launches 57 KNN searches per
+forward of which 31 are exact repeats) and without any `.item()` host sync
+(scene sizes are host-known from the collate step).
+
+`fused=True` (default) routes the local aggregation and the CBL loss through the fused CUDA
+kernels of libcbops (ptlayer.py / cbl.py); `fused=False` keeps the reference's op-by-op math on
+top of the stand-alone pointops kernels (used for parity tests of the fused path).
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointops
+
+
+@dataclass
+class ContrastCfg:          # reference yaml `contrast:` block (config/s3dis/origin_multi-...yaml:61-69)
+    stage: str = "Ua"
+    contrast: str = "softnn"
+    ftype: str = "latent"
+    dist: str = "l2"
+    temperature: Optional[float] = 1.0
+    weight: float = 0.1     # 'w.1'
+
+
+@dataclass
+class CBLConfig:
+    fea_dim: int = 6
+    classes: int = 13
+    planes: List[int] = field(default_factory=lambda: [32, 64, 128, 256, 512])
+    blocks: List[int] = field(default_factory=lambda: [2, 3, 4, 6, 3])
+    stride: List[int] = field(default_factory=lambda: [1, 4, 4, 4, 4])
+    nsample_backbone: List[int] = field(default_factory=lambda: [8, 16, 16, 16, 16])   # pointtransformer_seg.py:44
+    share_planes: int = 8
+    base_fdim: int = 32
+    nsample: List[int] = field(default_factory=lambda: [36, 24, 24, 24, 24])           # contrast head only (yaml:57)
+    nstride: List[int] = field(default_factory=lambda: [4, 4, 4, 4])
+    ignore_label: int = 255
+    contrast: Optional[ContrastCfg] = field(default_factory=ContrastCfg)
+    multi: bool = True      # MultiHead(stage 'Ua', ftype latent, combine concat)
+    fused: bool = False
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry: everything that depends on coordinates only
+# ------------------------------------------------------------------------------------------------
+class Level:
+    __slots__ = ("p", "o", "o_host", "n", "knn", "fps_idx", "down_idx", "up_idx", "up_w", "head_idx",
+                 "label_idx", "cbl_idx", "scene_id")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def _lens(o_host):
+    return [o_host[0]] + [o_host[i] - o_host[i - 1] for i in range(1, len(o_host))]
+
+
+def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
+    """All sampling / neighbour searches of one forward.  p0 (n,3) f32, o0 (b) int32 cumulative ends,
+    o0_host = the same offsets as a python list (known from collate; avoids device->host syncs)."""
+    levels = []
+    p, o, oh = p0, o0, list(o0_host)
+    nl = len(cfg.planes)
+    for l in range(nl):
+        lv = Level()
+        if l > 0:
+            # TransitionDown sampling (blocks.py:64-70): per-scene floor(n_b / stride)
+            prev = levels[-1]
+            lens = [x // cfg.stride[l] for x in _lens(prev.o_host)]
+            oh = []
+            acc = 0
+            for x in lens:
+                acc += x
+                oh.append(acc)
+            o = torch.tensor(oh, dtype=torch.int32, device=p0.device)
+            fidx = pointops.furthestsampling_known(prev.p, prev.o, o, max(_lens(prev.o_host)), acc)
+            p = prev.p[fidx.long(), :].contiguous()
+            lv.fps_idx = fidx
+            # neighbours of the new points among the previous level (blocks.py:71)
+            lv.down_idx, _ = pointops.knn_raw(cfg.nsample_backbone[l], prev.p, p, prev.o, o, True)
+        lv.p, lv.o, lv.o_host, lv.n = p, o, oh, p.shape[0]
+        lv.knn, _ = pointops.knn_raw(cfg.nsample_backbone[l], p, p, o, o, True)          # blocks.py:34-35
+        levels.append(lv)
+    for l in range(nl - 1):
+        # TransitionUp interpolation l+1 -> l, k=3 (blocks.py:108, pointops.py:164-178)
+        fine, coarse = levels[l], levels[l + 1]
+        idx, dist = pointops.knn_raw(3, coarse.p, fine.p, coarse.o, fine.o, True)
+        dr = 1.0 / (dist + 1e-8)
+        fine.up_idx, fine.up_w = idx, (dr / dr.sum(1, keepdim=True)).contiguous()
+    for l in range(1, nl):
+        # MultiHead nearest upsample l -> 0, k=1 (heads.py:44-51)
+        levels[l].head_idx, _ = pointops.knn_raw(1, levels[l].p, levels[0].p, levels[l].o, levels[0].o, True)
+    # dec5 per-scene mean (blocks.py:94-103)
+    last = levels[-1]
+    sid = torch.zeros(last.n, dtype=torch.long, device=p0.device)
+    if len(last.o_host) > 1:
+        sid[torch.tensor(last.o_host[:-1], device=p0.device, dtype=torch.long)] = 1
+        sid = torch.cumsum(sid, 0)
+    last.scene_id = sid
+    if with_contrast and cfg.contrast is not None:
+        kr = 1
+        for l in range(nl):
+            lv = levels[l]
+            if l > 0:
+                kr *= cfg.nstride[l - 1]
+                # sub-scene labels: kr nearest full-resolution points (basic_operators.py:20-30)
+                lv.label_idx, _ = pointops.knn_raw(kr, levels[0].p, lv.p, levels[0].o, lv.o, True)
+            lv.cbl_idx, _ = pointops.knn_raw(cfg.nsample[l], lv.p, lv.p, lv.o, lv.o, True)   # heads.py:192
+    return levels
+
+
+# ------------------------------------------------------------------------------------------------
+# blocks (parameter names follow the reference so its checkpoints load)
+# ------------------------------------------------------------------------------------------------
+def _bn_rows(bn: nn.BatchNorm1d, x):
+    """BatchNorm1d over the last dim of (..., c): same statistics as the reference's
+    transpose(1,2) -> BatchNorm1d -> transpose(1,2) (blocks.py:38,40) without the two copies."""
+    shp = x.shape
+    return bn(x.reshape(-1, shp[-1])).view(shp)
+
+
+class PointTransformerLayer(nn.Module):
+    """blocks.py:14-44"""
+
+    def __init__(self, in_planes, out_planes, share_planes=8, nsample=16):
+        super().__init__()
+        self.mid_planes = mid_planes = out_planes // 1
+        self.out_planes = out_planes
+        self.share_planes = share_planes
+        self.nsample = nsample
+        self.linear_q = nn.Linear(in_planes, mid_planes)
+        self.linear_k = nn.Linear(in_planes, mid_planes)
+        self.linear_v = nn.Linear(in_planes, out_planes)
+        self.linear_p = nn.Sequential(nn.Linear(3, 3), nn.BatchNorm1d(3), nn.ReLU(inplace=True), nn.Linear(3, out_planes))
+        self.linear_w = nn.Sequential(nn.BatchNorm1d(mid_planes), nn.ReLU(inplace=True),
+                                      nn.Linear(mid_planes, mid_planes // share_planes),
+                                      nn.BatchNorm1d(mid_planes // share_planes), nn.ReLU(inplace=True),
+                                      nn.Linear(out_planes // share_planes, out_planes // share_planes))
+        self.fused = True
+
+    def forward(self, p, x, idx):
+        x_q, x_k, x_v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
+        if self.fused:
+            from . import ptlayer
+            return ptlayer.pt_attention(self, p, x_q, x_k, x_v, idx)
+        n, k = idx.shape
+        c, s = self.out_planes, self.share_planes
+        p_r = pointops.grouping(p, idx) - p.unsqueeze(1)                       # (n,k,3)
+        x_kg, x_vg = pointops.grouping(x_k, idx), pointops.grouping(x_v, idx)  # (n,k,c)
+        p_r = self.linear_p[0](p_r)
+        p_r = F.relu(_bn_rows(self.linear_p[1], p_r))
+        p_r = self.linear_p[3](p_r)                                            # (n,k,c)
+        w = x_kg - x_q.unsqueeze(1) + p_r
+        w = F.relu(_bn_rows(self.linear_w[0], w))
+        w = self.linear_w[2](w)
+        w = F.relu(_bn_rows(self.linear_w[3], w))
+        w = self.linear_w[5](w)
+        w = F.softmax(w, dim=1)                                                # over the k neighbours
+        return ((x_vg + p_r).view(n, k, s, c // s) * w.unsqueeze(2)).sum(1).view(n, c)
+
+
+class TransitionDown(nn.Module):
+    """blocks.py:47-77"""
+
+    def __init__(self, in_planes, out_planes, stride=1, nsample=16):
+        super().__init__()
+        self.stride, self.nsample = stride, nsample
+        if stride != 1:
+            self.linear = nn.Linear(3 + in_planes, out_planes, bias=False)
+        else:
+            self.linear = nn.Linear(in_planes, out_planes, bias=False)
+        self.bn = nn.BatchNorm1d(out_planes)
+
+    def forward(self, x, prev_level=None, level=None):
+        if self.stride == 1:
+            return F.relu(self.bn(self.linear(x)))
+        idx = level.down_idx                                                   # (m,k) into prev_level
+        g_xyz = pointops.grouping(prev_level.p, idx) - level.p.unsqueeze(1)    # (m,k,3)
+        g = torch.cat((g_xyz, pointops.grouping(x, idx)), -1)                  # (m,k,3+c)
+        h = F.relu(_bn_rows(self.bn, self.linear(g)))                          # (m,k,c')
+        return h.max(1)[0]                                                     # MaxPool1d(nsample)
+
+
+class TransitionUp(nn.Module):
+    """blocks.py:80-109"""
+
+    def __init__(self, in_planes, out_planes=None):
+        super().__init__()
+        if out_planes is None:
+            self.linear1 = nn.Sequential(nn.Linear(2 * in_planes, in_planes), nn.BatchNorm1d(in_planes), nn.ReLU(inplace=True))
+            self.linear2 = nn.Sequential(nn.Linear(in_planes, in_planes), nn.ReLU(inplace=True))
+        else:
+            self.linear1 = nn.Sequential(nn.Linear(out_planes, out_planes), nn.BatchNorm1d(out_planes), nn.ReLU(inplace=True))
+            self.linear2 = nn.Sequential(nn.Linear(in_planes, out_planes), nn.BatchNorm1d(out_planes), nn.ReLU(inplace=True))
+
+    def forward(self, x1, level1, x2=None):
+        if x2 is None:   # head of the decoder: concat the per-scene mean
+            b = len(level1.o_host)
+            cnt = torch.tensor(_lens(level1.o_host), dtype=x1.dtype, device=x1.device).unsqueeze(1)
+            mean = torch.zeros(b, x1.shape[1], dtype=x1.dtype, device=x1.device).index_add_(0, level1.scene_id, x1) / cnt
+            g = self.linear2(mean)[level1.scene_id]
+            return self.linear1(torch.cat((x1, g), 1))
+        up = pointops._InterpolationFn.apply(self.linear2(x2), level1.up_idx, level1.up_w)
+        return self.linear1(x1) + up
+
+
+class PointTransformerBlock(nn.Module):
+    """blocks.py:112-133"""
+    expansion = 1
+
+    def __init__(self, in_planes, planes, share_planes=8, nsample=16):
+        super().__init__()
+        self.linear1 = nn.Linear(in_planes, planes, bias=False)
+        self.bn1 = nn.BatchNorm1d(planes)
+        self.transformer2 = PointTransformerLayer(planes, planes, share_planes, nsample)
+        self.bn2 = nn.BatchNorm1d(planes)
+        self.linear3 = nn.Linear(planes, planes * self.expansion, bias=False)
+        self.bn3 = nn.BatchNorm1d(planes * self.expansion)
+
+    def forward(self, p, x, idx):
+        identity = x
+        x = F.relu(self.bn1(self.linear1(x)))
+        x = F.relu(self.bn2(self.transformer2(p, x, idx)))
+        x = self.bn3(self.linear3(x))
+        return F.relu(x + identity)
+
+
+class _LatentMLP(nn.Module):
+    """heads MLP for ftype 'latent' (blocks.py:157-192): Linear -> BN -> ReLU under `.infer`"""
+
+    def __init__(self, fdim, d_out):
+        super().__init__()
+        self.infer = nn.Sequential(nn.Linear(fdim, d_out), nn.BatchNorm1d(d_out), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        return self.infer(x)
+
+
+class MultiHead(nn.Module):
+    """heads.py:13-61 with stage 'Ua', ftype latent, combine concat"""
+
+    def __init__(self, fdims, cfg: CBLConfig):
+        super().__init__()
+        self.infer_list = nn.ModuleList([_LatentMLP(f, cfg.base_fdim) for f in fdims])
+        self.cls = nn.Linear(cfg.base_fdim * len(fdims), cfg.classes)
+
+    def forward(self, feats, levels):
+        latents, collect = [], []
+        for i, (f, mlp) in enumerate(zip(feats, self.infer_list)):
+            lat = mlp(f)
+            latents.append(lat)
+            # nearest (k=1) upsample: interpolation weight is exactly 1 (pointops.py:171-173)
+            collect.append(lat if i == 0 else pointops.grouping(lat, levels[i].head_idx).squeeze(1))
+        return self.cls(torch.cat(collect, 1)), latents
+
+
+class PointTransformerSeg(nn.Module):
+    """pointtransformer_seg.py:27-143 (pointtransformer_seg_repro: blocks [2,3,4,6,3])"""
+
+    def __init__(self, cfg: Optional[CBLConfig] = None):
+        super().__init__()
+        self.cfg = cfg = cfg or CBLConfig()
+        self.c = cfg.fea_dim
+        self.in_planes = cfg.fea_dim
+        pl, bl, sp, ns, st = cfg.planes, cfg.blocks, cfg.share_planes, cfg.nsample_backbone, cfg.stride
+        for i in range(5):
+            setattr(self, f"enc{i + 1}", self._make_enc(pl[i], bl[i], sp, st[i], ns[i]))
+        self.dec5 = self._make_dec(pl[4], 2, sp, ns[4], True)
+        self.dec4 = self._make_dec(pl[3], 2, sp, ns[3])
+        self.dec3 = self._make_dec(pl[2], 2, sp, ns[2])
+        self.dec2 = self._make_dec(pl[1], 2, sp, ns[1])
+        self.dec1 = self._make_dec(pl[0], 2, sp, ns[0])
+        if cfg.multi:
+            self.head = MultiHead(pl, cfg)
+            self.cls = None
+        else:
+            self.head = None
+            self.cls = nn.Sequential(nn.Linear(pl[0], pl[0]), nn.BatchNorm1d(pl[0]), nn.ReLU(inplace=True), nn.Linear(pl[0], cfg.classes))
+        self.set_fused(cfg.fused)
+
+    def set_fused(self, flag):
+        for m in self.modules():
+            if isinstance(m, PointTransformerLayer):
+                m.fused = bool(flag)
+
+    def _make_enc(self, planes, blocks, share_planes, stride, nsample):
+        layers = [TransitionDown(self.in_planes, planes, stride, nsample)]
+        self.in_planes = planes
+        for _ in range(1, blocks):
+            layers.append(PointTransformerBlock(planes, planes, share_planes, nsample))
+        return nn.Sequential(*layers)
+
+    def _make_dec(self, planes, blocks, share_planes, nsample, is_head=False):
+        layers = [TransitionUp(self.in_planes, None if is_head else planes)]
+        self.in_planes = planes
+        for _ in range(1, blocks):
+            layers.append(PointTransformerBlock(planes, planes, share_planes, nsample))
+        return nn.Sequential(*layers)
+
+    def forward(self, inputs, levels=None):
+        """inputs: dict(points (n,3), features (n,3), offset (b) int32[, offset_host list]).
+        returns logits (n, classes), stages dict(levels, up feats, latent)"""
+        p0, x0, o0 = inputs["points"], inputs["features"], inputs["offset"]
+        if levels is None:
+            o_host = inputs.get("offset_host")
+            if o_host is None:
+                o_host = o0.tolist()
+            levels = build_geometry(p0, o0, o_host, self.cfg, self.cfg.contrast is not None and self.training)
+        if self.c == 3:
+            x = p0
+        elif self.c == 6:
+            x = torch.cat((p0, x0), 1)
+        else:
+            x = torch.cat((torch.ones_like(p0[..., :1]), p0, x0), 1)
+        encs = [self.enc1, self.enc2, self.enc3, self.enc4, self.enc5]
+        down = []
+        for l, enc in enumerate(encs):
+            x = enc[0](x, levels[l - 1] if l > 0 else None, levels[l])
+            for blk in list(enc)[1:]:
+                x = blk(levels[l].p, x, levels[l].knn)
+            down.append(x)
+        decs = [self.dec1, self.dec2, self.dec3, self.dec4, self.dec5]
+        up = [None] * 5
+        x = decs[4][0](down[4], levels[4])
+        for blk in list(decs[4])[1:]:
+            x = blk(levels[4].p, x, levels[4].knn)
+        up[4] = x
+        for l in range(3, -1, -1):
+            x = decs[l][0](down[l], levels[l], up[l + 1])
+            for blk in list(decs[l])[1:]:
+                x = blk(levels[l].p, x, levels[l].knn)
+            up[l] = x
+        stages = {"levels": levels, "down": down, "up": up}
+        if self.head is not None:
+            logits, latents = self.head(up, levels)
+            stages["latent"] = latents
+        else:
+            logits = self.cls(up[0])
+        return logits, stages
+
+
+# ------------------------------------------------------------------------------------------------
+# contrastive boundary loss head
+# ------------------------------------------------------------------------------------------------
+_EPS = 1e-12   # basic_operators.py:7
+
+
+class ContrastHead(nn.Module):
+    """heads.py:63-253, configuration of the shipped yaml (softnn / l2 / label / cnt / T=1 / w=0.1)."""
+
+    def __init__(self, cfg: CBLConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.fused = cfg.fused
+
+    def subscene_labels(self, l, levels, target):
+        """basic_operators.py:9-50: one-hot at level 0, mean one-hot of the kr nearest full-res points above."""
+        onehot = F.one_hot(target, self.cfg.classes).float()
+        if l == 0:
+            return onehot
+        idx = levels[l].label_idx
+        return pointops.grouping(onehot, idx).mean(1)
+
+    def stage_loss(self, l, levels, latent, target):
+        cc = self.cfg.contrast
+        if self.fused:
+            from . import cbl
+            return cbl.cbl_stage_loss(self, l, levels, latent, target)
+        labels = self.subscene_labels(l, levels, target)                        # (m, ncls)
+        idx = levels[l].cbl_idx[:, 1:].contiguous()                             # drop self (heads.py:196)
+        nb_label = pointops.grouping(labels, idx)                               # (m, k-1, ncls)
+        nb_feat = pointops.grouping(latent, idx)                                # (m, k-1, d)
+        posmask = labels.argmax(-1, keepdim=True) == nb_label.argmax(-1)        # heads.py:145-149
+        cnt = posmask.sum(-1)
+        point_mask = (cnt > 0) & (cnt < idx.shape[1])                           # boundary points only (heads.py:213-214)
+        dist = torch.sqrt(((latent.unsqueeze(1) - nb_feat) ** 2).sum(-1) + _EPS)   # heads.py:116-119
+        d = -dist
+        d = d - d.max(-1, keepdim=True)[0]
+        if cc.temperature is not None:
+            d = d / cc.temperature
+        e = torch.exp(d)
+        pos = (e * posmask).sum(-1)
+        neg = e.sum(-1)
+        loss = -torch.log(pos / neg + _EPS)                                     # heads.py:151-165
+        pm = point_mask.float()
+        # mean over boundary points; 0 (no grad) when a stage has none (heads.py:222-233, kept on device)
+        loss = (loss * pm).sum() / pm.sum().clamp(min=1.0)
+        return loss * cc.weight
+
+    def forward(self, stages, target):
+        levels, latents = stages["levels"], stages["latent"]
+        return [self.stage_loss(l, levels, latents[l], target) for l in range(len(levels))]
+
+
+class Loss(nn.Module):
+    """pointtransformer_seg.py:15-25: stack [cross-entropy, cbl_0 .. cbl_4]"""
+
+    def __init__(self, cfg: CBLConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.contrast_head = ContrastHead(cfg) if cfg.contrast is not None else None
+        self.xen = nn.CrossEntropyLoss(ignore_index=cfg.ignore_label)
+
+    def forward(self, output, target, stages):
+        losses = [self.xen(output, target)]
+        if self.contrast_head is not None:
+            losses += self.contrast_head(stages, target)
+        return torch.stack(losses)

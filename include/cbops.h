@@ -38,6 +38,7 @@ extern "C" {
 
 int cb_version(void);
 const char *cb_last_error_string(void);
+unsigned long long cb_launch_count(void); /* kernels launched by this library so far (host-side counter) */
 
 /* ------------------------------------------------------------------------------------------------
  * a1  K-nearest-neighbour query            replaces knnquery_cuda_launcher

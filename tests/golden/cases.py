@@ -106,3 +106,47 @@ def tf_sphere():
     """a ~15000-point input 'sphere' (config 3 shape) and its 5 pyramid levels"""
     c, f, l = S.make_scene(15000, 3000)
     return c, f, l.astype(np.int32)
+
+
+# ---- model-level cases --------------------------------------------------------------------------
+def model_batch():
+    """two rooms (4096 + 3000 points): deep levels get shorter than K, so padding paths are exercised"""
+    b = S.make_batch(2, [4096, 3000], 31)
+    return b
+
+
+def deterministic_init(model, seed=0):
+    """Fill every parameter / BN buffer from a per-name seeded generator, so that the reference model,
+    the oracle restatement and the product model (same state_dict names) get identical weights
+    without shipping a checkpoint."""
+    import zlib
+    import torch
+    with torch.no_grad():
+        for name, t in list(model.named_parameters()) + list(model.named_buffers()):
+            if not t.dtype.is_floating_point:
+                continue
+            g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
+            r = torch.randn(t.shape, generator=g)
+            if name.endswith("running_var"):
+                v = 1.0 + 0.1 * r.abs()
+            elif name.endswith("running_mean"):
+                v = 0.05 * r
+            elif t.dim() == 1 and name.endswith("weight"):      # BatchNorm gamma
+                v = 1.0 + 0.2 * r
+            elif t.dim() == 1:                                  # biases / BatchNorm beta
+                v = 0.1 * r
+            else:                                               # Linear weights
+                v = r * (1.0 / t.shape[1]) ** 0.5
+            t.copy_(v.to(t.device))
+
+
+GOLDEN_GRADS = ["enc1.0.linear.weight", "enc1.1.transformer2.linear_p.0.weight", "enc1.1.transformer2.linear_w.2.weight",
+                "enc3.1.transformer2.linear_w.5.weight", "enc5.2.transformer2.linear_w.2.weight", "dec5.0.linear2.0.bias",
+                "dec2.0.linear2.0.weight", "head.cls.weight", "head.infer_list.3.infer.0.weight"]
+
+
+def grad_is_analytically_zero(name):
+    """biases that feed straight into a training-mode BatchNorm have zero gradient; what either
+    implementation reports for them is rounding noise and is not compared."""
+    import re
+    return bool(re.search(r"(linear_[qkv]\.bias|linear_p\.3\.bias|linear_p\.0\.bias|linear_w\.[25]\.bias|infer\.0\.bias|dec\d\.0\.linear1\.0\.bias|dec[1-4]\.0\.linear2\.0\.bias)$", name))

@@ -1,0 +1,79 @@
+"""GPU parity of the full network (product model on libcbops) against the golden vectors made by
+the REAL reference model code on CPU (tests/golden/model_ref.npz).  Tolerance: logits / loss
+1e-4 relative (BASELINE.json north_star); gradient norms 1e-3 relative (float scatter order)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def run_product(fused):
+    from contrastboundary_b200 import engine, model
+    cfg = model.CBLConfig(fused=fused)
+    ts = engine.TrainStep(cfg, "cuda")
+    cases.deterministic_init(ts.model, 0)
+    hb = engine.host_batch_from_numpy(cases.model_batch(), pin=False)
+    batch = engine.to_device(hb, ts.device)
+    out, stages = ts.model(batch)
+    loss = ts.criterion(out, batch["point_labels"], stages)
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    return ts.model, out, loss, stages
+
+
+def check_against_golden(mdl, out, loss, stages, g, tol):
+    ref_logits = g["logits"]
+    err = np.abs(out.detach().cpu().numpy() - ref_logits).max() / np.abs(ref_logits).max()
+    assert err < tol, f"logits rel err {err}"
+    l, rl = loss.detach().cpu().numpy(), g["loss"]
+    assert np.allclose(l, rl, rtol=tol, atol=1e-7), (l, rl)
+    for i in range(5):
+        a, b = stages["latent"][i].detach().cpu().numpy()[:64], g[f"latent/{i}"]
+        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-6) < tol * 5, f"latent {i}"
+    norms = json.loads(bytes(g["grad_norms_json"]).decode())
+    params = dict(mdl.named_parameters())
+    assert set(norms) == {n for n, p in params.items() if p.grad is not None}
+    worst = 0.0
+    for name, ref in norms.items():
+        if cases.grad_is_analytically_zero(name):
+            continue
+        rel = abs(float(params[name].grad.norm()) - ref) / max(ref, 1e-6)
+        worst = max(worst, rel)
+        assert rel < 10 * tol, (name, rel)
+    for name in cases.GOLDEN_GRADS:
+        a, b = params[name].grad.cpu().numpy(), g["grad/" + name]
+        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-9) < 10 * tol, name
+
+
+def test_unfused_model_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_ref.npz"))
+    check_against_golden(*run_product(False), g, 1e-4)
+
+
+def test_fused_model_matches_reference(golden_dir):
+    from contrastboundary_b200 import ptlayer
+    if not getattr(ptlayer, "READY", False):
+        pytest.skip("fused layer kernels not built yet")
+    g = np.load(os.path.join(golden_dir, "model_ref.npz"))
+    check_against_golden(*run_product(True), g, 1e-4)
+
+
+def test_train_step_runs_and_updates():
+    from contrastboundary_b200 import engine, model, synthetic
+    ts = engine.TrainStep(model.CBLConfig(), "cuda")
+    hb = engine.host_batch_from_numpy(synthetic.make_batch(2, [2048, 1024], 3), pin=False)
+    batch = engine.to_device(hb, ts.device)
+    w0 = ts.model.head.cls.weight.detach().clone()
+    l1 = ts.step(batch)
+    l2 = ts.step(batch)
+    assert torch.isfinite(l1).all() and torch.isfinite(l2).all()
+    assert not torch.equal(w0, ts.model.head.cls.weight.detach())
