@@ -333,6 +333,13 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
 // (knnquery_cuda_kernel.cu:21-48,91-110) in shared memory.
 // ---------------------------------------------------------------------------------------------
 #define CB_REPLAY_THREADS 256
+#define CB_REPLAY_PER_THREAD 16
+#define CB_REPLAY_BATCH (CB_REPLAY_THREADS * CB_REPLAY_PER_THREAD)
+// The heap replay itself is serial (the reference's result under ties is defined by its heap
+// history), but only candidates with d2 < root are ever inserted and the root never grows.  So the
+// block filters a batch of 4096 candidates in parallel against the root at the start of the batch
+// (an upper bound for every later root), compacts the survivors IN INDEX ORDER, and thread 0
+// replays just those — a handful per batch once the heap has warmed up.
 __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const float *__restrict__ xyz,
                                                                  const float *__restrict__ new_xyz,
                                                                  const int *__restrict__ offset,
@@ -342,10 +349,13 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
                                                                  const int *__restrict__ flagged)
 {
     extern __shared__ unsigned char smem_raw[];
-    float *hd = (float *)smem_raw;          // K
-    int *hi = (int *)(hd + K);              // K
-    float *cd = (float *)(hi + K);          // CB_REPLAY_THREADS
-    const int t = threadIdx.x;
+    float *hd = (float *)smem_raw;                     // K
+    int *hi = (int *)(hd + K);                         // K
+    float *cd = (float *)(hi + K);                     // CB_REPLAY_BATCH survivors (distance)
+    int *ci = (int *)(cd + CB_REPLAY_BATCH);           // CB_REPLAY_BATCH survivors (index)
+    __shared__ int warp_cnt[CB_REPLAY_THREADS / 32];
+    __shared__ int s_total;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int count = hdr->flagged_count;
     for (int f = blockIdx.x; f < count; f += gridDim.x) {
         const int q = flagged[f];
@@ -354,44 +364,65 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
         const float qx = new_xyz[3 * q], qy = new_xyz[3 * q + 1], qz = new_xyz[3 * q + 2];
         for (int k = t; k < K; k += CB_REPLAY_THREADS) { hd[k] = 1e10f; hi[k] = start; }
         __syncthreads();
-        for (int base = start; base < end; base += CB_REPLAY_THREADS) {
-            const int i = base + t;
-            float d = 3.0e38f;
-            if (i < end) d = cb_sqdist(qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
-            cd[t] = d;
-            const int any = __syncthreads_or(i < end && d < hd[0]);
-            if (any) {
-                if (t == 0) {
-                    const int lim = min(CB_REPLAY_THREADS, end - base);
-                    for (int u = 0; u < lim; u++) {
-                        const float d2 = cd[u];
-                        if (d2 < hd[0]) {
-                            hd[0] = d2; hi[0] = base + u;
-                            int root = 0, child = 1;                       // reheap
-                            while (child < K) {
-                                if (child + 1 < K && hd[child + 1] > hd[child]) child++;
-                                if (hd[root] > hd[child]) break;
-                                float td = hd[root]; hd[root] = hd[child]; hd[child] = td;
-                                int ti = hi[root]; hi[root] = hi[child]; hi[child] = ti;
-                                root = child; child = root * 2 + 1;
-                            }
+        for (int base = start; base < end; base += CB_REPLAY_BATCH) {
+            const float root = hd[0];
+            const int i0 = base + t * CB_REPLAY_PER_THREAD;
+            float d[CB_REPLAY_PER_THREAD];
+            int npass = 0;
+#pragma unroll
+            for (int u = 0; u < CB_REPLAY_PER_THREAD; u++) {
+                const int i = i0 + u;
+                d[u] = 3.0e38f;
+                if (i < end) d[u] = cb_sqdist(qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+                npass += d[u] < root;
+            }
+            // block exclusive scan of npass (thread order == index order)
+            int inc = npass;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(CB_FULL_MASK, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) warp_cnt[w] = inc;
+            __syncthreads();
+            int woff = 0;
+            for (int k = 0; k < w; k++) woff += warp_cnt[k];
+            if (t == CB_REPLAY_THREADS - 1) s_total = woff + inc;
+            int pos = woff + inc - npass;
+#pragma unroll
+            for (int u = 0; u < CB_REPLAY_PER_THREAD; u++)
+                if (d[u] < root) { cd[pos] = d[u]; ci[pos] = i0 + u; pos++; }
+            __syncthreads();
+            if (t == 0) {
+                const int total = s_total;
+                for (int u = 0; u < total; u++) {
+                    const float d2 = cd[u];
+                    if (d2 < hd[0]) {
+                        hd[0] = d2; hi[0] = ci[u];
+                        int r = 0, child = 1;                              // reheap (knnquery_cuda_kernel.cu:21-36)
+                        while (child < K) {
+                            if (child + 1 < K && hd[child + 1] > hd[child]) child++;
+                            if (hd[r] > hd[child]) break;
+                            float td = hd[r]; hd[r] = hd[child]; hd[child] = td;
+                            int ti = hi[r]; hi[r] = hi[child]; hi[child] = ti;
+                            r = child; child = r * 2 + 1;
                         }
                     }
                 }
             }
             __syncthreads();
         }
-        if (t == 0) {                                                       // heap_sort
+        if (t == 0) {                                                       // heap_sort (:39-48)
             for (int i = K - 1; i > 0; i--) {
                 float td = hd[0]; hd[0] = hd[i]; hd[i] = td;
                 int ti = hi[0]; hi[0] = hi[i]; hi[i] = ti;
-                int root = 0, child = 1;
+                int r = 0, child = 1;
                 while (child < i) {
                     if (child + 1 < i && hd[child + 1] > hd[child]) child++;
-                    if (hd[root] > hd[child]) break;
-                    float t2 = hd[root]; hd[root] = hd[child]; hd[child] = t2;
-                    int t3 = hi[root]; hi[root] = hi[child]; hi[child] = t3;
-                    root = child; child = root * 2 + 1;
+                    if (hd[r] > hd[child]) break;
+                    float t2 = hd[r]; hd[r] = hd[child]; hd[child] = t2;
+                    int t3 = hi[r]; hi[r] = hi[child]; hi[child] = t3;
+                    r = child; child = r * 2 + 1;
                 }
             }
         }
@@ -468,7 +499,7 @@ void cb_knn_replay_launch(int K, int m, const float *xyz, const float *new_xyz, 
                           const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, const CbGridView &v,
                           cudaStream_t st)
 {
-    const size_t smem = (size_t)K * 8 + CB_REPLAY_THREADS * 4;
+    const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
     const int rblocks = K <= 256 ? 148 : (m < 148 * 8 ? (m > 0 ? m : 1) : 148 * 8);
     k_knn_replay<<<rblocks, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, dist2,
                                                            sqrt_dist, v.hdr, v.flagged);

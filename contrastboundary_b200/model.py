@@ -56,7 +56,7 @@ class CBLConfig:
 # ------------------------------------------------------------------------------------------------
 class Level:
     __slots__ = ("p", "o", "o_host", "n", "knn", "fps_idx", "down_idx", "up_idx", "up_w", "head_idx",
-                 "label_idx", "cbl_idx", "scene_id")
+                 "label_idx", "cbl_idx", "scene_id", "rel", "rel_mom")
 
     def __init__(self):
         for s in self.__slots__:
@@ -92,6 +92,9 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
             lv.down_idx, _ = pointops.knn_raw(cfg.nsample_backbone[l], prev.p, p, prev.o, o, True)
         lv.p, lv.o, lv.o_host, lv.n = p, o, oh, p.shape[0]
         lv.knn, _ = pointops.knn_raw(cfg.nsample_backbone[l], p, p, o, o, True)          # blocks.py:34-35
+        if cfg.fused:
+            from . import ptlayer
+            lv.rel, lv.rel_mom = ptlayer.pt_rel(p, lv.knn)
         levels.append(lv)
     for l in range(nl - 1):
         # TransitionUp interpolation l+1 -> l, k=3 (blocks.py:108, pointops.py:164-178)
@@ -150,11 +153,12 @@ class PointTransformerLayer(nn.Module):
                                       nn.Linear(out_planes // share_planes, out_planes // share_planes))
         self.fused = True
 
-    def forward(self, p, x, idx):
+    def forward(self, lv, x):
+        p, idx = lv.p, lv.knn
         x_q, x_k, x_v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
         if self.fused:
             from . import ptlayer
-            return ptlayer.pt_attention(self, p, x_q, x_k, x_v, idx)
+            return ptlayer.pt_attention(self, lv, x_q, x_k, x_v)
         n, k = idx.shape
         c, s = self.out_planes, self.share_planes
         p_r = pointops.grouping(p, idx) - p.unsqueeze(1)                       # (n,k,3)
@@ -229,10 +233,10 @@ class PointTransformerBlock(nn.Module):
         self.linear3 = nn.Linear(planes, planes * self.expansion, bias=False)
         self.bn3 = nn.BatchNorm1d(planes * self.expansion)
 
-    def forward(self, p, x, idx):
+    def forward(self, lv, x):
         identity = x
         x = F.relu(self.bn1(self.linear1(x)))
-        x = F.relu(self.bn2(self.transformer2(p, x, idx)))
+        x = F.relu(self.bn2(self.transformer2(lv, x)))
         x = self.bn3(self.linear3(x))
         return F.relu(x + identity)
 
@@ -329,18 +333,18 @@ class PointTransformerSeg(nn.Module):
         for l, enc in enumerate(encs):
             x = enc[0](x, levels[l - 1] if l > 0 else None, levels[l])
             for blk in list(enc)[1:]:
-                x = blk(levels[l].p, x, levels[l].knn)
+                x = blk(levels[l], x)
             down.append(x)
         decs = [self.dec1, self.dec2, self.dec3, self.dec4, self.dec5]
         up = [None] * 5
         x = decs[4][0](down[4], levels[4])
         for blk in list(decs[4])[1:]:
-            x = blk(levels[4].p, x, levels[4].knn)
+            x = blk(levels[4], x)
         up[4] = x
         for l in range(3, -1, -1):
             x = decs[l][0](down[l], levels[l], up[l + 1])
             for blk in list(decs[l])[1:]:
-                x = blk(levels[l].p, x, levels[l].knn)
+                x = blk(levels[l], x)
             up[l] = x
         stages = {"levels": levels, "down": down, "up": up}
         if self.head is not None:

@@ -1,6 +1,113 @@
-"""Fused PointTransformer local aggregation (placeholder until the fused kernels land):
-falls back to nothing — raising keeps the contract that there is no silent fallback."""
+"""Fused PointTransformer local aggregation (reference: PointTransformerLayer.forward,
+pytorch/model/blocks.py:31-44) as one autograd Function over libcbops' cb_pt_layer_forward /
+cb_pt_layer_backward.  Parameters stay ordinary nn.Parameters of the layer module (state_dict
+compatible with the reference); BatchNorm running statistics are updated in-kernel."""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+READY = True
+_FP = C.c_void_p
 
 
-def pt_attention(layer, p, x_q, x_k, x_v, idx):
-    raise NotImplementedError("fused pt_attention not built yet")
+class CbPtLayer(C.Structure):
+    _fields_ = [(n, _FP) for n in (
+        "w1", "b1", "bn1_weight", "bn1_bias", "bn1_running_mean", "bn1_running_var",
+        "w2", "b2", "bn2_weight", "bn2_bias", "bn2_running_mean", "bn2_running_var",
+        "w3", "b3", "bn3_weight", "bn3_bias", "bn3_running_mean", "bn3_running_var",
+        "w4", "b4")] + [("momentum", C.c_float), ("eps", C.c_float), ("training", C.c_int)]
+
+
+def _param_struct(params, buffers, momentum, eps, training):
+    (w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, g3, be3, w4, b4) = params
+    (rm1, rv1, rm2, rv2, rm3, rv3) = buffers
+    s = CbPtLayer()
+    for name, t in (("w1", w1), ("b1", b1), ("bn1_weight", g1), ("bn1_bias", be1), ("bn1_running_mean", rm1),
+                    ("bn1_running_var", rv1), ("w2", w2), ("b2", b2), ("bn2_weight", g2), ("bn2_bias", be2),
+                    ("bn2_running_mean", rm2), ("bn2_running_var", rv2), ("w3", w3), ("b3", b3), ("bn3_weight", g3),
+                    ("bn3_bias", be3), ("bn3_running_mean", rm3), ("bn3_running_var", rv3), ("w4", w4), ("b4", b4)):
+        assert t.is_contiguous() and t.dtype == torch.float32
+        setattr(s, name, t.data_ptr())
+    s.momentum, s.eps, s.training = float(momentum), float(eps), int(training)
+    return s
+
+
+class PtAttentionFn(Function):
+    @staticmethod
+    def forward(ctx, rel, moments, idx, xq, xk, xv, buffers, momentum, eps, training, *params):
+        n, k = idx.shape
+        c = xq.shape[1]
+        cs = c // 8
+        dev = xq.device
+        xq, xk, xv = xq.contiguous(), xk.contiguous(), xv.contiguous()
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+        w2buf = torch.empty((n, k, cs), dtype=torch.float32, device=dev)
+        abuf = torch.empty((n, k, cs), dtype=torch.float32, device=dev)
+        lib = L.lib()
+        lib.cb_pt_bnbuf_floats.restype = C.c_size_t
+        lib.cb_pt_stats_doubles.restype = C.c_size_t
+        bnbuf = torch.empty(lib.cb_pt_bnbuf_floats(C.c_int(c)), dtype=torch.float32, device=dev)
+        stats = torch.empty(lib.cb_pt_stats_doubles(C.c_int(c)), dtype=torch.float64, device=dev)
+        ps = _param_struct(params, buffers, momentum, eps, training)
+        rc = lib.cb_pt_layer_forward(C.c_int(n), C.c_int(k), C.c_int(c), C.byref(ps), L.ptr(rel), L.ptr(moments), L.ptr(idx),
+                                     L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(out), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf),
+                                     L.ptr(stats), L.stream())
+        L.check(rc, "cb_pt_layer_forward")
+        ctx.save_for_backward(rel, idx, xq, xk, xv, w2buf, abuf, bnbuf, *params)
+        ctx.training = training
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        rel, idx, xq, xk, xv, w2buf, abuf, bnbuf = ctx.saved_tensors[:8]
+        params = ctx.saved_tensors[8:]
+        n, k = idx.shape
+        c = xq.shape[1]
+        cs = c // 8
+        dev = xq.device
+        gout = gout.contiguous()
+        gxq = torch.empty_like(xq)
+        gxk = torch.zeros_like(xk)
+        gxv = torch.zeros_like(xv)
+        lib = L.lib()
+        lib.cb_pt_bwd_scratch_floats.restype = C.c_size_t
+        scratch = torch.empty(lib.cb_pt_bwd_scratch_floats(C.c_int(n), C.c_int(k), C.c_int(c)), dtype=torch.float32, device=dev)
+        # parameter gradients in one zeroed buffer (layout of cb_pt_layer_backward)
+        sizes = [9, 3, 3, 3, c * 3, c, c, c, cs * c, cs, cs, cs, cs * cs, cs]
+        gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        ps = _param_struct(params, (params[0],) * 6, 0.0, 0.0, ctx.training)   # running stats unused in backward
+        rc = lib.cb_pt_layer_backward(C.c_int(n), C.c_int(k), C.c_int(c), C.byref(ps), L.ptr(rel), L.ptr(idx), L.ptr(xq),
+                                      L.ptr(xk), L.ptr(xv), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf), L.ptr(gout),
+                                      L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.stream())
+        L.check(rc, "cb_pt_layer_backward")
+        grads, o = [], 0
+        for sz, p in zip(sizes, params):
+            grads.append(gbuf[o:o + sz].view_as(p))
+            o += sz
+        return (None, None, None, gxq, gxk, gxv, None, None, None, None, *grads)
+
+
+def pt_attention(layer, lv, x_q, x_k, x_v):
+    lp, lw = layer.linear_p, layer.linear_w
+    params = (lp[0].weight, lp[0].bias, lp[1].weight, lp[1].bias, lp[3].weight, lp[3].bias,
+              lw[0].weight, lw[0].bias, lw[2].weight, lw[2].bias, lw[3].weight, lw[3].bias, lw[5].weight, lw[5].bias)
+    buffers = (lp[1].running_mean, lp[1].running_var, lw[0].running_mean, lw[0].running_var,
+               lw[3].running_mean, lw[3].running_var)
+    training = layer.training
+    if training:
+        for bn in (lp[1], lw[0], lw[3]):
+            bn.num_batches_tracked += 1
+    return PtAttentionFn.apply(lv.rel, lv.rel_mom, lv.knn, x_q, x_k, x_v, buffers, lp[1].momentum, lp[1].eps,
+                               training, *params)
+
+
+def pt_rel(p, idx):
+    """rel (n,k,3) = p[idx] - p[n], moments (9) float64 — geometry only, once per level"""
+    n, k = idx.shape
+    rel = torch.empty((n, k, 3), dtype=torch.float32, device=p.device)
+    mom = torch.empty(9, dtype=torch.float64, device=p.device)
+    L.call("cb_pt_rel", n, k, p, idx, rel, mom, L.stream())
+    return rel, mom

@@ -119,6 +119,48 @@ int cb_interpolation_forward(int n, int c, int k, const float *input, const int 
 int cb_interpolation_backward(int n, int c, int k, const float *grad_output, const int *idx, const float *weight,
                               float *grad_input, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * a4  fused PointTransformer local aggregation (vector self-attention over the K neighbours)
+ *     replaces PointTransformerLayer.forward, pytorch/model/blocks.py:31-44 — and with it the
+ *     subtraction / aggregation kernels it subsumes (pointops.py:103-161) and ~25 torch kernels.
+ * Given x_q, x_k, x_v = linear_{q,k,v}(x) (n,c), neighbour idx (n,k) and rel = p[idx]-p (cb_pt_rel):
+ *     out = sum_k (x_v[idx] + pr) * softmax_k(linear_w(x_k[idx] - x_q + pr)),  pr = linear_p(rel)
+ * with training-mode BatchNorm statistics computed in-kernel (running stats updated, momentum/eps as
+ * torch.nn.BatchNorm1d).  CbPtLayer holds DEVICE pointers to the layer's parameters in the layout of
+ * the reference's state_dict (linear weights row-major [out][in]).
+ * Buffers (caller-allocated): w2buf, abuf (n,k,c/8) f32 and bnbuf (cb_pt_bnbuf_floats(c)) are saved
+ * for backward; stats = cb_pt_stats_doubles(c) doubles of scratch.  c in {32,64,128,256,512}, k <= 32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct CbPtLayer {
+    const float *w1, *b1;                                   /* linear_p.0  (3,3),(3)   */
+    const float *bn1_weight, *bn1_bias; float *bn1_running_mean, *bn1_running_var;   /* linear_p.1 */
+    const float *w2, *b2;                                   /* linear_p.3  (c,3),(c)   */
+    const float *bn2_weight, *bn2_bias; float *bn2_running_mean, *bn2_running_var;   /* linear_w.0 */
+    const float *w3, *b3;                                   /* linear_w.2  (c/8,c),(c/8) */
+    const float *bn3_weight, *bn3_bias; float *bn3_running_mean, *bn3_running_var;   /* linear_w.3 */
+    const float *w4, *b4;                                   /* linear_w.5  (c/8,c/8),(c/8) */
+    float momentum, eps;
+    int training;
+} CbPtLayer;
+
+size_t cb_pt_bnbuf_floats(int c);
+size_t cb_pt_stats_doubles(int c);
+/* rel (n,k,3) = p[idx] - p[n] and its 9 moments (3 sums, 6 second moments) — once per level */
+int cb_pt_rel(int n, int k, const float *p, const int *idx, float *rel, double *moments, void *stream);
+int cb_pt_layer_forward(int n, int k, int c, const CbPtLayer *L, const float *rel, const double *moments,
+                        const int *idx, const float *xq, const float *xk, const float *xv, float *out,
+                        float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream);
+
+/* backward of cb_pt_layer_forward.  grad_xk / grad_xv (n,c) and grad_params must be ZERO-FILLED by the
+ * caller (scatter / accumulation targets); grad_xq is overwritten.  grad_params layout (floats):
+ * [dW1 9][db1 3][dbn1_w 3][dbn1_b 3][dW2 3c][db2 c][dbn2_w c][dbn2_b c][dW3 c*c/8][db3 c/8][dbn3_w c/8]
+ * [dbn3_b c/8][dW4 (c/8)^2][db4 c/8].  scratch: cb_pt_bwd_scratch_floats(n,k,c) floats, 16-byte aligned. */
+size_t cb_pt_bwd_scratch_floats(int n, int k, int c);
+int cb_pt_layer_backward(int n, int k, int c, const CbPtLayer *L, const float *rel, const int *idx,
+                         const float *xq, const float *xk, const float *xv, const float *w2buf,
+                         const float *abuf, const float *bnbuf, const float *grad_out, float *grad_xq,
+                         float *grad_xk, float *grad_xv, float *grad_params, float *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""GPU parity of the fused PointTransformer layer kernels (cb_pt_layer_forward/backward) against the
+op-by-op torch path of the same module (which mirrors blocks.py:31-44), forward and every gradient."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def make_level(n_list, k, seed):
+    from contrastboundary_b200 import model, pointops, ptlayer, synthetic
+    b = synthetic.make_batch(len(n_list), n_list, seed)
+    lv = model.Level()
+    lv.p = torch.from_numpy(b["points"]).cuda()
+    lv.o = torch.from_numpy(b["offset"]).cuda()
+    lv.n = lv.p.shape[0]
+    lv.knn, _ = pointops.knn_raw(k, lv.p, lv.p, lv.o, lv.o, True)
+    lv.rel, lv.rel_mom = ptlayer.pt_rel(lv.p, lv.knn)
+    return lv
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
+
+
+@pytest.mark.parametrize("c,k,n_list", [(32, 8, [3000, 2000]), (64, 16, [1500, 900]), (128, 16, [700, 500]),
+                                        (256, 16, [300, 200]), (512, 16, [90, 70]), (32, 16, [12, 700])])
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_layer_matches_unfused(c, k, n_list, training):
+    from contrastboundary_b200 import model
+    lv = make_level(n_list, k, 100 + c)
+    torch.manual_seed(c + k)
+    layer = model.PointTransformerLayer(c, c, 8, k).cuda()
+    cases.deterministic_init(layer, 3)
+    layer.train(training)
+    x = torch.randn(lv.n, c, device="cuda")
+    gout = torch.randn(lv.n, c, device="cuda")
+    res = {}
+    for fused in (False, True):
+        layer.fused = fused
+        for bn in (layer.linear_p[1], layer.linear_w[0], layer.linear_w[3]):   # same running stats for both runs
+            bn.running_mean.zero_().add_(0.05); bn.running_var.fill_(1.3)
+        layer.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        out = layer(lv, xi)
+        out.backward(gout)
+        torch.cuda.synchronize()
+        res[fused] = (out.detach(), xi.grad.detach(), {n: p.grad.detach().clone() for n, p in layer.named_parameters()},
+                      {n: b2.detach().clone() for n, b2 in layer.named_buffers() if b2.dtype.is_floating_point})
+    o0, gx0, gp0, bf0 = res[False]
+    o1, gx1, gp1, bf1 = res[True]
+    assert rel_err(o1, o0) < 2e-5, f"out {rel_err(o1, o0)}"
+    assert rel_err(gx1, gx0) < 2e-4, f"grad x {rel_err(gx1, gx0)}"
+    for name in gp0:
+        scale = gp0[name].abs().max()
+        if cases.grad_is_analytically_zero("transformer2." + name) or scale < 1e-6:
+            continue
+        assert rel_err(gp1[name], gp0[name]) < 5e-4, f"grad {name} {rel_err(gp1[name], gp0[name])}"
+    if training:
+        for name in bf0:
+            assert rel_err(bf1[name], bf0[name]) < 1e-4, f"buffer {name}"
