@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             for out in ex.map(run, jobs):
                 if verbose and out:
                     print(out)
-    if jobs or not os.path.exists(LIB):
+    if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 

@@ -48,7 +48,7 @@ class CBLConfig:
     ignore_label: int = 255
     contrast: Optional[ContrastCfg] = field(default_factory=ContrastCfg)
     multi: bool = True      # MultiHead(stage 'Ua', ftype latent, combine concat)
-    fused: bool = False
+    fused: bool = True
 
 
 # ------------------------------------------------------------------------------------------------
@@ -367,7 +367,7 @@ class ContrastHead(nn.Module):
     def __init__(self, cfg: CBLConfig):
         super().__init__()
         self.cfg = cfg
-        self.fused = cfg.fused
+        self.fused = False      # fused CBL kernel: see cbl.py (enabled by Loss when available)
 
     def subscene_labels(self, l, levels, target):
         """basic_operators.py:9-50: one-hot at level 0, mean one-hot of the kr nearest full-res points above."""

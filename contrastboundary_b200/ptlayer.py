@@ -83,6 +83,7 @@ class PtAttentionFn(Function):
                                       L.ptr(xk), L.ptr(xv), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf), L.ptr(gout),
                                       L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.stream())
         L.check(rc, "cb_pt_layer_backward")
+        PtAttentionFn.debug_last = (scratch, gbuf, bnbuf)
         grads, o = [], 0
         for sz, p in zip(sizes, params):
             grads.append(gbuf[o:o + sz].view_as(p))
