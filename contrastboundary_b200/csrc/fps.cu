@@ -13,7 +13,7 @@
 // is strictly greater (sampling_cuda_kernel.cu:5-10) — so the winner has the smallest
 // (bit-reverse_B(t), r / B).  We give every point that 32-bit priority and reduce
 // the pair (distance bits, ~priority) with max, which reproduces the rule under any reduction order.
-#include "common.cuh"
+#include "knn.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
 namespace cg = cooperative_groups;
@@ -134,6 +134,168 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) k_fps(const float *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bucket-pruned exact FPS (scenes whose running min-distance array fits in shared memory).
+//
+// The supports are first sorted by grid cell (the KNN grid of knn.cu), so 32 consecutive sorted
+// points form a spatially compact BUCKET with a small bounding box.  An iteration only has to touch
+// buckets whose box is closer to the new sample than the bucket's current maximum min-distance —
+// for every other bucket min(d, tmp) == tmp for all its points, so skipping them is exact.  After the
+// first few dozen samples only the handful of buckets around the new sample are touched, which turns
+// the reference's O(n) sweep per iteration into O(n / j).
+// One CTA of 32 warps per scene.  Bucket b is OWNED by lane (b/32)%32 of warp b%32 (slot b/1024): its
+// box, its current arg-max (distance bits, ~priority, coordinates, index) live in that lane's
+// registers; the min-distances live in shared memory.  Per iteration: register-only box tests ->
+// the warp refreshes its touched buckets (one 32-point load each) -> warp arg-max -> ONE
+// __syncthreads -> every warp reduces the 32 warp results.  Tie rule: see the header of this file.
+// ---------------------------------------------------------------------------------------------
+#define FPSB_SLOTS 2            // buckets per lane  -> up to 2048 buckets = 65536 points per scene
+#define FPSB_MAX_POINTS 49152   // 192 KB of min-distances in shared memory
+
+struct FpsSlot {
+    unsigned d, np;
+    float x, y, z;
+    int orig;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_fps_bucket(const float4 *__restrict__ sorted, const float *__restrict__ xyz,
+                                                        const int *__restrict__ offset, const int *__restrict__ new_offset,
+                                                        float *__restrict__ tmp, int *__restrict__ idx, int logB)
+{
+    extern __shared__ float md[];                          // running min distance, sorted order
+    __shared__ FpsSlot slots[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bid = blockIdx.x;
+    const int S0 = bid == 0 ? 0 : offset[bid - 1], S1 = offset[bid];
+    const int start_m = bid == 0 ? 0 : new_offset[bid - 1], end_m = new_offset[bid];
+    const int ns = S1 - S0;
+    if (ns <= 0 || end_m <= start_m) return;
+    const int Bref = 1 << logB;
+    const unsigned S = (unsigned)((ns + Bref - 1) >> logB);
+    const int nb = (ns + 31) >> 5;
+
+    float lox[FPSB_SLOTS], loy[FPSB_SLOTS], loz[FPSB_SLOTS], hix[FPSB_SLOTS], hiy[FPSB_SLOTS], hiz[FPSB_SLOTS];
+    unsigned bd[FPSB_SLOTS], bp[FPSB_SLOTS];
+    float bx[FPSB_SLOTS], by[FPSB_SLOTS], bz[FPSB_SLOTS];
+    int bo[FPSB_SLOTS];
+#pragma unroll
+    for (int t = 0; t < FPSB_SLOTS; t++) {
+        lox[t] = loy[t] = loz[t] = 3.0e38f; hix[t] = hiy[t] = hiz[t] = -3.0e38f;
+        bd[t] = 0u; bp[t] = 0u; bx[t] = by[t] = bz[t] = 0.f; bo[t] = S0;
+    }
+    auto priority = [&](int orig) -> unsigned {
+        const unsigned r = (unsigned)(orig - S0);
+        const unsigned tt = r & (unsigned)(Bref - 1);
+        const unsigned brev = logB ? (__brev(tt) >> (32 - logB)) : 0u;
+        return ~(brev * S + (r >> logB));
+    };
+    // refresh bucket b against sample (sx,sy,sz); with init=true also builds the box and loads tmp
+    auto refresh = [&](int b, int owner, int t, float sx, float sy, float sz, bool init) {
+        const int i = (b << 5) + lane;
+        const bool valid = i < ns;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) p = __ldg(sorted + S0 + i);
+        const int orig = __float_as_int(p.w);
+        float m;
+        if (init) {
+            m = valid ? tmp[orig] : 0.f;
+        } else {
+            const float d = cb_sqdist(p.x, p.y, p.z, sx, sy, sz);
+            m = valid ? fminf(d, md[i]) : 0.f;
+        }
+        if (valid) md[i] = m;
+        const unsigned db = valid ? __float_as_uint(fmaxf(m, 0.f)) : 0u;
+        const unsigned np = valid ? priority(orig) : 0u;
+        const unsigned wd = __reduce_max_sync(CB_FULL_MASK, db);
+        const unsigned wp = __reduce_max_sync(CB_FULL_MASK, db == wd ? np : 0u);
+        const int src = __ffs(__ballot_sync(CB_FULL_MASK, db == wd && np == wp)) - 1;
+        const float cx = __shfl_sync(CB_FULL_MASK, p.x, src), cy = __shfl_sync(CB_FULL_MASK, p.y, src),
+                    cz = __shfl_sync(CB_FULL_MASK, p.z, src);
+        const int co = __shfl_sync(CB_FULL_MASK, orig, src);
+        float mnx = 0, mny = 0, mnz = 0, mxx = 0, mxy = 0, mxz = 0;
+        if (init) {
+            const unsigned big = 0xffffffffu;
+            mnx = cb_ord2f(__reduce_min_sync(CB_FULL_MASK, valid ? cb_f2ord(p.x) : big));
+            mny = cb_ord2f(__reduce_min_sync(CB_FULL_MASK, valid ? cb_f2ord(p.y) : big));
+            mnz = cb_ord2f(__reduce_min_sync(CB_FULL_MASK, valid ? cb_f2ord(p.z) : big));
+            mxx = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.x) : 0u));
+            mxy = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.y) : 0u));
+            mxz = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.z) : 0u));
+        }
+        if (lane == owner) {
+#pragma unroll
+            for (int tt = 0; tt < FPSB_SLOTS; tt++)
+                if (tt == t) {
+                    bd[tt] = wd; bp[tt] = wp; bx[tt] = cx; by[tt] = cy; bz[tt] = cz; bo[tt] = co;
+                    if (init) { lox[tt] = mnx; loy[tt] = mny; loz[tt] = mnz; hix[tt] = mxx; hiy[tt] = mxy; hiz[tt] = mxz; }
+                }
+        }
+    };
+    // ---- init: every warp builds its own buckets: b = warp + 32 * (owner + 32 * t)
+#pragma unroll 1
+    for (int t = 0; t < FPSB_SLOTS; t++)
+#pragma unroll 1
+        for (int owner = 0; owner < 32; owner++) {
+            const int b = warp + 32 * (owner + 32 * t);
+            if (b < nb) refresh(b, owner, t, 0.f, 0.f, 0.f, true);
+        }
+    int old = S0;
+    float sx = __ldg(xyz + 3 * old), sy = __ldg(xyz + 3 * old + 1), sz = __ldg(xyz + 3 * old + 2);
+    if (tid == 0) idx[start_m] = old;                        // sampling_cuda_kernel.cu:39
+    for (int j = start_m + 1; j < end_m; j++) {
+        const int par = j & 1;
+        // 1. which of my buckets can change?  (box distance, with a 1e-4 safety margin for fp32 rounding)
+#pragma unroll
+        for (int t = 0; t < FPSB_SLOTS; t++) {
+            const float dx = fmaxf(fmaxf(lox[t] - sx, sx - hix[t]), 0.f), dy = fmaxf(fmaxf(loy[t] - sy, sy - hiy[t]), 0.f),
+                        dz = fmaxf(fmaxf(loz[t] - sz, sz - hiz[t]), 0.f);
+            const float lb = (dx * dx + dy * dy + dz * dz) * 0.9999f;
+            unsigned touched = __ballot_sync(CB_FULL_MASK, bd[t] != 0u && lb < __uint_as_float(bd[t]));
+            while (touched) {
+                const int owner = __ffs(touched) - 1;
+                touched &= touched - 1;
+                refresh(warp + 32 * (owner + 32 * t), owner, t, sx, sy, sz, false);
+            }
+        }
+        // 2. warp arg-max over the buckets its lanes own
+        unsigned md_ = bd[0], mp_ = bp[0];
+        int mt = 0;
+#pragma unroll
+        for (int t = 1; t < FPSB_SLOTS; t++)
+            if (bd[t] > md_ || (bd[t] == md_ && bp[t] > mp_)) { md_ = bd[t]; mp_ = bp[t]; mt = t; }
+        float mx = bx[0], my = by[0], mz = bz[0];
+        int mo = bo[0];
+#pragma unroll
+        for (int t = 1; t < FPSB_SLOTS; t++)
+            if (mt == t) { mx = bx[t]; my = by[t]; mz = bz[t]; mo = bo[t]; }
+        {
+            const unsigned wd = __reduce_max_sync(CB_FULL_MASK, md_);
+            const unsigned wp = __reduce_max_sync(CB_FULL_MASK, md_ == wd ? mp_ : 0u);
+            const int src = __ffs(__ballot_sync(CB_FULL_MASK, md_ == wd && mp_ == wp)) - 1;
+            if (lane == src) {
+                FpsSlot sl;
+                sl.d = wd; sl.np = wp; sl.x = mx; sl.y = my; sl.z = mz; sl.orig = mo;
+                slots[par][warp] = sl;
+            }
+        }
+        __syncthreads();
+        // 3. CTA arg-max (every warp redundantly)
+        {
+            const FpsSlot sl = slots[par][lane];
+            const unsigned wd = __reduce_max_sync(CB_FULL_MASK, sl.d);
+            const unsigned wp = __reduce_max_sync(CB_FULL_MASK, sl.d == wd ? sl.np : 0u);
+            const int src = __ffs(__ballot_sync(CB_FULL_MASK, sl.d == wd && sl.np == wp)) - 1;
+            sx = __shfl_sync(CB_FULL_MASK, sl.x, src); sy = __shfl_sync(CB_FULL_MASK, sl.y, src);
+            sz = __shfl_sync(CB_FULL_MASK, sl.z, src);
+            old = __shfl_sync(CB_FULL_MASK, sl.orig, src);
+        }
+        if (tid == 0) idx[j] = old;
+    }
+    // leave the running min-distance where the reference leaves it
+    __syncthreads();
+    for (int i = tid; i < ns; i += 1024) tmp[__float_as_int(__ldg(sorted + S0 + i).w)] = md[i];
+}
+
 template <int CL, int PPT>
 static cudaError_t launch_fps(int b, const float *xyz, const int *offset, const int *new_offset, float *tmp, int *idx,
                               int logB, cudaStream_t st)
@@ -182,5 +344,32 @@ extern "C" int cb_furthest_sampling(int b, int n_max, const float *xyz, const in
     }
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_furthest_sampling");
+    return CB_OK;
+}
+
+// Same operator with a caller-provided workspace (>= cb_knn_workspace_bytes(n, 0, b)): enables the
+// bucket-pruned kernel for scenes of 8192 < n_max <= 49152 points.
+extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n, const int *offset,
+                                       const int *new_offset, float *tmp, int *idx, void *workspace,
+                                       size_t workspace_bytes, void *stream)
+{
+    if (!workspace || n_max <= 8192 || n_max > FPSB_MAX_POINTS)
+        return cb_furthest_sampling(b, n_max, xyz, offset, new_offset, tmp, idx, stream);
+    CB_REQUIRE(b > 0 && n >= 0 && xyz && offset && new_offset && tmp && idx, CB_EINVAL, "cb_furthest_sampling_ws: bad arguments");
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, 0, b, workspace, &v);
+    CB_REQUIRE(workspace_bytes >= need, CB_EWORKSPACE, "cb_furthest_sampling_ws: workspace %zu < %zu", workspace_bytes, need);
+    CB_REQUIRE(((uintptr_t)workspace & 255) == 0, CB_EINVAL, "cb_furthest_sampling_ws: workspace not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cb_grid_build_impl(xyz, n, offset, b, 16, v, st);
+    if (rc) return rc;
+    int pow_2 = (int)(log((double)n_max) / log(2.0));
+    if (pow_2 > 10) pow_2 = 10;
+    if (pow_2 < 0) pow_2 = 0;
+    const size_t smem = (size_t)n_max * sizeof(float);
+    cudaFuncSetAttribute(k_fps_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fps_bucket<<<b, 1024, smem, st>>>(v.sorted, xyz, offset, new_offset, tmp, idx, pow_2);
+    CB_COUNT(1);
+    CB_CUDA_CHECK("cb_furthest_sampling_ws");
     return CB_OK;
 }

@@ -33,6 +33,14 @@ def _max_scene_len(offset_cpu):
     return n_max
 
 
+def _fps_call(b, n_max, xyz, offset, new_offset, tmp, idx):
+    n = xyz.shape[0]
+    ws = L.workspace(L.lib().cb_knn_workspace_bytes(n, 0, b), xyz.device, "knn")
+    rc = L.lib().cb_furthest_sampling_ws(C.c_int(b), C.c_int(n_max), L.ptr(xyz), C.c_int(n), L.ptr(offset), L.ptr(new_offset),
+                                         L.ptr(tmp), L.ptr(idx), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
+    L.check(rc, "cb_furthest_sampling_ws")
+
+
 class FurthestSampling(Function):
     @staticmethod
     def forward(ctx, xyz, offset, new_offset):
@@ -48,7 +56,7 @@ class FurthestSampling(Function):
         n_max = _max_scene_len(off_cpu)
         idx = torch.zeros(m, dtype=torch.int32, device=xyz.device)
         tmp = torch.full((n,), 1e10, dtype=torch.float32, device=xyz.device)
-        L.call("cb_furthest_sampling", b, n_max, xyz, offset.int(), new_offset.int(), tmp, idx, L.stream())
+        _fps_call(b, n_max, xyz, offset.int(), new_offset.int(), tmp, idx)
         return idx
 
 
@@ -60,7 +68,7 @@ def furthestsampling_known(xyz, offset, new_offset, n_max, m):
     """Same op when the host already knows n_max and m: no device->host sync."""
     idx = torch.empty(m, dtype=torch.int32, device=xyz.device)
     tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
-    L.call("cb_furthest_sampling", offset.shape[0], int(n_max), xyz, offset, new_offset, tmp, idx, L.stream())
+    _fps_call(offset.shape[0], int(n_max), xyz, offset, new_offset, tmp, idx)
     return idx
 
 

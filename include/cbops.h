@@ -87,6 +87,11 @@ int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n, const floa
  * ---------------------------------------------------------------------------------------------- */
 int cb_furthest_sampling(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
                          float *tmp, int *idx, void *stream);
+/* same results; with a workspace (>= cb_knn_workspace_bytes(n, 0, b), 256-byte aligned) scenes of
+ * 8192 < n_max <= 49152 points use the bucket-pruned kernel (grid-sorted supports, min-distances in
+ * shared memory, O(n/j) work in iteration j instead of O(n)). */
+int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n, const int *offset, const int *new_offset,
+                            float *tmp, int *idx, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a3  grouping                            replaces grouping_{forward,backward}_cuda_launcher
