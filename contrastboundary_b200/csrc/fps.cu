@@ -152,6 +152,9 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) k_fps(const float *__restrict_
 #define FPSB_SLOTS 2            // buckets per lane  -> up to 2048 buckets = 65536 points per scene
 #define FPSB_MAX_POINTS 49152   // 192 KB of min-distances in shared memory
 
+__device__ unsigned long long g_fps_dbg[8];   // [0] touched buckets, [1] iterations, [2] cycles (warp 0), [3] cycles in refresh (warp 0)
+__device__ int g_fps_dbg_on = 0;
+
 struct FpsSlot {
     unsigned d, np;
     float x, y, z;
@@ -242,6 +245,10 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket(const float4 *__restrict
     int old = S0;
     float sx = __ldg(xyz + 3 * old), sy = __ldg(xyz + 3 * old + 1), sz = __ldg(xyz + 3 * old + 2);
     if (tid == 0) idx[start_m] = old;                        // sampling_cuda_kernel.cu:39
+    const int dbg = g_fps_dbg_on;
+    long long t_start = 0, t_refresh = 0;
+    unsigned long long n_touched = 0;
+    if (dbg) t_start = clock64();
     for (int j = start_m + 1; j < end_m; j++) {
         const int par = j & 1;
         // 1. which of my buckets can change?  (box distance, with a 1e-4 safety margin for fp32 rounding)
@@ -251,11 +258,14 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket(const float4 *__restrict
                         dz = fmaxf(fmaxf(loz[t] - sz, sz - hiz[t]), 0.f);
             const float lb = (dx * dx + dy * dy + dz * dz) * 0.9999f;
             unsigned touched = __ballot_sync(CB_FULL_MASK, bd[t] != 0u && lb < __uint_as_float(bd[t]));
+            if (dbg) n_touched += __popc(touched);
+            const long long c0 = dbg ? clock64() : 0;
             while (touched) {
                 const int owner = __ffs(touched) - 1;
                 touched &= touched - 1;
                 refresh(warp + 32 * (owner + 32 * t), owner, t, sx, sy, sz, false);
             }
+            if (dbg) t_refresh += clock64() - c0;
         }
         // 2. warp arg-max over the buckets its lanes own
         unsigned md_ = bd[0], mp_ = bp[0];
@@ -290,6 +300,14 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket(const float4 *__restrict
             old = __shfl_sync(CB_FULL_MASK, sl.orig, src);
         }
         if (tid == 0) idx[j] = old;
+    }
+    if (dbg && lane == 0) {
+        atomicAdd(&g_fps_dbg[0], n_touched);
+        if (warp == 0 && bid == 0) {
+            g_fps_dbg[1] = (unsigned long long)(end_m - start_m - 1);
+            g_fps_dbg[2] = (unsigned long long)(clock64() - t_start);
+            g_fps_dbg[3] = (unsigned long long)t_refresh;
+        }
     }
     // leave the running min-distance where the reference leaves it
     __syncthreads();
@@ -372,4 +390,13 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_furthest_sampling_ws");
     return CB_OK;
+}
+
+extern "C" int cb_debug_fps(int enable, unsigned long long *out8)
+{
+    if (out8) cudaMemcpyFromSymbol(out8, g_fps_dbg, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_fps_dbg, z, sizeof(z));
+    cudaMemcpyToSymbol(g_fps_dbg_on, &enable, sizeof(int));
+    return 0;
 }

@@ -1,0 +1,61 @@
+"""Tall-skinny FP32 linear layers (cb_linear_forward / dgrad / wgrad) for the per-point MLPs.
+`Linear` is a drop-in nn.Linear (same parameters / state_dict) that routes large-n, narrow
+problems to libcbops and everything else to torch."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib as L
+
+MIN_ROWS = 8192        # below this cuBLAS is fine (and launch latency dominates anyway)
+MAX_CO = 512
+MAX_WGRAD = 8192       # ci*co handled by the custom wgrad kernel
+
+
+class _SkinnyLinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        n, ci = x.shape
+        co = weight.shape[0]
+        y = torch.empty((n, co), dtype=torch.float32, device=x.device)
+        L.call("cb_linear_forward", n, ci, co, x, weight, bias, y, L.stream())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        n, ci = x.shape
+        co = weight.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            L.call("cb_linear_dgrad", n, ci, co, g, weight, gx, L.stream())
+        if ctx.needs_input_grad[1]:
+            if ci * co <= MAX_WGRAD and co <= 256:
+                gw = torch.empty_like(weight)
+                gb = torch.empty(co, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                L.call("cb_linear_wgrad", n, ci, co, x, g, gw, gb, L.stream())
+            else:
+                gw = g.t().mm(x)
+                gb = g.sum(0) if ctx.has_bias else None
+        elif ctx.has_bias:
+            gb = g.sum(0)
+        return gx, gw, gb
+
+
+def fast_linear(x, weight, bias=None):
+    if (x.is_cuda and x.dtype == torch.float32 and weight.shape[0] <= MAX_CO and x.numel() // x.shape[-1] >= MIN_ROWS
+            and weight.is_contiguous()):
+        shp = x.shape
+        y = _SkinnyLinearFn.apply(x.reshape(-1, shp[-1]).contiguous(), weight, bias)
+        return y.view(*shp[:-1], weight.shape[0])
+    return F.linear(x, weight, bias)
+
+
+class Linear(nn.Linear):
+    def forward(self, x):
+        return fast_linear(x, self.weight, self.bias)

@@ -21,6 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointops
+from .linear_ops import Linear
 
 
 @dataclass
@@ -143,14 +144,14 @@ class PointTransformerLayer(nn.Module):
         self.out_planes = out_planes
         self.share_planes = share_planes
         self.nsample = nsample
-        self.linear_q = nn.Linear(in_planes, mid_planes)
-        self.linear_k = nn.Linear(in_planes, mid_planes)
-        self.linear_v = nn.Linear(in_planes, out_planes)
-        self.linear_p = nn.Sequential(nn.Linear(3, 3), nn.BatchNorm1d(3), nn.ReLU(inplace=True), nn.Linear(3, out_planes))
+        self.linear_q = Linear(in_planes, mid_planes)
+        self.linear_k = Linear(in_planes, mid_planes)
+        self.linear_v = Linear(in_planes, out_planes)
+        self.linear_p = nn.Sequential(Linear(3, 3), nn.BatchNorm1d(3), nn.ReLU(inplace=True), Linear(3, out_planes))
         self.linear_w = nn.Sequential(nn.BatchNorm1d(mid_planes), nn.ReLU(inplace=True),
-                                      nn.Linear(mid_planes, mid_planes // share_planes),
+                                      Linear(mid_planes, mid_planes // share_planes),
                                       nn.BatchNorm1d(mid_planes // share_planes), nn.ReLU(inplace=True),
-                                      nn.Linear(out_planes // share_planes, out_planes // share_planes))
+                                      Linear(out_planes // share_planes, out_planes // share_planes))
         self.fused = True
 
     def forward(self, lv, x):
@@ -182,9 +183,9 @@ class TransitionDown(nn.Module):
         super().__init__()
         self.stride, self.nsample = stride, nsample
         if stride != 1:
-            self.linear = nn.Linear(3 + in_planes, out_planes, bias=False)
+            self.linear = Linear(3 + in_planes, out_planes, bias=False)
         else:
-            self.linear = nn.Linear(in_planes, out_planes, bias=False)
+            self.linear = Linear(in_planes, out_planes, bias=False)
         self.bn = nn.BatchNorm1d(out_planes)
 
     def forward(self, x, prev_level=None, level=None):
@@ -203,11 +204,11 @@ class TransitionUp(nn.Module):
     def __init__(self, in_planes, out_planes=None):
         super().__init__()
         if out_planes is None:
-            self.linear1 = nn.Sequential(nn.Linear(2 * in_planes, in_planes), nn.BatchNorm1d(in_planes), nn.ReLU(inplace=True))
-            self.linear2 = nn.Sequential(nn.Linear(in_planes, in_planes), nn.ReLU(inplace=True))
+            self.linear1 = nn.Sequential(Linear(2 * in_planes, in_planes), nn.BatchNorm1d(in_planes), nn.ReLU(inplace=True))
+            self.linear2 = nn.Sequential(Linear(in_planes, in_planes), nn.ReLU(inplace=True))
         else:
-            self.linear1 = nn.Sequential(nn.Linear(out_planes, out_planes), nn.BatchNorm1d(out_planes), nn.ReLU(inplace=True))
-            self.linear2 = nn.Sequential(nn.Linear(in_planes, out_planes), nn.BatchNorm1d(out_planes), nn.ReLU(inplace=True))
+            self.linear1 = nn.Sequential(Linear(out_planes, out_planes), nn.BatchNorm1d(out_planes), nn.ReLU(inplace=True))
+            self.linear2 = nn.Sequential(Linear(in_planes, out_planes), nn.BatchNorm1d(out_planes), nn.ReLU(inplace=True))
 
     def forward(self, x1, level1, x2=None):
         if x2 is None:   # head of the decoder: concat the per-scene mean
@@ -226,11 +227,11 @@ class PointTransformerBlock(nn.Module):
 
     def __init__(self, in_planes, planes, share_planes=8, nsample=16):
         super().__init__()
-        self.linear1 = nn.Linear(in_planes, planes, bias=False)
+        self.linear1 = Linear(in_planes, planes, bias=False)
         self.bn1 = nn.BatchNorm1d(planes)
         self.transformer2 = PointTransformerLayer(planes, planes, share_planes, nsample)
         self.bn2 = nn.BatchNorm1d(planes)
-        self.linear3 = nn.Linear(planes, planes * self.expansion, bias=False)
+        self.linear3 = Linear(planes, planes * self.expansion, bias=False)
         self.bn3 = nn.BatchNorm1d(planes * self.expansion)
 
     def forward(self, lv, x):
@@ -246,7 +247,7 @@ class _LatentMLP(nn.Module):
 
     def __init__(self, fdim, d_out):
         super().__init__()
-        self.infer = nn.Sequential(nn.Linear(fdim, d_out), nn.BatchNorm1d(d_out), nn.ReLU(inplace=True))
+        self.infer = nn.Sequential(Linear(fdim, d_out), nn.BatchNorm1d(d_out), nn.ReLU(inplace=True))
 
     def forward(self, x):
         return self.infer(x)
@@ -258,7 +259,7 @@ class MultiHead(nn.Module):
     def __init__(self, fdims, cfg: CBLConfig):
         super().__init__()
         self.infer_list = nn.ModuleList([_LatentMLP(f, cfg.base_fdim) for f in fdims])
-        self.cls = nn.Linear(cfg.base_fdim * len(fdims), cfg.classes)
+        self.cls = Linear(cfg.base_fdim * len(fdims), cfg.classes)
 
     def forward(self, feats, levels):
         latents, collect = [], []
@@ -291,7 +292,7 @@ class PointTransformerSeg(nn.Module):
             self.cls = None
         else:
             self.head = None
-            self.cls = nn.Sequential(nn.Linear(pl[0], pl[0]), nn.BatchNorm1d(pl[0]), nn.ReLU(inplace=True), nn.Linear(pl[0], cfg.classes))
+            self.cls = nn.Sequential(Linear(pl[0], pl[0]), nn.BatchNorm1d(pl[0]), nn.ReLU(inplace=True), Linear(pl[0], cfg.classes))
         self.set_fused(cfg.fused)
 
     def set_fused(self, flag):
@@ -367,7 +368,7 @@ class ContrastHead(nn.Module):
     def __init__(self, cfg: CBLConfig):
         super().__init__()
         self.cfg = cfg
-        self.fused = False      # fused CBL kernel: see cbl.py (enabled by Loss when available)
+        self.fused = cfg.fused
 
     def subscene_labels(self, l, levels, target):
         """basic_operators.py:9-50: one-hot at level 0, mean one-hot of the kr nearest full-res points above."""

@@ -156,6 +156,30 @@ int cb_pt_layer_forward(int n, int k, int c, const CbPtLayer *L, const float *re
                         const int *idx, const float *xq, const float *xk, const float *xv, float *out,
                         float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * a9  fused contrastive-boundary loss of one stage        replaces ContrastHead.point_contrast
+ *     pytorch/model/heads.py:185-246 (+ dist_l2 :116-119, posmask_cnt :145-149, contrast_softnn
+ *     :151-165) and the sub-scene label propagation of pytorch/model/basic_operators.py:9-50.
+ * cb_cbl_classes: cls[i] = target[i] (label_idx NULL) or the arg-max class among the kr nearest
+ *   full-resolution labels target[label_idx[i,:]] (first maximum).  target is int64 as in torch.
+ * cb_cbl_forward : sums[0] += sum of loss_i over boundary points, sums[1] += their count (sums zeroed by the caller);
+ *   idx (m,K) int32 with column 0 = the point itself (dropped as heads.py:196); d in {32,64,72}; K <= 65.
+ * cb_cbl_backward: grad_feat (m,d), zero-filled by the caller, += scale[0] * d(sum loss_i)/d feat.
+ * ---------------------------------------------------------------------------------------------- */
+int cb_cbl_classes(int m, int kr, int ncls, const int *label_idx, const long long *target, int *cls, void *stream);
+int cb_cbl_forward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                   float *sums, void *stream);
+int cb_cbl_backward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                    const float *scale, float *grad_feat, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tall-skinny FP32 linear layers of the per-point MLPs (nn.Linear calls of blocks.py:33,72,76,108,
+ * 127-131 and the heads' MLPs): Y = X W^T + b ; dX = G W ; dW = G^T X, db = sum G (dW/db overwritten).
+ * ---------------------------------------------------------------------------------------------- */
+int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream);
+int cb_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, void *stream);
+int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, void *stream);
+
 /* backward of cb_pt_layer_forward.  grad_xk / grad_xv (n,c) and grad_params must be ZERO-FILLED by the
  * caller (scatter / accumulation targets); grad_xq is overwritten.  grad_params layout (floats):
  * [dW1 9][db1 3][dbn1_w 3][dbn1_b 3][dW2 3c][db2 c][dbn2_w c][dbn2_b c][dW3 c*c/8][db3 c/8][dbn3_w c/8]

@@ -82,3 +82,26 @@ def test_train_step_runs_and_updates():
     l2 = ts.step(batch)
     assert torch.isfinite(l1).all() and torch.isfinite(l2).all()
     assert not torch.equal(w0, ts.model.head.cls.weight.detach())
+
+
+def test_fused_cbl_matches_unfused():
+    """fused CBL stage loss (cb_cbl_*) vs the op-by-op torch path of ContrastHead (heads.py math)"""
+    from contrastboundary_b200 import engine, model, synthetic
+    cfg = model.CBLConfig()
+    hb = engine.host_batch_from_numpy(synthetic.make_batch(2, [4096, 2500], 17), pin=False)
+    batch = engine.to_device(hb, torch.device("cuda"))
+    levels = model.build_geometry(batch["points"], batch["offset"], batch["offset_host"], cfg, True)
+    head = model.ContrastHead(cfg)
+    torch.manual_seed(0)
+    for l in range(5):
+        lat = torch.randn(levels[l].n, cfg.base_fdim, device="cuda")
+        res = {}
+        for fused in (False, True):
+            head.fused = fused
+            x = lat.clone().requires_grad_(True)
+            loss = head.stage_loss(l, levels, x, batch["point_labels"])
+            loss.backward()
+            res[fused] = (float(loss), x.grad.clone())
+        assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0]) + 1e-9, (l, res[True][0], res[False][0])
+        ref = res[False][1]
+        assert float((res[True][1] - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-12, l

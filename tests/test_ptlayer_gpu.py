@@ -81,3 +81,27 @@ def test_fused_layer_matches_unfused(c, k, n_list, training):
     if training:
         for name in bf0:
             assert rel_err(bf1[name], bf0[name]) < 1e-4, f"buffer {name}"
+
+
+@pytest.mark.parametrize("n,ci,co,bias", [(20000, 32, 32, True), (163840, 6, 32, False), (50000, 35, 64, False),
+                                         (16384, 67, 128, False), (30000, 160, 13, True), (9000, 131, 256, False)])
+def test_skinny_linear(n, ci, co, bias):
+    from contrastboundary_b200 import linear_ops
+    torch.manual_seed(n % 97)
+    x = torch.randn(n, ci, device="cuda", requires_grad=True)
+    w = (torch.randn(co, ci, device="cuda") / ci ** 0.5).requires_grad_(True)
+    b = torch.randn(co, device="cuda", requires_grad=True) if bias else None
+    g = torch.randn(n, co, device="cuda")
+    y = linear_ops.fast_linear(x, w, b)
+    y.backward(g)
+    got = (y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone() if bias else None)
+    x.grad = None; w.grad = None
+    if bias:
+        b.grad = None
+    yr = torch.nn.functional.linear(x.double(), w.double(), b.double() if bias else None)
+    yr.backward(g.double())
+    assert rel_err(got[0], yr.float()) < 1e-5
+    assert rel_err(got[1], x.grad.float()) < 1e-5
+    assert rel_err(got[2], w.grad.float()) < 1e-4
+    if bias:
+        assert rel_err(got[3], b.grad.float()) < 1e-4
