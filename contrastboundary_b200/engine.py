@@ -20,7 +20,8 @@ class TrainStep:
             from torch.nn.parallel import DistributedDataParallel as DDP
             self.net = DDP(self.model, device_ids=[self.device.index], gradient_as_bucket_view=True)
         # reference optimiser: SGD(lr=base_lr, momentum, weight_decay) (train.py:154)
-        self.opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                   fused=self.device.type == "cuda")
         self.model.train()
 
     def step(self, batch, update=True):
