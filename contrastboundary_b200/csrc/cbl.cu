@@ -49,7 +49,8 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(CBL_THREADS) k_cbl(int m, int K, const float *__restrict__ feat,
                                                      const int *__restrict__ idx, const int *__restrict__ cls,
                                                      float inv_t, float *__restrict__ sums,
-                                                     const float *__restrict__ scale_ptr, float *__restrict__ gfeat)
+                                                     const float *__restrict__ scale_ptr, float *__restrict__ gfeat,
+                                                     int n_valid, int flavour)
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warps = gridDim.x * (CBL_THREADS / 32);
@@ -58,20 +59,25 @@ __global__ void __launch_bounds__(CBL_THREADS) k_cbl(int m, int K, const float *
     const float scale = MODE == 1 ? __ldg(scale_ptr) : 0.f;
     for (int i = blockIdx.x * (CBL_THREADS / 32) + wib; i < m; i += warps) {
         const int ci = __ldg(cls + i);
-        // pass 1: positives count (cheap) -> skip non-boundary points before touching features
-        int npos = 0;
+        // pass 1: positives / negatives among VALID neighbours (cheap) -> skip non-boundary points early
+        int npos = 0, nneg = 0;
         for (int k0 = 0; k0 < nk; k0 += 32) {
             const int k = k0 + lane;
-            bool pos = false;
-            if (k < nk) pos = __ldg(cls + __ldg(idx + (size_t)i * K + 1 + k)) == ci;
+            bool pos = false, ok = false;
+            if (k < nk) {
+                const int j = __ldg(idx + (size_t)i * K + 1 + k);
+                ok = j < n_valid;                                    // shadow neighbours (TF radius search) are invalid
+                if (ok) pos = __ldg(cls + j) == ci;
+            }
             npos += __popc(__ballot_sync(CB_FULL_MASK, pos));
+            nneg += __popc(__ballot_sync(CB_FULL_MASK, ok && !pos));
         }
-        if (!(npos > 0 && npos < nk)) continue;                     // heads.py:213-214
+        if (!(npos > 0 && nneg > 0)) continue;                      // heads.py:213-214 / head.py:641-662
         float f[D];
         cbl_load_row<D>(feat + (size_t)i * D, f);
         // per-lane neighbour state for up to 2 rounds (K-1 <= 64)
         float dist[2], e[2];
-        bool posm[2], val[2];
+        bool posm[2], val[2], clampd[2] = {false, false};
         int nb[2];
         float mx = -3.0e38f;
 #pragma unroll
@@ -79,13 +85,15 @@ __global__ void __launch_bounds__(CBL_THREADS) k_cbl(int m, int K, const float *
             const int k = r * 32 + lane;
             val[r] = k < nk;
             nb[r] = val[r] ? __ldg(idx + (size_t)i * K + 1 + k) : i;
+            if (nb[r] >= n_valid) { val[r] = false; nb[r] = i; }
             posm[r] = val[r] && (__ldg(cls + nb[r]) == ci);
             float g[D];
             cbl_load_row<D>(feat + (size_t)nb[r] * D, g);
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < D; c++) { const float t = f[c] - g[c]; s = fmaf(t, t, s); }
-            dist[r] = sqrtf(s + CBL_EPS);
+            dist[r] = flavour == 0 ? sqrtf(s + CBL_EPS) : sqrtf(fmaxf(s, CBL_EPS));   // heads.py:116-119 / head.py:183-185
+            if (flavour == 1 && s < CBL_EPS) clampd[r] = true;
             if (val[r]) mx = fmaxf(mx, -dist[r]);
         }
 #pragma unroll
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(CBL_THREADS) k_cbl(int m, int K, const float *
             for (int r = 0; r < 2; r++) {
                 if (!val[r]) continue;
                 const float ddist = outer * e[r] * ((posm[r] ? neg : 0.f) - pos);
-                const float coef = ddist / dist[r];              // d dist / d s = 1/(2 dist); d s / d f = 2 (f - g)
+                const float coef = clampd[r] ? 0.f : ddist / dist[r];   // d dist / d s = 1/(2 dist); d s / d f = 2 (f - g); max() clamps -> 0
                 float g[D];
                 cbl_load_row<D>(feat + (size_t)nb[r] * D, g);
                 float *dst = gfeat + (size_t)nb[r] * D;
@@ -161,16 +169,16 @@ extern "C" int cb_cbl_classes(int m, int kr, int ncls, const int *label_idx, con
 
 template <int MODE>
 static int cbl_launch(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
-                      float *sums, const float *scale, float *gfeat, cudaStream_t st)
+                      float *sums, const float *scale, float *gfeat, int n_valid, int flavour, cudaStream_t st)
 {
     int grid = (m + CBL_THREADS / 32 - 1) / (CBL_THREADS / 32);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
     const float inv_t = 1.0f / temperature;
     switch (D) {
-    case 32: k_cbl<32, MODE><<<grid, CBL_THREADS, 0, st>>>(m, K, feat, idx, cls, inv_t, sums, scale, gfeat); break;
-    case 64: k_cbl<64, MODE><<<grid, CBL_THREADS, 0, st>>>(m, K, feat, idx, cls, inv_t, sums, scale, gfeat); break;
-    case 72: k_cbl<72, MODE><<<grid, CBL_THREADS, 0, st>>>(m, K, feat, idx, cls, inv_t, sums, scale, gfeat); break;
+    case 32: k_cbl<32, MODE><<<grid, CBL_THREADS, 0, st>>>(m, K, feat, idx, cls, inv_t, sums, scale, gfeat, n_valid, flavour); break;
+    case 64: k_cbl<64, MODE><<<grid, CBL_THREADS, 0, st>>>(m, K, feat, idx, cls, inv_t, sums, scale, gfeat, n_valid, flavour); break;
+    case 72: k_cbl<72, MODE><<<grid, CBL_THREADS, 0, st>>>(m, K, feat, idx, cls, inv_t, sums, scale, gfeat, n_valid, flavour); break;
     default:
         cb_set_error("cb_cbl: feature dim %d unsupported (32, 64, 72)", D);
         return CB_EUNSUPPORTED;
@@ -178,26 +186,41 @@ static int cbl_launch(int m, int K, int D, const float *feat, const int *idx, co
     return CB_OK;
 }
 
+extern "C" int cb_cbl_forward_ex(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                                 float *sums, int n_valid, int flavour, void *stream);
+extern "C" int cb_cbl_backward_ex(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                                  const float *scale, float *grad_feat, int n_valid, int flavour, void *stream);
 extern "C" int cb_cbl_forward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
                               float *sums, void *stream)
+{
+    return cb_cbl_forward_ex(m, K, D, feat, idx, cls, temperature, sums, 0x7fffffff, 0, stream);
+}
+extern "C" int cb_cbl_backward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                               const float *scale, float *grad_feat, void *stream)
+{
+    return cb_cbl_backward_ex(m, K, D, feat, idx, cls, temperature, scale, grad_feat, 0x7fffffff, 0, stream);
+}
+
+extern "C" int cb_cbl_forward_ex(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                                 float *sums, int n_valid, int flavour, void *stream)
 {
     CB_REQUIRE(m >= 0 && K >= 2 && K <= 65 && feat && idx && cls && sums && temperature > 0.f, CB_EINVAL,
                "cb_cbl_forward: bad arguments (2 <= K <= 65)");
     if (m == 0) return CB_OK;
-    int rc = cbl_launch<0>(m, K, D, feat, idx, cls, temperature, sums, nullptr, nullptr, (cudaStream_t)stream);
+    int rc = cbl_launch<0>(m, K, D, feat, idx, cls, temperature, sums, nullptr, nullptr, n_valid, flavour, (cudaStream_t)stream);
     if (rc) return rc;
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_cbl_forward");
     return CB_OK;
 }
 
-extern "C" int cb_cbl_backward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
-                               const float *scale, float *grad_feat, void *stream)
+extern "C" int cb_cbl_backward_ex(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                                  const float *scale, float *grad_feat, int n_valid, int flavour, void *stream)
 {
     CB_REQUIRE(m >= 0 && K >= 2 && K <= 65 && feat && idx && cls && scale && grad_feat && temperature > 0.f, CB_EINVAL,
                "cb_cbl_backward: bad arguments");
     if (m == 0) return CB_OK;
-    int rc = cbl_launch<1>(m, K, D, feat, idx, cls, temperature, nullptr, scale, grad_feat, (cudaStream_t)stream);
+    int rc = cbl_launch<1>(m, K, D, feat, idx, cls, temperature, nullptr, scale, grad_feat, n_valid, flavour, (cudaStream_t)stream);
     if (rc) return rc;
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_cbl_backward");

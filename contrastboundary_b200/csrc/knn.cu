@@ -106,10 +106,16 @@ __global__ void k_bbox(const float *__restrict__ xyz, int n, const int *__restri
     }
 }
 
-__device__ __forceinline__ float cb_target_occ(int nsample)
+static float g_occ_factor = 0.45f;   // points per occupied cell = factor * K (tuning knob, cb_knn_set_occupancy)
+extern "C" float cb_knn_set_occupancy(float f)
+{
+    if (f > 0.05f && f < 4.f) g_occ_factor = f;
+    return g_occ_factor;
+}
+__device__ __forceinline__ float cb_target_occ(int nsample, float factor)
 {
     // points per occupied cell that makes the 3x3x3 block hold the K nearest for most queries
-    return fminf(fmaxf(0.45f * (float)nsample, 2.0f), 48.0f);
+    return fminf(fmaxf(factor * (float)nsample, 2.0f), 48.0f);
 }
 
 // dims for cell size h; returns number of cells
@@ -124,9 +130,9 @@ __device__ __forceinline__ long long cb_dims(float ex, float ey, float ez, float
 
 // phase 0: trial grid from the bbox-volume heuristic; phase 1: final grid from measured occupancy
 __global__ void k_params(CbGridHeader *hdr, CbScene *scenes, const unsigned *bbox, const int *occ,
-                         const int *__restrict__ offset, int b, int n, int nsample, int cap, int phase)
+                         const int *__restrict__ offset, int b, int n, int nsample, int cap, int phase, float occ_factor)
 {
-    const float target = cb_target_occ(nsample);
+    const float target = cb_target_occ(nsample, occ_factor);
     for (int s = threadIdx.x; s < b; s += blockDim.x) {
         CbScene sc;
         sc.start = s == 0 ? 0 : offset[s - 1];
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
                                                    const CbScene *__restrict__ scenes, const int *__restrict__ cells,
                                                    const float4 *__restrict__ sorted, int *__restrict__ idx,
                                                    float *__restrict__ dist2, int sqrt_dist, CbGridHeader *hdr,
-                                                   int *flagged)
+                                                   int *flagged, int dist_mode, float r2, int pad_idx)
 {
     __shared__ CbWarpScratch scratch[4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -309,10 +315,10 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
     }
     const int s = cb_scene_of(q, new_offset, b);
     const CbScene sc = scenes[s];
-    CbTopK<KPL> tk;
+    typename CbTopKSel<KPL>::type tk;
     tk.init(K, lane, sc.start);
-    bool ok = cb_grid_search<KPL>(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
-    if (ok && tk.has_tie()) ok = false;
+    bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane, dist_mode);
+    if (ok && dist_mode == 0 && tk.has_tie()) ok = false;
     if (!ok) {
         if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
         return;
@@ -321,8 +327,12 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
     for (int j = 0; j < KPL; j++) {
         const int e = j * 32 + lane;
         if (e < K) {
-            idx[(size_t)q * K + e] = tk.i[j];
-            dist2[(size_t)q * K + e] = sqrt_dist ? __fsqrt_rn(tk.d[j]) : tk.d[j];
+            if (dist_mode == 0) {
+                idx[(size_t)q * K + e] = tk.out_i(j);
+                dist2[(size_t)q * K + e] = sqrt_dist ? __fsqrt_rn(tk.out_d(j)) : tk.out_d(j);
+            } else {
+                idx[(size_t)q * K + e] = tk.out_d(j) < r2 ? tk.out_i(j) : pad_idx;
+            }
         }
     }
 }
@@ -346,7 +356,8 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
                                                                  const int *__restrict__ new_offset, int b,
                                                                  int *__restrict__ idx, float *__restrict__ dist2,
                                                                  int sqrt_dist, const CbGridHeader *hdr,
-                                                                 const int *__restrict__ flagged)
+                                                                 const int *__restrict__ flagged, int dist_mode, float r2,
+                                                                 int pad_idx)
 {
     extern __shared__ unsigned char smem_raw[];
     float *hd = (float *)smem_raw;                     // K
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
             for (int u = 0; u < CB_REPLAY_PER_THREAD; u++) {
                 const int i = i0 + u;
                 d[u] = 3.0e38f;
-                if (i < end) d[u] = cb_sqdist(qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+                if (i < end) d[u] = cb_sqdist_mode(dist_mode, qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
                 npass += d[u] < root;
             }
             // block exclusive scan of npass (thread order == index order)
@@ -428,8 +439,12 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
         }
         __syncthreads();
         for (int k = t; k < K; k += CB_REPLAY_THREADS) {
-            idx[(size_t)q * K + k] = hi[k];
-            dist2[(size_t)q * K + k] = sqrt_dist ? __fsqrt_rn(hd[k]) : hd[k];
+            if (dist_mode == 0) {
+                idx[(size_t)q * K + k] = hi[k];
+                dist2[(size_t)q * K + k] = sqrt_dist ? __fsqrt_rn(hd[k]) : hd[k];
+            } else {
+                idx[(size_t)q * K + k] = hd[k] < r2 ? hi[k] : pad_idx;
+            }
         }
         __syncthreads();
     }
@@ -457,12 +472,12 @@ int cb_grid_build_impl(const float *xyz, int n, const int *offset, int b, int ns
     k_bbox_init<<<ib, 128, 0, st>>>(v.bbox, v.occ, b, v.hdr, n);
     if (n > 0) k_bbox<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.bbox);
     // trial grid
-    k_params<<<1, 128, 0, st>>>(v.hdr, v.scenes, v.bbox, v.occ, offset, b, n, nsample_hint, v.trial_cap, 0);
+    k_params<<<1, 128, 0, st>>>(v.hdr, v.scenes, v.bbox, v.occ, offset, b, n, nsample_hint, v.trial_cap, 0, g_occ_factor);
     k_zero_cells<<<148, 256, 0, st>>>(v.cells, v.coarse, v.hdr, 1);
     if (n > 0) k_count<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.scenes, v.cells, v.coarse, v.occ,
                                                              v.point_cell, v.point_rank, 1);
     // final grid
-    k_params<<<1, 128, 0, st>>>(v.hdr, v.scenes, v.bbox, v.occ, offset, b, n, nsample_hint, v.cell_cap, 1);
+    k_params<<<1, 128, 0, st>>>(v.hdr, v.scenes, v.bbox, v.occ, offset, b, n, nsample_hint, v.cell_cap, 1, g_occ_factor);
     k_zero_cells<<<148 * 2, 256, 0, st>>>(v.cells, v.coarse, v.hdr, 0);
     if (n > 0) k_count<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.scenes, v.cells, v.coarse, v.occ,
                                                              v.point_cell, v.point_rank, 0);
@@ -502,7 +517,32 @@ void cb_knn_replay_launch(int K, int m, const float *xyz, const float *new_xyz, 
     const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
     const int rblocks = K <= 256 ? 148 : (m < 148 * 8 ? (m > 0 ? m : 1) : 148 * 8);
     k_knn_replay<<<rblocks, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, dist2,
-                                                           sqrt_dist, v.hdr, v.flagged);
+                                                           sqrt_dist, v.hdr, v.flagged, 0, 0.f, 0);
+}
+
+int cb_knn_query_radius_impl(int m, int K, const float *xyz, int n, const float *new_xyz, const int *offset,
+                             const int *new_offset, int b, int *idx, float r2, int pad_idx, const CbGridView &v,
+                             cudaStream_t st)
+{
+    if (m == 0 || K == 0) return CB_OK;
+    CB_REQUIRE(K <= 256, CB_EUNSUPPORTED, "radius neighbours: row width %d > 256 unsupported", K);
+    const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
+    const int blocks = (m + 3) / 4;
+    k_reset_flagged<<<1, 1, 0, st>>>(v.hdr);
+#define CB_LAUNCH_R(KPL)                                                                                          \
+    k_knn_query<KPL><<<blocks, 128, 0, st>>>(m, K, new_xyz, new_offset, b, self_query, v.scenes, v.cells, v.sorted, \
+                                              idx, nullptr, 0, v.hdr, v.flagged, 1, r2, pad_idx)
+    if (K <= 32) CB_LAUNCH_R(1);
+    else if (K <= 64) CB_LAUNCH_R(2);
+    else if (K <= 128) CB_LAUNCH_R(4);
+    else CB_LAUNCH_R(8);
+#undef CB_LAUNCH_R
+    const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
+    k_knn_replay<<<148, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, nullptr, 0, v.hdr,
+                                                       v.flagged, 1, r2, pad_idx);
+    CB_COUNT(3);
+    CB_CUDA_CHECK("cb_batch_radius_neighbors");
+    return CB_OK;
 }
 
 void cb_knn_reset_flagged(const CbGridView &v, cudaStream_t st) { k_reset_flagged<<<1, 1, 0, st>>>(v.hdr); }
@@ -518,7 +558,7 @@ static int query_impl(int m, int K, const float *xyz, int n, const float *new_xy
         k_reset_flagged<<<1, 1, 0, st>>>(v.hdr);
 #define CB_LAUNCH_Q(KPL)                                                                                          \
     k_knn_query<KPL><<<blocks, 128, 0, st>>>(m, K, new_xyz, new_offset, b, self_query, v.scenes, v.cells, v.sorted, \
-                                              idx, dist2, sqrt_dist, v.hdr, v.flagged)
+                                              idx, dist2, sqrt_dist, v.hdr, v.flagged, 0, 0.f, 0)
         if (K <= 32) CB_LAUNCH_Q(1);
         else if (K <= 64) CB_LAUNCH_Q(2);
         else if (K <= 128) CB_LAUNCH_Q(4);

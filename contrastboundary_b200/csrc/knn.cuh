@@ -49,6 +49,13 @@ void cb_knn_replay_launch(int K, int m, const float *xyz, const float *new_xyz, 
                           const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, const CbGridView &v,
                           cudaStream_t st);
 void cb_knn_reset_flagged(const CbGridView &v, cudaStream_t st);
+// radius flavour of the query (TF batch_ordered_neighbors): nanoflann distance arithmetic, entries with
+// d2 >= r2 replaced by pad_idx, ties left in search order (the reference's std::sort leaves them unspecified)
+int cb_knn_query_radius_impl(int m, int K, const float *xyz, int n, const float *new_xyz, const int *offset,
+                             const int *new_offset, int b, int *idx, float r2, int pad_idx, const CbGridView &v,
+                             cudaStream_t st);
+__global__ void k_bbox_init(unsigned *bbox, int *occ, int b, CbGridHeader *hdr, int n);
+__global__ void k_bbox(const float *__restrict__ xyz, int n, const int *__restrict__ offset, int b, unsigned *bbox);
 
 // ---------------------------------------------------------------------------------------------
 // Warp-resident sorted top-K list: entry e = j*32 + lane lives in register j of lane `lane`.
@@ -121,6 +128,9 @@ struct CbTopK {
         }
     }
 
+    __device__ __forceinline__ float out_d(int j) const { return d[j]; }
+    __device__ __forceinline__ int out_i(int j) const { return i[j]; }
+
     // true if the reference's result for this query may depend on its heap mechanics
     __device__ __forceinline__ bool has_tie() const
     {
@@ -141,19 +151,201 @@ struct CbTopK {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Bitonic variant for K <= 64: the list holds the 32*KPL smallest (d2, idx) keys seen so far as
+// 64-bit keys (d2 >= 0, so its float bits order like an unsigned int).  A batch of 32 candidates is
+// pre-filtered against the (K+1)-th smallest, and the survivors are either inserted one by one (few)
+// or warp-sorted with a 15-stage bitonic network and merged with the list (many): ~130 instructions
+// per batch however many candidates enter, instead of ~25 per inserted candidate.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long cb_key;
+#define CB_KEY_INF 0xffffffffffffffffull
+
+__device__ __forceinline__ cb_key cb_make_key(float d, int i) { return ((cb_key)__float_as_uint(d) << 32) | (unsigned)i; }
+__device__ __forceinline__ float cb_key_d(cb_key k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ int cb_key_i(cb_key k) { return (int)(unsigned)(k & 0xffffffffu); }
+__device__ __forceinline__ cb_key cb_shfl_key(cb_key k, int src)
+{
+    return ((cb_key)__shfl_sync(CB_FULL_MASK, (unsigned)(k >> 32), src) << 32) | __shfl_sync(CB_FULL_MASK, (unsigned)k, src);
+}
+__device__ __forceinline__ cb_key cb_shfl_xor_key(cb_key k, int m)
+{
+    return ((cb_key)__shfl_xor_sync(CB_FULL_MASK, (unsigned)(k >> 32), m) << 32) | __shfl_xor_sync(CB_FULL_MASK, (unsigned)k, m);
+}
+// Compare-exchange networks on (d bits, idx) pairs.  Only the distance is compared; on equal distances
+// both lanes keep their own element (ties are re-done by the exact replay anyway), which keeps the
+// multiset intact with a single 32-bit compare per stage.
+__device__ __forceinline__ void cb_cmpx(unsigned &d, unsigned &i, int j, bool keep_min)
+{
+    const unsigned pd = __shfl_xor_sync(CB_FULL_MASK, d, j), pi = __shfl_xor_sync(CB_FULL_MASK, i, j);
+    const bool take = keep_min ? (pd < d) : (pd > d);
+    d = take ? pd : d;
+    i = take ? pi : i;
+}
+// ascending bitonic merge of a bitonic 32-sequence held one key per lane
+__device__ __forceinline__ cb_key cb_bitonic_merge32(cb_key k, int lane)
+{
+    unsigned d = (unsigned)(k >> 32), i = (unsigned)k;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) cb_cmpx(d, i, j, (lane & j) == 0);
+    return ((cb_key)d << 32) | i;
+}
+// full ascending bitonic sort of 32 keys
+__device__ __forceinline__ cb_key cb_bitonic_sort32(cb_key k, int lane)
+{
+    unsigned d = (unsigned)(k >> 32), i = (unsigned)k;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+        const bool up = size == 32 ? true : ((lane & size) == 0);
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) cb_cmpx(d, i, j, ((lane & j) == 0) == up);
+    }
+    return ((cb_key)d << 32) | i;
+}
+
+template <int KPL>
+struct CbTopKB {
+    cb_key key[KPL];    // entry e = j*32 + lane, ascending
+    float kth;          // K-th smallest d2 (entry K-1), uniform
+    float thr;          // pre-filter threshold: (K+1)-th smallest (entry min(K, 32*KPL-1))
+    float tie_val;      // only needed when K == 32*KPL: a dropped / evicted value equal to the then-last entry
+    int K, lane, cap_e;
+
+    __device__ __forceinline__ void init(int K_, int lane_, int pad_idx)
+    {
+        K = K_; lane = lane_;
+        cap_e = K < 32 * KPL - 1 ? K : 32 * KPL - 1;
+#pragma unroll
+        for (int j = 0; j < KPL; j++) key[j] = cb_make_key(1e10f, pad_idx);
+        kth = 1e10f; thr = 1e10f; tie_val = -1.f;
+    }
+    __device__ __forceinline__ cb_key entry(int e) const
+    {
+        cb_key v = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; j++) {
+            const cb_key t = cb_shfl_key(key[j], e & 31);
+            if ((e >> 5) == j) v = t;
+        }
+        return v;
+    }
+    __device__ __forceinline__ void refresh_thresholds()
+    {
+        kth = cb_key_d(entry(K - 1));
+        thr = cb_key_d(entry(cap_e));
+    }
+    // sorted insertion of one key (uniform across the warp), shifting the tail right by one
+    __device__ __forceinline__ void insert(cb_key c)
+    {
+        int p = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; j++) p += __popc(__ballot_sync(CB_FULL_MASK, (unsigned)(key[j] >> 32) <= (unsigned)(c >> 32)));
+#pragma unroll
+        for (int j = KPL - 1; j >= 0; j--) {
+            cb_key up = ((cb_key)__shfl_up_sync(CB_FULL_MASK, (unsigned)(key[j] >> 32), 1) << 32) |
+                        __shfl_up_sync(CB_FULL_MASK, (unsigned)key[j], 1);
+            if (j > 0) {
+                const cb_key w = cb_shfl_key(key[j - 1], 31);
+                if (lane == 0) up = w;
+            }
+            const int e = j * 32 + lane;
+            if (e > p) key[j] = up;
+            else if (e == p) key[j] = c;
+        }
+    }
+    __device__ __forceinline__ void offer(bool valid, float cd, int ci)
+    {
+        if (K == 32 * KPL) {   // no spare entry: remember candidates dropped with equality to the last entry
+            if (__ballot_sync(CB_FULL_MASK, valid && cd == thr)) tie_val = thr;
+        }
+        unsigned pass = __ballot_sync(CB_FULL_MASK, valid && cd < thr);
+        if (!pass) return;
+        cb_key c = (valid && cd < thr) ? cb_make_key(cd, ci) : CB_KEY_INF;
+        if (__popc(pass) <= 5) {
+            while (pass) {
+                const int src = __ffs(pass) - 1;
+                pass &= pass - 1;
+                if (K == 32 * KPL) {        // the evicted entry is the current last one
+                    const float old_last = cb_key_d(entry(32 * KPL - 1));
+                    insert(cb_shfl_key(c, src));
+                    if (cb_key_d(entry(32 * KPL - 1)) == old_last) tie_val = old_last;
+                } else {
+                    insert(cb_shfl_key(c, src));
+                }
+            }
+        } else {
+            c = cb_bitonic_sort32(c, lane);
+            // merge into register 0, carry the upper half into the next register
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const cb_key r = cb_shfl_key(c, 31 - lane);
+                const bool r_less = (unsigned)(r >> 32) < (unsigned)(key[j] >> 32);
+                const cb_key lo = r_less ? r : key[j], hi = r_less ? key[j] : r;
+                key[j] = cb_bitonic_merge32(lo, lane);
+                if (j + 1 < KPL) {
+                    c = cb_bitonic_merge32(hi, lane);
+                } else if (K == 32 * KPL) {
+                    // evicted = hi; a boundary tie exists iff its smallest REAL value equals the new last entry
+                    const unsigned hb = (unsigned)(hi >> 32);
+                    const unsigned mn = __reduce_min_sync(CB_FULL_MASK, hb);
+                    const float new_last = cb_key_d(cb_shfl_key(key[j], 31));
+                    if (__uint_as_float(mn) == new_last) tie_val = new_last;
+                }
+            }
+        }
+        refresh_thresholds();
+    }
+    __device__ __forceinline__ bool has_tie() const
+    {
+        bool t = (K == 32 * KPL) && (tie_val == thr) && (thr < 1e10f);
+#pragma unroll
+        for (int j = 0; j < KPL; j++) {
+            cb_key nx = ((cb_key)__shfl_down_sync(CB_FULL_MASK, (unsigned)(key[j] >> 32), 1) << 32) |
+                        __shfl_down_sync(CB_FULL_MASK, (unsigned)key[j], 1);
+            if (j + 1 < KPL) {
+                const cb_key w = cb_shfl_key(key[j + 1], 0);
+                if (lane == 31) nx = w;
+            }
+            const int e = j * 32 + lane;
+            const bool last = (j + 1 == KPL) && lane == 31;
+            const float d0 = cb_key_d(key[j]), d1 = cb_key_d(nx);
+            const bool adj = !last && (e + 1 <= cap_e) && (d0 == d1) && (d0 < 1e10f);
+            t = t || __any_sync(CB_FULL_MASK, adj);
+        }
+        return t;
+    }
+    __device__ __forceinline__ float out_d(int j) const { return cb_key_d(key[j]); }
+    __device__ __forceinline__ int out_i(int j) const { return cb_key_i(key[j]); }
+};
+
 // Per-warp scratch for flattening cell-row ranges into candidate slots.
 struct CbWarpScratch {
     int start[32];
     int excl[33];
 };
 
+template <int KPL> struct CbTopKSel { typedef CbTopK<KPL> type; };
+template <> struct CbTopKSel<1> { typedef CbTopKB<1> type; };
+template <> struct CbTopKSel<2> { typedef CbTopKB<2> type; };
+
 // Search the grid for the K nearest supports of query (qx,qy,qz) in scene `sc`.
 // Returns false if the query must be replayed by the exact brute-force kernel instead
 // (too many rings).  All lanes of the warp call this together.
-template <int KPL>
-__device__ __forceinline__ bool cb_grid_search(CbTopK<KPL> &tk, const CbScene &sc, float qx, float qy, float qz,
+// squared distance in the arithmetic of the operator being replaced:
+//   mode 0  pointops CUDA kernels (fma contraction, common.cuh cb_sqdist)
+//   mode 1  nanoflann L2_Simple_Adaptor on the host (no fma): ((0 + dx*dx) + dy*dy) + dz*dz, d = q - p
+//           (tensorflow/ops/tf_custom_ops/cpp_utils/nanoflann/nanoflann.hpp:432-440)
+__device__ __forceinline__ float cb_sqdist_mode(int mode, float qx, float qy, float qz, float px, float py, float pz)
+{
+    if (mode == 0) return cb_sqdist(qx, qy, qz, px, py, pz);
+    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <class TK>
+__device__ __forceinline__ bool cb_grid_search(TK &tk, const CbScene &sc, float qx, float qy, float qz,
                                                const int *__restrict__ cells, const float4 *__restrict__ sorted,
-                                               CbWarpScratch *ws, int lane)
+                                               CbWarpScratch *ws, int lane, int dist_mode = 0)
 {
     const float fx = fminf(fmaxf(cb_cellf(qx, sc.ox, sc.inv_h), -1.0e6f), 1.0e6f);
     const float fy = fminf(fmaxf(cb_cellf(qy, sc.oy, sc.inv_h), -1.0e6f), 1.0e6f);
@@ -230,7 +422,7 @@ __device__ __forceinline__ bool cb_grid_search(CbTopK<KPL> &tk, const CbScene &s
                             if (ws->excl[mid] <= j) lo = mid; else hi = mid - 1;
                         }
                         const float4 c = __ldg(sorted + ws->start[lo] + (j - ws->excl[lo]));
-                        cd = cb_sqdist(qx, qy, qz, c.x, c.y, c.z);
+                        cd = cb_sqdist_mode(dist_mode, qx, qy, qz, c.x, c.y, c.z);
                         ci = __float_as_int(c.w);
                     }
                     tk.offer(valid, cd, ci);

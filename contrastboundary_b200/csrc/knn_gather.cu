@@ -12,8 +12,8 @@
 // Algorithmic HBM bytes per call: 12 n + 4 n c + 8 m K + 4 m K c  (SURVEY.md §8(d)).
 #include "knn.cuh"
 
-#define KG_WARPS 4
-#define KG_SLAB_BYTES 16384
+#define KG_WARPS 8
+static int g_kg_chunk_bytes = 2048;    // bytes per TMA chunk (two chunks are in flight per warp)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -49,19 +49,27 @@ __device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// rows per slab chunk: power of two <= 32 with R * row_bytes <= KG_SLAB_BYTES
-static int kg_rows_per_chunk(int c)
+// rows per chunk: power of two <= 32 with R * row_bytes <= chunk_bytes (at least 1)
+static int kg_rows_per_chunk(int c, int chunk_bytes)
 {
     int r = 32;
-    while (r > 1 && (size_t)r * c * 4 > KG_SLAB_BYTES) r >>= 1;
+    while (r > 1 && (size_t)r * c * 4 > (size_t)chunk_bytes) r >>= 1;
     return r;
 }
 
+// One warp per query (persistent over a query stream).  After the search the K rows are moved in
+// chunks of R rows through a two-deep ring of shared-memory slabs: the lanes holding the chunk's
+// neighbour indices each issue ONE cp.async.bulk global->shared (TMA) for their row, lane 0 then
+// issues ONE cp.async.bulk shared->global for the whole chunk (grouped[q, e0:e0+R, :] is contiguous).
+// Loads of chunk c+1 are issued before the store of chunk c has drained, and the next query's search
+// runs under the tail of this query's stores; no feature byte passes through registers.
 template <int KPL>
-__global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int c, int R, const float *__restrict__ new_xyz,
+__global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int c, int R, int slab_bytes,
+                                                              const float *__restrict__ new_xyz,
                                                               const float *__restrict__ feat,
                                                               const int *__restrict__ new_offset, int b, int self_query,
                                                               const CbScene *__restrict__ scenes,
@@ -72,16 +80,17 @@ __global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int 
 {
     extern __shared__ __align__(128) unsigned char kg_smem[];
     __shared__ CbWarpScratch scratch[KG_WARPS];
-    __shared__ __align__(8) unsigned long long bars[KG_WARPS];
+    __shared__ __align__(8) unsigned long long bars[KG_WARPS][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char *slab = kg_smem + (size_t)wib * KG_SLAB_BYTES;
-    const unsigned slab_s = smem_u32(slab), bar_s = smem_u32(&bars[wib]);
+    const unsigned slab0 = smem_u32(kg_smem + (size_t)wib * 2 * slab_bytes);
+    const unsigned bar0 = smem_u32(&bars[wib][0]);
     if (lane == 0) {
-        mbar_init(bar_s, 1);
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    unsigned parity = 0;
+    unsigned phase[2] = {0u, 0u};
     const unsigned row_bytes = (unsigned)c * 4u;
     const int total_warps = gridDim.x * KG_WARPS;
     for (int w = blockIdx.x * KG_WARPS + wib; w < m; w += total_warps) {
@@ -95,9 +104,9 @@ __global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int 
         }
         const int s = cb_scene_of(q, new_offset, b);
         const CbScene sc = scenes[s];
-        CbTopK<KPL> tk;
+        typename CbTopKSel<KPL>::type tk;
         tk.init(K, lane, sc.start);
-        bool ok = cb_grid_search<KPL>(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+        bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
         if (ok && tk.has_tie()) ok = false;
         if (!ok) {   // exact replay + re-gather happen in follow-up kernels
             if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
@@ -107,30 +116,41 @@ __global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int 
         for (int j = 0; j < KPL; j++) {
             const int e = j * 32 + lane;
             if (e < K) {
-                idx[(size_t)q * K + e] = tk.i[j];
-                dist2[(size_t)q * K + e] = tk.d[j];
+                idx[(size_t)q * K + e] = tk.out_i(j);
+                dist2[(size_t)q * K + e] = tk.out_d(j);
             }
         }
-        // gather: chunks of R rows; entry e of the chunk starting at e0 lives in lane (e & 31), reg (e >> 5)
-        for (int e0 = 0; e0 < K; e0 += R) {
+        // issue the loads of chunk `ci` into slab (ci & 1)
+        const int nchunks = (K + R - 1) / R;
+        auto issue = [&](int ci) {
+            const int e0 = ci * R;
             const int rows = min(R, K - e0);
-            if (lane == 0) {
-                bulk_wait_read();                      // slab free (previous store has read it)
-                mbar_expect_tx(bar_s, (unsigned)rows * row_bytes);
-            }
+            const unsigned bar = bar0 + 8u * (ci & 1), slab = slab0 + (unsigned)(ci & 1) * (unsigned)slab_bytes;
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)rows * row_bytes);
             __syncwarp();
-            const int j = e0 >> 5;
             int my = 0;
 #pragma unroll
             for (int jj = 0; jj < KPL; jj++)
-                if (jj == j) my = tk.i[jj];
+                if (jj == (e0 >> 5)) my = tk.out_i(jj);
             const int rel = lane - (e0 & 31);
-            if (rel >= 0 && rel < rows)
-                bulk_g2s(slab_s + (unsigned)rel * row_bytes, feat + (size_t)my * c, row_bytes, bar_s);
-            mbar_wait(bar_s, parity);
-            parity ^= 1u;
-            if (lane == 0) bulk_s2g(grouped + ((size_t)q * K + e0) * c, slab_s, (unsigned)rows * row_bytes);
+            if (rel >= 0 && rel < rows) bulk_g2s(slab + (unsigned)rel * row_bytes, feat + (size_t)my * c, row_bytes, bar);
+        };
+        if (lane == 0) bulk_wait_read0();     // both slabs free (stores of the previous query have read them)
+        __syncwarp();
+        issue(0);
+        if (nchunks > 1) issue(1);
+        for (int ci = 0; ci < nchunks; ci++) {
+            const int sl = ci & 1;
+            mbar_wait(bar0 + 8u * sl, phase[sl]);
+            phase[sl] ^= 1u;
+            const int e0 = ci * R;
+            const int rows = min(R, K - e0);
+            if (lane == 0) {
+                bulk_s2g(grouped + ((size_t)q * K + e0) * c, slab0 + (unsigned)sl * (unsigned)slab_bytes, (unsigned)rows * row_bytes);
+                if (ci + 2 < nchunks) bulk_wait_read0();   // slab `sl` must be drained before it is refilled
+            }
             __syncwarp();
+            if (ci + 2 < nchunks) issue(ci + 2);
         }
     }
     if (lane == 0) bulk_wait_all();
@@ -150,41 +170,27 @@ __global__ void k_regather_flagged(int K, int c, const float *__restrict__ feat,
     }
 }
 
-extern "C" int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz, const float *feat,
-                             const int *offset, const int *new_offset, int b, int *idx, float *dist2, float *grouped,
-                             void *workspace, size_t workspace_bytes, void *stream)
+static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const float *new_xyz, const float *feat,
+                             const int *offset, const int *new_offset, int b, int n, int *idx, float *dist2, float *grouped,
+                             const CbGridView &v, cudaStream_t st)
 {
-    CB_REQUIRE(m >= 0 && n >= 0 && b > 0 && c > 0, CB_EINVAL, "cb_knn_gather: bad sizes");
-    CB_REQUIRE(nsample >= 1 && nsample <= CB_KNN_MAX_NSAMPLE, CB_EINVAL, "cb_knn_gather: nsample=%d", nsample);
-    CB_REQUIRE((xyz || n == 0) && feat && offset && new_offset && workspace && idx && dist2 && grouped, CB_EINVAL,
-               "cb_knn_gather: NULL pointer");
-    CB_REQUIRE(((uintptr_t)workspace & 255) == 0, CB_EINVAL, "cb_knn_gather: workspace not 256-byte aligned");
-    if (!new_xyz) new_xyz = xyz;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool tma_ok = (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 &&
-                        (size_t)c * 4 <= KG_SLAB_BYTES;
-    if (!tma_ok) {   // unfused composition with identical results
-        int rc = cb_knn_query(m, nsample, xyz, n, new_xyz, offset, new_offset, b, idx, dist2, 0, workspace,
-                              workspace_bytes, stream);
-        if (rc) return rc;
-        return cb_grouping_forward(m, nsample, c, feat, idx, grouped, stream);
-    }
-    CbGridView v;
-    const size_t need = cb_grid_layout(n, m, b, workspace, &v);
-    CB_REQUIRE(workspace_bytes >= need, CB_EWORKSPACE, "cb_knn_gather: workspace %zu < %zu", workspace_bytes, need);
-    int rc = cb_grid_build_impl(xyz, n, offset, b, nsample, v, st);
-    if (rc) return rc;
     if (m == 0) return CB_OK;
     cb_knn_reset_flagged(v, st);
     const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
-    const int R = kg_rows_per_chunk(c);
-    const size_t smem = (size_t)KG_WARPS * KG_SLAB_BYTES;
-    int blocks = 148 * 3;
+    int slab = g_kg_chunk_bytes;
+    if (slab < c * 4) slab = c * 4;
+    const int R = kg_rows_per_chunk(c, slab);
+    slab = R * c * 4;
+    const size_t smem = (size_t)KG_WARPS * 2 * slab;
+    int per_sm = (int)((200 * 1024) / (smem + 2048));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int blocks = 148 * per_sm;
     if (blocks > (m + KG_WARPS - 1) / KG_WARPS) blocks = (m + KG_WARPS - 1) / KG_WARPS;
 #define KG_LAUNCH(KPL)                                                                                              \
     do {                                                                                                            \
         cudaFuncSetAttribute(k_knn_gather<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-        k_knn_gather<KPL><<<blocks, KG_WARPS * 32, smem, st>>>(m, nsample, c, R, new_xyz, feat, new_offset, b,       \
+        k_knn_gather<KPL><<<blocks, KG_WARPS * 32, smem, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, \
                                                                self_query, v.scenes, v.cells, v.sorted, idx, dist2, \
                                                                grouped, v.hdr, v.flagged);                          \
     } while (0)
@@ -198,4 +204,57 @@ extern "C" int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n,
     CB_COUNT(4);
     CB_CUDA_CHECK("cb_knn_gather");
     return CB_OK;
+}
+
+static bool kg_tma_ok(int c, int nsample, const float *feat, const float *grouped)
+{
+    return (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 && (size_t)c * 4 <= 16384;
+}
+
+extern "C" int cb_knn_gather_set_chunk_bytes(int bytes)
+{
+    if (bytes >= 512 && bytes <= 16384) g_kg_chunk_bytes = bytes;
+    return g_kg_chunk_bytes;
+}
+
+// split form: the support grid was built by cb_grid_build (same workspace)
+extern "C" int cb_knn_gather_grid(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz, const float *feat,
+                                  const int *offset, const int *new_offset, int b, int *idx, float *dist2, float *grouped,
+                                  void *grid, size_t grid_bytes, void *stream)
+{
+    CB_REQUIRE(m >= 0 && n >= 0 && b > 0 && c > 0 && nsample >= 1 && nsample <= 256, CB_EINVAL, "cb_knn_gather_grid: bad sizes");
+    CB_REQUIRE((xyz || n == 0) && feat && offset && new_offset && grid && idx && dist2 && grouped, CB_EINVAL,
+               "cb_knn_gather_grid: NULL pointer");
+    if (!new_xyz) new_xyz = xyz;
+    CB_REQUIRE(kg_tma_ok(c, nsample, feat, grouped), CB_EUNSUPPORTED, "cb_knn_gather_grid: needs c %% 4 == 0 and 16-byte aligned rows");
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, m, b, grid, &v);
+    CB_REQUIRE(grid_bytes >= need, CB_EWORKSPACE, "cb_knn_gather_grid: workspace %zu < %zu", grid_bytes, need);
+    return knn_gather_launch(m, nsample, c, xyz, new_xyz, feat, offset, new_offset, b, n, idx, dist2, grouped, v,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz, const float *feat,
+                             const int *offset, const int *new_offset, int b, int *idx, float *dist2, float *grouped,
+                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    CB_REQUIRE(m >= 0 && n >= 0 && b > 0 && c > 0, CB_EINVAL, "cb_knn_gather: bad sizes");
+    CB_REQUIRE(nsample >= 1 && nsample <= CB_KNN_MAX_NSAMPLE, CB_EINVAL, "cb_knn_gather: nsample=%d", nsample);
+    CB_REQUIRE((xyz || n == 0) && feat && offset && new_offset && workspace && idx && dist2 && grouped, CB_EINVAL,
+               "cb_knn_gather: NULL pointer");
+    CB_REQUIRE(((uintptr_t)workspace & 255) == 0, CB_EINVAL, "cb_knn_gather: workspace not 256-byte aligned");
+    if (!new_xyz) new_xyz = xyz;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!kg_tma_ok(c, nsample, feat, grouped)) {   // unfused composition with identical results
+        int rc = cb_knn_query(m, nsample, xyz, n, new_xyz, offset, new_offset, b, idx, dist2, 0, workspace,
+                              workspace_bytes, stream);
+        if (rc) return rc;
+        return cb_grouping_forward(m, nsample, c, feat, idx, grouped, stream);
+    }
+    CbGridView v;
+    const size_t need = cb_grid_layout(n, m, b, workspace, &v);
+    CB_REQUIRE(workspace_bytes >= need, CB_EWORKSPACE, "cb_knn_gather: workspace %zu < %zu", workspace_bytes, need);
+    int rc = cb_grid_build_impl(xyz, n, offset, b, nsample, v, st);
+    if (rc) return rc;
+    return knn_gather_launch(m, nsample, c, xyz, new_xyz, feat, offset, new_offset, b, n, idx, dist2, grouped, v, st);
 }

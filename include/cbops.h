@@ -76,6 +76,12 @@ int cb_knn_query_grid(int m, int nsample, const float *xyz, int n, const float *
 int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz,
                   const float *feat, const int *offset, const int *new_offset, int b, int *idx, float *dist2,
                   float *grouped, void *workspace, size_t workspace_bytes, void *stream);
+/* split form on a grid built by cb_grid_build (c % 4 == 0, 16-byte aligned feat/grouped, nsample <= 256) */
+int cb_knn_gather_grid(int m, int nsample, int c, const float *xyz, int n, const float *new_xyz,
+                       const float *feat, const int *offset, const int *new_offset, int b, int *idx, float *dist2,
+                       float *grouped, void *grid, size_t grid_bytes, void *stream);
+float cb_knn_set_occupancy(float factor);       /* tuning knob: target points per occupied grid cell = factor * K (default 0.45) */
+int cb_knn_gather_set_chunk_bytes(int bytes);   /* tuning knob: bytes per TMA chunk (default 2048); returns the value in use */
 
 /* ------------------------------------------------------------------------------------------------
  * a2  farthest point sampling             replaces furthestsampling_cuda_launcher
@@ -157,6 +163,45 @@ int cb_pt_layer_forward(int n, int k, int c, const CbPtLayer *L, const float *re
                         float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a12  radius neighbours        replaces batch_nanoflann_neighbors / op BatchOrderedNeighbors
+ *      tensorflow/ops/tf_custom_ops/tf_neighbors/neighbors/neighbors.cpp:213-336, tf_batch_neighbors.cpp:8-120
+ * Distances in nanoflann's arithmetic (no fma, nanoflann.hpp:432-440), strict d2 < r^2, rows ascending,
+ * padded with ns (the shadow index).  q_offset / s_offset are CUMULATIVE ends (the python facade converts
+ * the reference's per-scene lengths).  Two steps because the row width is data dependent:
+ *   cb_radius_count: builds the support grid in `workspace`, writes counts[nq] and *max_count (device int);
+ *   cb_radius_fill : rows of `width` nearest (width = max count for the reference's behaviour, or a
+ *                    smaller neighbourhood limit: datasets/base.py:762 crops columns right afterwards).
+ * Tie order inside a row is unspecified in the reference (std::sort on distance only).  width <= 256.
+ * ---------------------------------------------------------------------------------------------- */
+int cb_radius_count(int nq, const float *queries, int ns, const float *supports, const int *q_offset,
+                    const int *s_offset, int b, float radius, int *counts, int *max_count, void *workspace,
+                    size_t workspace_bytes, void *stream);
+int cb_radius_fill(int nq, int width, const float *queries, int ns, const float *supports, const int *q_offset,
+                   const int *s_offset, int b, float radius, int *neighbors, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a11  grid subsampling         replaces batch_grid_subsampling (op BatchGridSubsampling) and the CPython
+ *      grid_subsampling.compute   tf_subsampling/grid_subsampling/grid_subsampling.cpp:6-162,
+ *                                 cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106
+ * cb_grid_subsample_cells (device): voxel barycentres (+ feature means), bit-exact (fp32 sums in arrival
+ *   order), in voxel-key order, plus each voxel's key (scene << 44 | key) and first input index.
+ * cb_unordered_map_order (HOST function on host arrays): the permutation that puts the voxels in the
+ *   reference's output order, i.e. the iteration order of its std::unordered_map<size_t, ...>.
+ * cb_grid_subsample_permute (device): apply it.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cb_grid_subsample_workspace_bytes(int n, int b, int fdim);
+int cb_grid_subsample_cells(const float *xyz, int n, const int *offset, int b, float dl, const float *feat, int fdim,
+                            float *cells_xyz, float *cells_feat, unsigned long long *cells_key, int *cells_first_idx,
+                            int *point_cell /* (n) voxel (key order) of every input point, may be NULL */,
+                            int *ncells_dev, void *workspace, size_t workspace_bytes, void *stream);
+int cb_label_vote_host(const int *labels, int count);   /* HOST: tie rule of the reference's label vote */
+int cb_unordered_map_order(const unsigned long long *keys, const int *first_idx, int ncells, int b, int *perm,
+                           int *scene_counts);
+int cb_grid_subsample_permute(int ncells, int fdim, const int *perm, const float *in_xyz, const float *in_feat,
+                              float *out_xyz, float *out_feat, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * a9  fused contrastive-boundary loss of one stage        replaces ContrastHead.point_contrast
  *     pytorch/model/heads.py:185-246 (+ dist_l2 :116-119, posmask_cnt :145-149, contrast_softnn
  *     :151-165) and the sub-scene label propagation of pytorch/model/basic_operators.py:9-50.
@@ -171,6 +216,30 @@ int cb_cbl_forward(int m, int K, int D, const float *feat, const int *idx, const
                    float *sums, void *stream);
 int cb_cbl_backward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
                     const float *scale, float *grad_feat, void *stream);
+/* a14  TF flavour of the same loss (contrast_head, tensorflow/models/heads/head.py:462-807 with softnn/l2):
+ * neighbours with idx >= n_valid are shadow entries of the radius search and count neither as positive nor
+ * negative (solve_samples_mask :641-662); flavour 1 uses dist = sqrt(max(s, 1e-12)) (calc_dist :183-185)
+ * instead of sqrt(s + 1e-12); the ratio is pos / (pos + neg) over valid neighbours (:750-771). */
+int cb_cbl_forward_ex(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                      float *sums, int n_valid, int flavour, void *stream);
+int cb_cbl_backward_ex(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
+                       const float *scale, float *grad_feat, int n_valid, int flavour, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a13  AdaptiveWeight ("ConvNet") local aggregation        tensorflow/models/local_aggregation_operators.py:316-500
+ *      with config/s3dis/adapt.yaml:19-26 (input 'dp', one FC, shared_channels 1, mean reduction, no softmax):
+ *      out[n,c] = sum_k (W[c,:].((support[idx]-query[n])/radius) + b[c]) * feat[idx[n,k],c] / (cnt[n] + 1e-5)
+ * shadow neighbours (idx >= n0) contribute zero; cnt = #(idx < max(idx)) as the reference counts (:466-470);
+ * pad_num (1 device int) receives max(idx) and is reused by the backward.  grad_feat / grad_W / grad_b must be
+ * zero-filled by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int cb_adaptive_weight_forward(int n, int k, int c, int n0, const float *query_pts, const float *support_pts,
+                               const int *idx, const float *feat, const float *W, const float *bias, float radius,
+                               int *pad_num, float *out, void *stream);
+int cb_adaptive_weight_backward(int n, int k, int c, int n0, const float *query_pts, const float *support_pts,
+                                const int *idx, const float *feat, const float *W, const float *bias, float radius,
+                                const int *pad_num, const float *grad_out, float *grad_feat, float *grad_W,
+                                float *grad_b, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * tall-skinny FP32 linear layers of the per-point MLPs (nn.Linear calls of blocks.py:33,72,76,108,

@@ -1,0 +1,139 @@
+"""GPU parity of the TF-side operators (grid subsampling, radius neighbours, knn_batch) against the
+golden vectors produced by the REFERENCE's own C++ cores (tests/golden/tfops_ref_cpu.npz) and the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+import oracle  # noqa: E402
+from test_oracle_cpu import rows_equal_mod_ties  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tf_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "tfops_ref_cpu.npz"))
+
+
+def test_config1_grid_subsampling_and_neighbors(tf_golden):
+    from contrastboundary_b200 import tf_ops
+    p, f, l = cases.tf_config1()
+    sp, sf, sl = tf_ops.grid_subsampling(p, f, l, 0.08)
+    assert np.array_equal(sp, tf_golden["c1/sub_points"])            # bit-exact barycentres in the reference's order
+    assert np.array_equal(sf, tf_golden["c1/sub_features"])
+    assert np.array_equal(sl, tf_golden["c1/sub_labels"])
+    lens = np.array([sp.shape[0]], np.int32)
+    nb = tf_ops.tf_batch_neighbors(sp, sp, lens, lens, 0.1).cpu().numpy()
+    assert rows_equal_mod_ties(nb, tf_golden["c1/neighbors"].astype(np.int32), sp, sp)
+
+
+def test_pyramid_levels(tf_golden):
+    from contrastboundary_b200 import tf_ops
+    p2 = cases.tf_config1()[0][:3000]
+    pts = np.concatenate([cases.tf_sphere()[0], p2], 0)
+    lens = np.array([15000, 3000], np.int32)
+    dl, r = 0.08, 0.1
+    for lvl in range(3):
+        g = lambda k: tf_golden[f"pyr/{lvl}/{k}"]  # noqa: E731
+        nb = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, r).cpu().numpy()
+        assert rows_equal_mod_ties(nb, g("neighbors").astype(np.int32), pts, pts), f"neighbors lvl {lvl}"
+        pool_pts, pool_lens = tf_ops.tf_batch_subsampling(pts, lens, dl)
+        pool_pts, pool_lens = pool_pts.cpu().numpy(), pool_lens.cpu().numpy()
+        assert np.array_equal(pool_pts, g("pool_pts")) and np.array_equal(pool_lens, g("pool_lens"))
+        pools = tf_ops.tf_batch_neighbors(pool_pts, pts, pool_lens, lens, r).cpu().numpy()
+        assert rows_equal_mod_ties(pools, g("pools").astype(np.int32), pool_pts, pts), f"pools lvl {lvl}"
+        ups = tf_ops.tf_batch_neighbors(pts, pool_pts, lens, pool_lens, 2 * r).cpu().numpy()
+        assert rows_equal_mod_ties(ups, g("upsamples").astype(np.int32), pts, pool_pts), f"upsamples lvl {lvl}"
+        # the caller crops to a neighbourhood limit (datasets/base.py:762): fused crop gives the same columns
+        lim = 20
+        cropped = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, r, limit=lim).cpu().numpy()
+        assert rows_equal_mod_ties(cropped, nb[:, :lim], pts, pts)
+        pts, lens, dl, r = pool_pts, pool_lens, dl * 2, r * 2
+
+
+def test_random_clouds_vs_oracle():
+    from contrastboundary_b200 import tf_ops
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        lens = rng.integers(1, 3000, 4).astype(np.int32)
+        lens[trial % 4] = 1                                       # a single-point scene
+        pts = (rng.random((int(lens.sum()), 3)) * rng.uniform(0.5, 3.0)).astype(np.float32)
+        dl = float(rng.uniform(0.05, 0.3))
+        a = tf_ops.tf_batch_subsampling(pts, lens, dl)
+        b = oracle.batch_grid_subsampling(pts, lens, dl)
+        assert np.array_equal(a[0].cpu().numpy(), b[0]) and np.array_equal(a[1].cpu().numpy(), b[1])
+        nb = tf_ops.tf_batch_neighbors(b[0], pts, b[1], lens, 1.5 * dl).cpu().numpy()
+        assert rows_equal_mod_ties(nb, oracle.batch_neighbors(b[0], pts, b[1], lens, 1.5 * dl), b[0], pts)
+        feats = rng.random((int(lens[1]), 5)).astype(np.float32)
+        labs = rng.integers(0, 4, (int(lens[1]), 2)).astype(np.int32)
+        seg = pts[lens[0]:lens[0] + lens[1]]
+        ga = tf_ops.grid_subsampling(seg, feats, labs, dl)
+        gb = oracle.grid_subsampling(seg, feats, labs, dl)
+        assert all(np.array_equal(x, y) for x, y in zip(ga, gb))
+
+
+def test_knn_batch():
+    from contrastboundary_b200 import tf_ops
+    rng = np.random.default_rng(6)
+    sup = rng.random((3, 500, 3)).astype(np.float32)
+    qry = rng.random((3, 120, 3)).astype(np.float32)
+    idx = tf_ops.tf_knn_search(qry, sup, 5).cpu().numpy()
+    ref = oracle.knn_batch(sup, qry, 5)
+    assert np.array_equal(idx, ref)
+
+
+def _pyramid_level(seed=3):
+    from contrastboundary_b200 import tf_ops
+    p2 = cases.tf_config1()[0][:3000]
+    pts = np.concatenate([cases.tf_sphere()[0][:6000], p2], 0)
+    lens = np.array([6000, 3000], np.int32)
+    nb = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, 0.1, limit=26)
+    return torch.from_numpy(pts).cuda(), nb
+
+
+def test_adaptive_weight_matches_restatement():
+    """a13 (parity unpinned: TF cannot run here; the checker is oracle/tf_model.py, a line-by-line restatement)"""
+    from contrastboundary_b200 import tf_model
+    from oracle import tf_model as otf
+    pts, nb = _pyramid_level()
+    torch.manual_seed(0)
+    for c in (72, 144, 32):
+        feat = torch.randn(pts.shape[0], c, device="cuda")
+        w = torch.randn(c, 3, device="cuda") * 0.5
+        b = torch.randn(c, device="cuda") * 0.1
+        g = torch.randn(pts.shape[0], c, device="cuda")
+        res = []
+        for fn in (otf.adaptive_weight, tf_model.adaptive_weight):
+            f2, w2, b2 = (x.clone().requires_grad_(True) for x in (feat, w, b))
+            out = fn(pts, pts, nb, f2, w2, b2, 0.1)
+            out.backward(g)
+            res.append((out.detach(), f2.grad, w2.grad, b2.grad))
+        for a, r in zip(res[1], res[0]):
+            assert float((a - r).abs().max()) <= 2e-5 * float(r.abs().max()) + 1e-7
+
+
+def test_tf_contrast_loss_matches_restatement():
+    """a14 (parity unpinned, same caveat)"""
+    from contrastboundary_b200 import tf_model
+    from oracle import tf_model as otf
+    pts, nb = _pyramid_level()
+    n = pts.shape[0]
+    torch.manual_seed(1)
+    labels = (pts[:, 0] * 3).long() % 5                      # spatially coherent labels -> boundaries exist
+    for d in (72, 32):
+        feat = torch.randn(n, d, device="cuda")
+        res = []
+        for fn in (otf.contrast_loss, tf_model.tf_contrast_loss):
+            f2 = feat.clone().requires_grad_(True)
+            loss = fn(f2, nb, labels, 1.0, 0.1)
+            loss.backward()
+            res.append((float(loss), f2.grad))
+        assert abs(res[1][0] - res[0][0]) <= 1e-5 * abs(res[0][0])
+        assert float((res[1][1] - res[0][1]).abs().max()) <= 1e-4 * float(res[0][1].abs().max())

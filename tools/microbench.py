@@ -40,6 +40,7 @@ def timeit(fn, iters=10, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
     dev = "cuda"
     pointops.set_knn_cache(0)
@@ -51,8 +52,14 @@ def main():
         import oracle
         ref = oracle.ref_pointops_cuda()
     print("== level-0 self KNN, n=163840 (4 x 40960)")
-    for k in (8, 16, 36):
-        med, mn = timeit(lambda: pointops.knn_raw(k, p0, p0, o0, o0, True))
+    import ctypes as C
+    from contrastboundary_b200 import _lib as L
+    L.lib().cb_knn_set_occupancy.restype = C.c_float
+    for k in ((8, 16, 36) if args.only in ("", "knn") else ()):
+        for f in (0.2, 0.3, 0.6, 0.45):
+            L.lib().cb_knn_set_occupancy(C.c_float(f))
+            med, mn = timeit(lambda: pointops.knn_raw(k, p0, p0, o0, o0, True))
+            print(f"     occupancy factor {f}: {med:.1f} us")
         line = f"  ours K={k:3d}: {med:9.1f} us (min {mn:.1f})"
         if ref is not None and k in (16,):
             idx = torch.zeros((p0.shape[0], k), dtype=torch.int32, device=dev)
@@ -63,7 +70,7 @@ def main():
     print("== FPS chain 163840 -> 40960 -> 10240 -> 2560 -> 640")
     p, o = p0, o0
     lens = [40960] * 4
-    for lvl in range(4):
+    for lvl in (range(4) if args.only in ("", "fps") else ()):
         nl = [x // 4 for x in lens]
         no = torch.tensor(np.cumsum(nl), dtype=torch.int32, device=dev)
         med, mn = timeit(lambda: pointops.furthestsampling_known(p, o, no, max(lens), sum(nl)), iters=5, warmup=2)
@@ -80,7 +87,7 @@ def main():
         idx = pointops.furthestsampling_known(p, o, no, max(lens), sum(nl))
         p, o, lens = p[idx.long()].contiguous(), no, nl
     print("== fused KNN+gather (north star): N=40960 K=16 C=256, single scene")
-    for (n, k, c) in [(40960, 16, 256), (40960, 16, 64), (1 << 16, 16, 256), (1 << 18, 16, 64)]:
+    for (n, k, c) in ([(40960, 16, 256), (40960, 16, 64), (1 << 16, 16, 256), (1 << 18, 16, 64)] if args.only in ("", "gather") else []):
         xyz = torch.from_numpy(synthetic.make_scene(n, 4242)[0]).to(dev)
         off = torch.tensor([n], dtype=torch.int32, device=dev)
         feat = torch.randn(n, c, device=dev)
@@ -88,6 +95,14 @@ def main():
         by = 12 * n + 4 * n * c + 8 * n * k + 4 * n * k * c
         print(f"  N={n:7d} K={k} C={c:3d}: {med:9.1f} us (min {mn:.1f})  alg {by / 1e6:.1f} MB -> {by / med / 1e3:.0f} GB/s"
               f" ({by / med / 1e3 / 6569.6 * 100:.0f}% of measured HBM)")
+        grid = fused.grid_build(xyz, off, k)
+        outb = fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off)
+        from contrastboundary_b200 import _lib as L
+        for cb in (1024, 2048, 4096, 8192):
+            L.lib().cb_knn_gather_set_chunk_bytes(cb)
+            medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb))
+            print(f"      kernel only (grid prebuilt), chunk {cb:5d} B: {medk:8.1f} us (min {mnk:.1f}) -> {by / medk / 1e3:.0f} GB/s ({by / medk / 1e3 / 6569.6 * 100:.0f}%)")
+        L.lib().cb_knn_gather_set_chunk_bytes(2048)
         med2, _ = timeit(lambda: pointops.knn_raw(k, xyz, xyz, off, off, False))
         idx, _ = pointops.knn_raw(k, xyz, xyz, off, off, False)
         med3, _ = timeit(lambda: pointops.grouping(feat, idx))
