@@ -216,12 +216,13 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
                                                            double *__restrict__ sums2)
 {
     constexpr int CS = C / 8;
-    constexpr int CT = C < 256 ? C : 256;
-    constexpr int RG = PT_THREADS / CT;
+    constexpr int CT = C < 256 ? C : 256;          // channels per block column
+    constexpr int RG = PT_THREADS / CT;            // row slots per block
+    constexpr int TR = 64;                         // rows staged per iteration (TR / RG rows per thread)
     const PtSmall sp = pt_small_load(smalld);
-    __shared__ float sdw2[RG][CS];
-    __shared__ float sg1[RG][3];
-    __shared__ int sidx[RG];
+    __shared__ float sdw2[TR][CS];
+    __shared__ float sg1[TR][3];
+    __shared__ int sidx[TR];
     const int tr = threadIdx.x / CT;
     const int ch = blockIdx.y * CT + threadIdx.x % CT;
     float w3c[CS], acc[CS];
@@ -231,11 +232,10 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
     const float sc2 = bn2[ch], sh2 = bn2[C + ch], mean2 = bn2[2 * C + ch], inv2 = bn2[3 * C + ch];
     float sa = 0.f, sb = 0.f, sdb3 = 0.f;
     const long long rows = (long long)n * k;
-    const long long groups = (rows + RG - 1) / RG;
-    for (long long gI = blockIdx.x; gI < groups; gI += gridDim.x) {
-        const long long row0 = gI * RG;
-        // stage dw2 rows, g1 and idx of this group
-        for (int e = threadIdx.x; e < RG * CS; e += PT_THREADS) {
+    const long long tiles = (rows + TR - 1) / TR;
+    for (long long tI = blockIdx.x; tI < tiles; tI += gridDim.x) {
+        const long long row0 = tI * TR;
+        for (int e = threadIdx.x; e < TR * CS; e += PT_THREADS) {
             const int r = e / CS, i = e % CS;
             const long long row = row0 + r;
             float v = 0.f;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
                            coef3[CS + i], coef3[2 * CS + i]);
             sdw2[r][i] = v;
         }
-        if (threadIdx.x < RG) {
+        if (threadIdx.x < TR) {
             const long long row = row0 + threadIdx.x;
             float g1[3] = {0, 0, 0}, h1[3];
             int j = 0;
@@ -256,32 +256,51 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
             sidx[threadIdx.x] = j;
         }
         __syncthreads();
-        const long long row = row0 + tr;
-        if (row < rows) {
-            const long long pt = row / k;
-            const float pr = wa * sg1[tr][0] + wb * sg1[tr][1] + wc * sg1[tr][2] + bb;
-            const float w0 = __ldg(xk + (size_t)sidx[tr] * C + ch) - __ldg(xq + (size_t)pt * C + ch) + pr;
-            const float y2 = w0 * sc2 + sh2;
-            const float u = fmaxf(y2, 0.f);
-            float du = 0.f;
+        // gather phase first (UB independent loads in flight), then the math
+        constexpr int RPT = TR / RG;                   // rows per thread and tile
+        constexpr int UB = RPT < 8 ? RPT : 8;
+#pragma unroll 1
+        for (int u0 = 0; u0 < RPT; u0 += UB) {
+            float xkv[UB], xqv[UB];
 #pragma unroll
-            for (int i = 0; i < CS; i++) {
-                const float d = sdw2[tr][i];
-                du += w3c[i] * d;
-                acc[i] += d * u;
+            for (int u = 0; u < UB; u++) {
+                const int r = tr + (u0 + u) * RG;
+                const long long row = row0 + r;
+                xkv[u] = 0.f; xqv[u] = 0.f;
+                if (row < rows) {
+                    xkv[u] = __ldg(xk + (size_t)sidx[r] * C + ch);
+                    xqv[u] = __ldg(xq + (size_t)(row / k) * C + ch);
+                }
             }
-            const float dy2 = y2 > 0.f ? du : 0.f;
-            sa += dy2;
-            sb += dy2 * ((w0 - mean2) * inv2);
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int r = tr + (u0 + u) * RG;
+                if (row0 + r < rows) {
+                    const float pr = wa * sg1[r][0] + wb * sg1[r][1] + wc * sg1[r][2] + bb;
+                    const float w0 = xkv[u] - xqv[u] + pr;
+                    const float y2 = w0 * sc2 + sh2;
+                    const float uu = fmaxf(y2, 0.f);
+                    float du = 0.f;
+#pragma unroll
+                    for (int i = 0; i < CS; i++) {
+                        const float d = sdw2[r][i];
+                        du += w3c[i] * d;
+                        acc[i] += d * uu;
+                    }
+                    const float dy2 = y2 > 0.f ? du : 0.f;
+                    sa += dy2;
+                    sb += dy2 * ((w0 - mean2) * inv2);
+                }
+            }
         }
-        if (blockIdx.y == 0 && threadIdx.x < RG * CS) {   // db3 = sum dw2 (once per row group)
-            const int r = threadIdx.x / CS, i = threadIdx.x % CS;
-            (void)r;
-            sdb3 += sdw2[threadIdx.x / CS][i];
+        if (blockIdx.y == 0 && threadIdx.x < CS) {       // db3 = sum dw2
+            float t = 0.f;
+            for (int r = 0; r < TR; r++) t += sdw2[r][threadIdx.x];
+            sdb3 += t;
         }
         __syncthreads();
     }
-    // combine the block's row-groups through shared memory (RG > 1), then global atomics
+    // combine the block's row slots through shared memory (RG > 1), then global atomics
     const int lc = threadIdx.x % CT;
     if constexpr (RG > 1) {
         __shared__ float comb[CS * CT + 2 * CT];
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
         atomicAdd(sums2 + C + ch, (double)sb);
         (void)lc;
     }
-    if (blockIdx.y == 0 && threadIdx.x < RG * CS) atomicAdd(gb3 + threadIdx.x % CS, sdb3);
+    if (blockIdx.y == 0 && threadIdx.x < CS) atomicAdd(gb3 + threadIdx.x, sdb3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -551,8 +570,7 @@ static int pt_backward_c(int n, int k, const CbPtLayer *L, const float *rel, con
     k_pt_bn_coef<<<1, 128, 0, st>>>(sums3, rows, CS, L->bn3_weight, bn3 + 3 * CS, L->training, coef3, gg3, gbe3);
     {
         constexpr int CT = C < 256 ? C : 256;
-        constexpr int RG = PT_THREADS / CT;
-        const long long groups = ((long long)n * k + RG - 1) / RG;
+        const long long groups = ((long long)n * k + 63) / 64;
         int gx = (int)(groups < 148 * 4 ? (groups < 1 ? 1 : groups) : 148 * 4);
         dim3 g4(gx, C / CT);
         k_pt_bwd_dw3<C><<<g4, PT_THREADS, 0, st>>>(n, k, rel, idx, xq, xk, L->w2, L->b2, small, bn2, bn3, coef3, L->w3, w2buf, D,

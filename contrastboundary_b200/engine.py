@@ -23,12 +23,49 @@ class TrainStep:
         self.opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay,
                                    fused=self.device.type == "cuda")
         self.model.train()
+        self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._geo = {}
 
-    def step(self, batch, update=True):
+    # ------------------------------------------------------------------------------------------
+    # Geometry (FPS chain + every neighbour search) depends on coordinates only.  Like the reference's
+    # TF input pipeline, which builds the neighbour pyramid of the NEXT batch on host workers while the
+    # GPU trains on the current one (tensorflow/datasets/base.py:75-118,767-842), the geometry of batch
+    # t+1 can be computed on a side stream while batch t is in forward/backward.  Every batch's geometry
+    # is still computed exactly once.
+    # ------------------------------------------------------------------------------------------
+    def prefetch_geometry(self, batch):
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)                      # the batch's H2D copies were enqueued on `main`
+        with torch.cuda.stream(self.side):
+            levels = build_geometry(batch["points"], batch["offset"], batch["offset_host"], self.cfg,
+                                    self.cfg.contrast is not None)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self._geo[id(batch)] = (levels, ev)
+
+    def _take_geometry(self, batch):
+        geo = self._geo.pop(id(batch), None)
+        if geo is None:
+            return None
+        levels, ev = geo
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(ev)
+        for lv in levels:                                 # allocated on the side stream, consumed on `main`
+            for name in lv.__slots__:
+                t = getattr(lv, name)
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(main)
+        return levels
+
+    def step(self, batch, update=True, next_batch=None):
         """batch: dict of DEVICE tensors points/features/point_labels/offset + python list offset_host.
+        next_batch: optional batch whose geometry is computed on the side stream during this step.
         returns the stacked loss vector [CE, cbl_0..cbl_4] (device tensor)."""
         self.opt.zero_grad(set_to_none=True)
-        out, stages = self.net(batch)
+        levels = self._take_geometry(batch)
+        if next_batch is not None:
+            self.prefetch_geometry(next_batch)
+        out, stages = self.net(batch, levels)
         loss = self.criterion(out, batch["point_labels"], stages)
         loss.sum().backward()
         if update:
