@@ -72,21 +72,29 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
     """All sampling / neighbour searches of one forward.  p0 (n,3) f32, o0 (b) int32 cumulative ends,
     o0_host = the same offsets as a python list (known from collate; avoids device->host syncs)."""
     levels = []
-    p, o, oh = p0, o0, list(o0_host)
     nl = len(cfg.planes)
+    # host-known scene sizes of every level (TransitionDown: per-scene floor(n_b / stride), blocks.py:64-67).
+    # All small H2D uploads happen HERE, before the first kernel is enqueued: a pageable host->device copy is
+    # synchronous with the host in stream order, so doing it between kernels would stall the launching thread
+    # for the whole FPS chain and defeat the geometry/compute overlap.
+    ohs = [list(o0_host)]
+    for l in range(1, nl):
+        acc, cur = 0, []
+        for x in _lens(ohs[-1]):
+            acc += x // cfg.stride[l]
+            cur.append(acc)
+        ohs.append(cur)
+    flat = torch.tensor([v for oh_ in ohs[1:] for v in oh_] + ohs[-1][:-1], dtype=torch.int32).to(p0.device)
+    b = len(o0_host)
+    o_dev = [o0] + [flat[(l - 1) * b:l * b] for l in range(1, nl)]
+    last_breaks = flat[(nl - 1) * b:(nl - 1) * b + b - 1].long()
+    p, o, oh = p0, o0, ohs[0]
     for l in range(nl):
         lv = Level()
         if l > 0:
-            # TransitionDown sampling (blocks.py:64-70): per-scene floor(n_b / stride)
             prev = levels[-1]
-            lens = [x // cfg.stride[l] for x in _lens(prev.o_host)]
-            oh = []
-            acc = 0
-            for x in lens:
-                acc += x
-                oh.append(acc)
-            o = torch.tensor(oh, dtype=torch.int32, device=p0.device)
-            fidx = pointops.furthestsampling_known(prev.p, prev.o, o, max(_lens(prev.o_host)), acc)
+            oh, o = ohs[l], o_dev[l]
+            fidx = pointops.furthestsampling_known(prev.p, prev.o, o, max(_lens(prev.o_host)), oh[-1])
             p = prev.p[fidx.long(), :].contiguous()
             lv.fps_idx = fidx
             # neighbours of the new points among the previous level (blocks.py:71)
@@ -110,7 +118,7 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
     last = levels[-1]
     sid = torch.zeros(last.n, dtype=torch.long, device=p0.device)
     if len(last.o_host) > 1:
-        sid[torch.tensor(last.o_host[:-1], device=p0.device, dtype=torch.long)] = 1
+        sid[last_breaks] = 1
         sid = torch.cumsum(sid, 0)
     last.scene_id = sid
     if with_contrast and cfg.contrast is not None:
@@ -213,7 +221,8 @@ class TransitionUp(nn.Module):
     def forward(self, x1, level1, x2=None):
         if x2 is None:   # head of the decoder: concat the per-scene mean
             b = len(level1.o_host)
-            cnt = torch.tensor(_lens(level1.o_host), dtype=x1.dtype, device=x1.device).unsqueeze(1)
+            o = level1.o
+            cnt = torch.cat([o[:1], o[1:] - o[:-1]]).to(x1.dtype).unsqueeze(1)       # device-side, no host sync
             mean = torch.zeros(b, x1.shape[1], dtype=x1.dtype, device=x1.device).index_add_(0, level1.scene_id, x1) / cnt
             g = self.linear2(mean)[level1.scene_id]
             return self.linear1(torch.cat((x1, g), 1))
