@@ -84,10 +84,9 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
             acc += x // cfg.stride[l]
             cur.append(acc)
         ohs.append(cur)
-    flat = torch.tensor([v for oh_ in ohs[1:] for v in oh_] + ohs[-1][:-1], dtype=torch.int32).to(p0.device)
+    flat = torch.tensor([v for oh_ in ohs[1:] for v in oh_], dtype=torch.int32).to(p0.device)
     b = len(o0_host)
     o_dev = [o0] + [flat[(l - 1) * b:l * b] for l in range(1, nl)]
-    last_breaks = flat[(nl - 1) * b:(nl - 1) * b + b - 1].long()
     p, o, oh = p0, o0, ohs[0]
     for l in range(nl):
         lv = Level()
@@ -116,11 +115,8 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
         levels[l].head_idx, _ = pointops.knn_raw(1, levels[l].p, levels[0].p, levels[l].o, levels[0].o, True)
     # dec5 per-scene mean (blocks.py:94-103)
     last = levels[-1]
-    sid = torch.zeros(last.n, dtype=torch.long, device=p0.device)
-    if len(last.o_host) > 1:
-        sid[last_breaks] = 1
-        sid = torch.cumsum(sid, 0)
-    last.scene_id = sid
+    # scene id of every point of the last level, device-side (tensor-indexed assignment would sync the host)
+    last.scene_id = torch.searchsorted(last.o.long(), torch.arange(last.n, device=p0.device), right=True)
     if with_contrast and cfg.contrast is not None:
         kr = 1
         for l in range(nl):
