@@ -64,6 +64,24 @@ class Level:
             setattr(self, s, None)
 
 
+_pinned = {}
+
+
+def _upload_i32(values, device):
+    """small int32 upload through a cached pinned staging buffer: asynchronous w.r.t. the host (a pageable copy
+    would block the launching thread until the stream reaches it)."""
+    n = len(values)
+    key = (n, torch.cuda.current_stream(device).cuda_stream)
+    ring = _pinned.get(key)
+    if ring is None:
+        ring = {"bufs": [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(4)], "i": 0}
+        _pinned[key] = ring
+    buf = ring["bufs"][ring["i"] % 4]          # 4-deep ring: a buffer is reused only 4 geometry builds later
+    ring["i"] += 1
+    buf.copy_(torch.tensor(values, dtype=torch.int32))
+    return buf.to(device, non_blocking=True)
+
+
 def _lens(o_host):
     return [o_host[0]] + [o_host[i] - o_host[i - 1] for i in range(1, len(o_host))]
 
@@ -84,7 +102,7 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
             acc += x // cfg.stride[l]
             cur.append(acc)
         ohs.append(cur)
-    flat = torch.tensor([v for oh_ in ohs[1:] for v in oh_], dtype=torch.int32).to(p0.device)
+    flat = _upload_i32([v for oh_ in ohs[1:] for v in oh_], p0.device)
     b = len(o0_host)
     o_dev = [o0] + [flat[(l - 1) * b:l * b] for l in range(1, nl)]
     p, o, oh = p0, o0, ohs[0]

@@ -40,7 +40,7 @@ def main():
     names = ["geometry (FPS + all KNN)", "forward (network)", "loss (CE + CBL)", "backward + SGD"]
     for i, nm in enumerate(names):
         print(f"{nm:28s} {ev[i].elapsed_time(ev[i + 1]):8.2f} ms")
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
         ts.step(batch)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=a.top, max_name_column_width=70))
