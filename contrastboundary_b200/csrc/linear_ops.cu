@@ -161,7 +161,7 @@ extern "C" int cb_linear_dgrad(int n, int ci, int co, const float *G, const floa
 extern "C" int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, void *stream)
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && X && G && dW, CB_EINVAL, "cb_linear_wgrad: bad arguments");
-    CB_REQUIRE(ci * co <= 16 * LG_THREADS * 2 && co <= LG_THREADS, CB_EUNSUPPORTED, "cb_linear_wgrad: ci*co=%d too large", ci * co);
+    CB_REQUIRE(ci * co <= 64 * LG_THREADS && co <= LG_THREADS, CB_EUNSUPPORTED, "cb_linear_wgrad: ci*co=%d too large", ci * co);
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)ci * co, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)co, st);
@@ -181,7 +181,8 @@ extern "C" int cb_linear_wgrad(int n, int ci, int co, const float *X, const floa
     else if (opt <= 4) WG_LAUNCH(4);
     else if (opt <= 8) WG_LAUNCH(8);
     else if (opt <= 16) WG_LAUNCH(16);
-    else WG_LAUNCH(32);
+    else if (opt <= 32) WG_LAUNCH(32);
+    else WG_LAUNCH(64);
 #undef WG_LAUNCH
     CB_COUNT(3);
     CB_CUDA_CHECK("cb_linear_wgrad");

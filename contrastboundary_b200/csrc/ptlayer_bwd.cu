@@ -56,7 +56,7 @@ __global__ void k_pt_bn_coef(const double *__restrict__ sums /* [2][C]: sum dy, 
 // B1: da[n,k,j] = sum_{c % CS = j} G[n,c] * (x_v[idx] + pr)[n,k,c]
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_da(int n, int k, const float *__restrict__ rel,
+__global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_da(int n, int k, int ld, const float *__restrict__ rel,
                                                           const int *__restrict__ idx, const float *__restrict__ xv,
                                                           const float *__restrict__ w2p, const float *__restrict__ b2p,
                                                           const float *__restrict__ smalld, const float *__restrict__ G,
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_da(int n, int k, const fl
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 float x[VW];
-                pt_load<VW>(xv + (size_t)j * C + M::ch(lane, s, 0), x);
+                pt_load<VW>(xv + (size_t)j * ld + M::ch(lane, s, 0), x);
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
                     const float pr = wa[s][v] * g1[0] + wb[s][v] * g1[1] + wc[s][v] * g1[2] + bb[s][v];
@@ -205,7 +205,7 @@ __device__ __forceinline__ float pt_dw2(float dy3, float w2v, float mean3, float
 // Thread (row-in-group, channel): CT = min(C,256) channels per block column, RG = 256/CT rows at once.
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const float *__restrict__ rel,
+__global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, int ld, const float *__restrict__ rel,
                                                            const int *__restrict__ idx, const float *__restrict__ xq,
                                                            const float *__restrict__ xk, const float *__restrict__ w2p,
                                                            const float *__restrict__ b2p, const float *__restrict__ smalld,
@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
                 const long long row = row0 + r;
                 xkv[u] = 0.f; xqv[u] = 0.f;
                 if (row < rows) {
-                    xkv[u] = __ldg(xk + (size_t)sidx[r] * C + ch);
-                    xqv[u] = __ldg(xq + (size_t)(row / k) * C + ch);
+                    xkv[u] = __ldg(xk + (size_t)sidx[r] * ld + ch);
+                    xqv[u] = __ldg(xq + (size_t)(row / k) * ld + ch);
                 }
             }
 #pragma unroll
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, const f
 // B5: main c-space backward (warp per point)
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, const float *__restrict__ rel,
+__global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld, const float *__restrict__ rel,
                                                             const int *__restrict__ idx, const float *__restrict__ xq,
                                                             const float *__restrict__ xk, const float *__restrict__ w2p,
                                                             const float *__restrict__ b2p, const float *__restrict__ smalld,
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, const 
         float q[NS][VW], g[NS][VW], dq[NS][VW];
 #pragma unroll
         for (int s = 0; s < NS; s++) {
-            pt_load<VW>(xq + (size_t)pt * C + M::ch(lane, s, 0), q[s]);
+            pt_load<VW>(xq + (size_t)pt * ld + M::ch(lane, s, 0), q[s]);
             pt_load<VW>(G + (size_t)pt * C + M::ch(lane, s, 0), g[s]);
 #pragma unroll
             for (int v = 0; v < VW; v++) dq[s][v] = 0.f;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, const 
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 float x[VW], aw[VW], w0[VW], du[VW];
-                pt_load<VW>(xk + (size_t)j * C + M::ch(lane, s, 0), x);
+                pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
                 pt_load<VW>(abuf + row * CS + (M::ch(lane, s, 0) % CS), aw);
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
@@ -435,11 +435,11 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, const 
                     ab2[s][v] += dpr;
                     dg[0] += dpr * wa[s][v]; dg[1] += dpr * wb[s][v]; dg[2] += dpr * wc[s][v];
                 }
-                pt_red_add<VW>(gxk + (size_t)j * C + M::ch(lane, s, 0), dw0);
+                pt_red_add<VW>(gxk + (size_t)j * ld + M::ch(lane, s, 0), dw0);
                 float xvadd[VW];
 #pragma unroll
                 for (int v = 0; v < VW; v++) xvadd[v] = dval[v];
-                pt_red_add<VW>(gxv + (size_t)j * C + M::ch(lane, s, 0), xvadd);
+                pt_red_add<VW>(gxv + (size_t)j * ld + M::ch(lane, s, 0), xvadd);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, const 
             }
         }
 #pragma unroll
-        for (int s = 0; s < NS; s++) pt_store<VW>(gxq + (size_t)pt * C + M::ch(lane, s, 0), dq[s]);
+        for (int s = 0; s < NS; s++) pt_store<VW>(gxq + (size_t)pt * ld + M::ch(lane, s, 0), dq[s]);
     }
     // block combine of dW2 / db2 / bn1 sums
     __shared__ float comb[4 * C + 6];
@@ -536,7 +536,7 @@ extern "C" size_t cb_pt_bwd_scratch_floats(int n, int k, int c)
 }
 
 template <int C>
-static int pt_backward_c(int n, int k, const CbPtLayer *L, const float *rel, const int *idx, const float *xq,
+static int pt_backward_c(int n, int k, int ld, const CbPtLayer *L, const float *rel, const int *idx, const float *xq,
                          const float *xk, const float *xv, const float *w2buf, const float *abuf, const float *bnbuf,
                          const float *G, float *gxq, float *gxk, float *gxv, float *gbuf, float *scratch, cudaStream_t st)
 {
@@ -558,7 +558,7 @@ static int pt_backward_c(int n, int k, const CbPtLayer *L, const float *rel, con
     const double rows = (double)n * (double)k;
     cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * CS + 2 * C + 8), st);
     const int grid = pt_grid(n);
-    k_pt_bwd_da<C><<<grid, PT_THREADS, 0, st>>>(n, k, rel, idx, xv, L->w2, L->b2, small, G, D);
+    k_pt_bwd_da<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xv, L->w2, L->b2, small, G, D);
     {
         const int PB = PT_THREADS / CS;
         const size_t smem = (size_t)(CS * (CS + 1) + 2 * PB * k * CS + 3 * CS) * sizeof(float);
@@ -573,14 +573,14 @@ static int pt_backward_c(int n, int k, const CbPtLayer *L, const float *rel, con
         const long long groups = ((long long)n * k + 63) / 64;
         int gx = (int)(groups < 148 * 4 ? (groups < 1 ? 1 : groups) : 148 * 4);
         dim3 g4(gx, C / CT);
-        k_pt_bwd_dw3<C><<<g4, PT_THREADS, 0, st>>>(n, k, rel, idx, xq, xk, L->w2, L->b2, small, bn2, bn3, coef3, L->w3, w2buf, D,
+        k_pt_bwd_dw3<C><<<g4, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, bn3, coef3, L->w3, w2buf, D,
                                                    gW3, gb3, sums2);
     }
     k_pt_bn_coef<<<(C + 127) / 128, 128, 0, st>>>(sums2, rows, C, L->bn2_weight, bn2 + 3 * C, L->training, coef2, gg2, gbe2);
     {
         const size_t smem = (size_t)CS * C * sizeof(float);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_bwd_main<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_pt_bwd_main<C><<<grid, PT_THREADS, smem, st>>>(n, k, rel, idx, xq, xk, L->w2, L->b2, small, bn1ms, bn2, bn3, coef2,
+        k_pt_bwd_main<C><<<grid, PT_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn1ms, bn2, bn3, coef2,
                                                          coef3, L->w3, w2buf, abuf, D, G, gxq, gxk, gxv, gW2, gb2, dy1,
                                                          sums1);
     }
@@ -597,7 +597,7 @@ static int pt_backward_c(int n, int k, const CbPtLayer *L, const float *rel, con
     return CB_OK;
 }
 
-extern "C" int cb_pt_layer_backward(int n, int k, int c, const CbPtLayer *L, const float *rel, const int *idx,
+extern "C" int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const int *idx,
                                     const float *xq, const float *xk, const float *xv, const float *w2buf,
                                     const float *abuf, const float *bnbuf, const float *grad_out, float *grad_xq,
                                     float *grad_xk, float *grad_xv, float *grad_params, float *scratch, void *stream)
@@ -609,7 +609,7 @@ extern "C" int cb_pt_layer_backward(int n, int k, int c, const CbPtLayer *L, con
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return CB_OK;
     switch (c) {
-#define PT_CASE(CC) case CC: return pt_backward_c<CC>(n, k, L, rel, idx, xq, xk, xv, w2buf, abuf, bnbuf, grad_out, grad_xq, grad_xk, grad_xv, grad_params, scratch, st);
+#define PT_CASE(CC) case CC: return pt_backward_c<CC>(n, k, ld, L, rel, idx, xq, xk, xv, w2buf, abuf, bnbuf, grad_out, grad_xq, grad_xk, grad_xv, grad_params, scratch, st);
         PT_CASE(32) PT_CASE(64) PT_CASE(128) PT_CASE(256) PT_CASE(512)
 #undef PT_CASE
     default:

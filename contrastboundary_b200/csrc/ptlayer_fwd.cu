@@ -134,7 +134,7 @@ __global__ void k_bn_finalize(const double *__restrict__ stats /* [2][C] */, dou
 // F1: statistics of w0 = x_k[idx] - x_q[n] + pr  (per channel sum / sum of squares)
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, const float *__restrict__ rel,
+__global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, int ld, const float *__restrict__ rel,
                                                             const int *__restrict__ idx, const float *__restrict__ xq,
                                                             const float *__restrict__ xk, const float *__restrict__ w2p,
                                                             const float *__restrict__ b2p, const float *__restrict__ smalld,
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, const 
     for (int pt = blockIdx.x * PT_WARPS + wib; pt < n; pt += warps) {
         float q[NS][VW];
 #pragma unroll
-        for (int s = 0; s < NS; s++) pt_load<VW>(xq + (size_t)pt * C + M::ch(lane, s, 0), q[s]);
+        for (int s = 0; s < NS; s++) pt_load<VW>(xq + (size_t)pt * ld + M::ch(lane, s, 0), q[s]);
         for (int kk = 0; kk < k; kk++) {
             const size_t row = (size_t)pt * k + kk;
             const int j = __ldg(idx + row);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, const 
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 float x[VW];
-                pt_load<VW>(xk + (size_t)j * C + M::ch(lane, s, 0), x);
+                pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
                     const float pr = wa[s][v] * g[0] + wb[s][v] * g[1] + wc[s][v] * g[2] + bb[s][v];
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, const 
 // F2: w2 = W3 relu(bn2(w0)) + b3  -> (n,k,CS) and its per-channel statistics
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(PT_THREADS) k_pt_w2(int n, int k, const float *__restrict__ rel,
+__global__ void __launch_bounds__(PT_THREADS) k_pt_w2(int n, int k, int ld, const float *__restrict__ rel,
                                                       const int *__restrict__ idx, const float *__restrict__ xq,
                                                       const float *__restrict__ xk, const float *__restrict__ w2p,
                                                       const float *__restrict__ b2p, const float *__restrict__ smalld,
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w2(int n, int k, const float 
     for (int pt = blockIdx.x * PT_WARPS + wib; pt < n; pt += warps) {
         float q[NS][VW];
 #pragma unroll
-        for (int s = 0; s < NS; s++) pt_load<VW>(xq + (size_t)pt * C + M::ch(lane, s, 0), q[s]);
+        for (int s = 0; s < NS; s++) pt_load<VW>(xq + (size_t)pt * ld + M::ch(lane, s, 0), q[s]);
         for (int kk = 0; kk < k; kk++) {
             const size_t row = (size_t)pt * k + kk;
             const int j = __ldg(idx + row);
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w2(int n, int k, const float 
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 float x[VW], u[VW];
-                pt_load<VW>(xk + (size_t)j * C + M::ch(lane, s, 0), x);
+                pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
                     const float pr = wa[s][v] * g[0] + wb[s][v] * g[1] + wc[s][v] * g[2] + bb[s][v];
@@ -356,7 +356,7 @@ __global__ void k_pt_softmax(int n, int k, int CS, const float *__restrict__ w2,
 // F4: out[n,c] = sum_k (x_v[idx] + pr)[c] * a[n,k,c % CS]
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(PT_THREADS) k_pt_aggregate(int n, int k, const float *__restrict__ rel,
+__global__ void __launch_bounds__(PT_THREADS) k_pt_aggregate(int n, int k, int ld, const float *__restrict__ rel,
                                                              const int *__restrict__ idx, const float *__restrict__ xv,
                                                              const float *__restrict__ w2p, const float *__restrict__ b2p,
                                                              const float *__restrict__ smalld, const float *__restrict__ a,
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_aggregate(int n, int k, const
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 float x[VW], aw[VW];
-                pt_load<VW>(xv + (size_t)j * C + M::ch(lane, s, 0), x);
+                pt_load<VW>(xv + (size_t)j * ld + M::ch(lane, s, 0), x);
                 pt_load<VW>(a + row * CS + (M::ch(lane, s, 0) % CS), aw);
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
@@ -438,7 +438,7 @@ extern "C" int cb_pt_rel(int n, int k, const float *p, const int *idx, float *re
 }
 
 template <int C>
-static int pt_forward_c(int n, int k, const CbPtLayer *L, const float *rel, const double *moments, const int *idx,
+static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *rel, const double *moments, const int *idx,
                         const float *xq, const float *xk, const float *xv, float *out, float *w2buf, float *abuf,
                         float *bnbuf, double *stats, cudaStream_t st)
 {
@@ -452,12 +452,12 @@ static int pt_forward_c(int n, int k, const CbPtLayer *L, const float *rel, cons
                                      L->bn1_running_var, L->momentum, L->eps, L->training, bnbuf + 12);
     const int grid = pt_grid(n);
     if (L->training)
-        k_pt_w0_stats<C><<<grid, PT_THREADS, 0, st>>>(n, k, rel, idx, xq, xk, L->w2, L->b2, small, stats2);
+        k_pt_w0_stats<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, stats2);
     k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(stats2, rows, C, L->bn2_weight, L->bn2_bias, L->bn2_running_mean,
                                                     L->bn2_running_var, L->momentum, L->eps, L->training, bn2);
     const size_t smem = (size_t)CS * C * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_w2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_pt_w2<C><<<grid, PT_THREADS, smem, st>>>(n, k, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3);
+    k_pt_w2<C><<<grid, PT_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3);
     k_bn_finalize<<<1, 128, 0, st>>>(stats3, rows, CS, L->bn3_weight, L->bn3_bias, L->bn3_running_mean,
                                       L->bn3_running_var, L->momentum, L->eps, L->training, bn3);
     const size_t smem4 = (size_t)(CS * (CS + 1) + 2 * CS) * sizeof(float);
@@ -466,7 +466,7 @@ static int pt_forward_c(int n, int k, const CbPtLayer *L, const float *rel, cons
     if (g4 > 148 * 8) g4 = 148 * 8;
     if (g4 < 1) g4 = 1;
     k_pt_softmax<<<g4, 256, smem4, st>>>(n, k, CS, w2buf, bn3, L->w4, L->b4, abuf);
-    k_pt_aggregate<C><<<grid, PT_THREADS, 0, st>>>(n, k, rel, idx, xv, L->w2, L->b2, small, abuf, out);
+    k_pt_aggregate<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xv, L->w2, L->b2, small, abuf, out);
     CB_COUNT(9);
     CB_CUDA_CHECK("cb_pt_layer_forward");
     return CB_OK;
@@ -475,21 +475,22 @@ static int pt_forward_c(int n, int k, const CbPtLayer *L, const float *rel, cons
 extern "C" size_t cb_pt_bnbuf_floats(int c) { return (size_t)(24 + 4 * c + 4 * (c / 8)); }
 extern "C" size_t cb_pt_stats_doubles(int c) { return (size_t)(2 * c + 2 * (c / 8) + 64); }
 
-extern "C" int cb_pt_layer_forward(int n, int k, int c, const CbPtLayer *L, const float *rel, const double *moments,
+extern "C" int cb_pt_layer_forward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const double *moments,
                                    const int *idx, const float *xq, const float *xk, const float *xv, float *out,
                                    float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream)
 {
     CB_REQUIRE(n >= 0 && k >= 1 && k <= PT_KMAX, CB_EINVAL, "cb_pt_layer_forward: n=%d k=%d (k <= %d)", n, k, PT_KMAX);
+    CB_REQUIRE(ld >= c && ld % 4 == 0, CB_EINVAL, "cb_pt_layer_forward: ld=%d (row stride of x_q/x_k/x_v) must be >= c and a multiple of 4", ld);
     CB_REQUIRE(L && rel && moments && idx && xq && xk && xv && out && w2buf && abuf && bnbuf && stats, CB_EINVAL,
                "cb_pt_layer_forward: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return CB_OK;
     switch (c) {
-    case 32: return pt_forward_c<32>(n, k, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 64: return pt_forward_c<64>(n, k, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 128: return pt_forward_c<128>(n, k, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 256: return pt_forward_c<256>(n, k, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 512: return pt_forward_c<512>(n, k, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
+    case 32: return pt_forward_c<32>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
+    case 64: return pt_forward_c<64>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
+    case 128: return pt_forward_c<128>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
+    case 256: return pt_forward_c<256>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
+    case 512: return pt_forward_c<512>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
     default:
         cb_set_error("cb_pt_layer_forward: c=%d unsupported (32,64,128,256,512)", c);
         return CB_EUNSUPPORTED;

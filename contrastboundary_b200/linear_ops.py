@@ -10,7 +10,7 @@ from . import _lib as L
 
 MIN_ROWS = 8192        # below this cuBLAS is fine (and launch latency dominates anyway)
 MAX_CO = 512
-MAX_WGRAD = 8192       # ci*co handled by the custom wgrad kernel
+MAX_WGRAD = 16384      # ci*co handled by the custom wgrad kernel
 
 
 class _SkinnyLinearFn(Function):

@@ -57,7 +57,7 @@ class CBLConfig:
 # ------------------------------------------------------------------------------------------------
 class Level:
     __slots__ = ("p", "o", "o_host", "n", "knn", "fps_idx", "down_idx", "up_idx", "up_w", "head_idx",
-                 "label_idx", "cbl_idx", "scene_id", "rel", "rel_mom")
+                 "label_idx", "cbl_idx", "scene_id", "rel", "rel_mom", "rel_down")
 
     def __init__(self):
         for s in self.__slots__:
@@ -116,6 +116,9 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
             lv.fps_idx = fidx
             # neighbours of the new points among the previous level (blocks.py:71)
             lv.down_idx, _ = pointops.knn_raw(cfg.nsample_backbone[l], prev.p, p, prev.o, o, True)
+            if cfg.fused:
+                from . import ptlayer
+                lv.rel_down = ptlayer.td_rel(prev.p, p, lv.down_idx)
         lv.p, lv.o, lv.o_host, lv.n = p, o, oh, p.shape[0]
         lv.knn, _ = pointops.knn_raw(cfg.nsample_backbone[l], p, p, o, o, True)          # blocks.py:34-35
         if cfg.fused:
@@ -178,10 +181,14 @@ class PointTransformerLayer(nn.Module):
 
     def forward(self, lv, x):
         p, idx = lv.p, lv.knn
-        x_q, x_k, x_v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
         if self.fused:
+            # one (c -> 3c) projection instead of three (the parameters stay linear_q / linear_k / linear_v)
             from . import ptlayer
-            return ptlayer.pt_attention(self, lv, x_q, x_k, x_v)
+            from .linear_ops import fast_linear
+            w = torch.cat((self.linear_q.weight, self.linear_k.weight, self.linear_v.weight), 0)
+            b = torch.cat((self.linear_q.bias, self.linear_k.bias, self.linear_v.bias), 0)
+            return ptlayer.pt_attention(self, lv, fast_linear(x, w, b))
+        x_q, x_k, x_v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
         n, k = idx.shape
         c, s = self.out_planes, self.share_planes
         p_r = pointops.grouping(p, idx) - p.unsqueeze(1)                       # (n,k,3)
@@ -209,10 +216,14 @@ class TransitionDown(nn.Module):
         else:
             self.linear = Linear(in_planes, out_planes, bias=False)
         self.bn = nn.BatchNorm1d(out_planes)
+        self.fused = True
 
     def forward(self, x, prev_level=None, level=None):
         if self.stride == 1:
             return F.relu(self.bn(self.linear(x)))
+        if self.fused and level.rel_down is not None and self.linear.weight.shape[0] in (32, 64, 128, 256, 512):
+            from . import ptlayer
+            return ptlayer.transition_down(self, x, prev_level, level)
         idx = level.down_idx                                                   # (m,k) into prev_level
         g_xyz = pointops.grouping(prev_level.p, idx) - level.p.unsqueeze(1)    # (m,k,3)
         g = torch.cat((g_xyz, pointops.grouping(x, idx)), -1)                  # (m,k,3+c)
@@ -320,7 +331,7 @@ class PointTransformerSeg(nn.Module):
 
     def set_fused(self, flag):
         for m in self.modules():
-            if isinstance(m, PointTransformerLayer):
+            if isinstance(m, (PointTransformerLayer, TransitionDown)):
                 m.fused = bool(flag)
 
     def _make_enc(self, planes, blocks, share_planes, stride, nsample):

@@ -37,12 +37,15 @@ def _param_struct(params, buffers, momentum, eps, training):
 
 class PtAttentionFn(Function):
     @staticmethod
-    def forward(ctx, rel, moments, idx, xq, xk, xv, buffers, momentum, eps, training, *params):
+    def forward(ctx, rel, moments, idx, qkv, buffers, momentum, eps, training, *params):
+        # qkv (n, 3c): the fused q/k/v projection; x_q, x_k, x_v are its column blocks (row stride ld = 3c)
         n, k = idx.shape
-        c = xq.shape[1]
+        c = qkv.shape[1] // 3
         cs = c // 8
-        dev = xq.device
-        xq, xk, xv = xq.contiguous(), xk.contiguous(), xv.contiguous()
+        dev = qkv.device
+        qkv = qkv.contiguous()
+        ld = 3 * c
+        xq, xk, xv = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
         out = torch.empty((n, c), dtype=torch.float32, device=dev)
         w2buf = torch.empty((n, k, cs), dtype=torch.float32, device=dev)
         abuf = torch.empty((n, k, cs), dtype=torch.float32, device=dev)
@@ -52,26 +55,27 @@ class PtAttentionFn(Function):
         bnbuf = torch.empty(lib.cb_pt_bnbuf_floats(C.c_int(c)), dtype=torch.float32, device=dev)
         stats = torch.empty(lib.cb_pt_stats_doubles(C.c_int(c)), dtype=torch.float64, device=dev)
         ps = _param_struct(params, buffers, momentum, eps, training)
-        rc = lib.cb_pt_layer_forward(C.c_int(n), C.c_int(k), C.c_int(c), C.byref(ps), L.ptr(rel), L.ptr(moments), L.ptr(idx),
+        rc = lib.cb_pt_layer_forward(C.c_int(n), C.c_int(k), C.c_int(c), C.c_int(ld), C.byref(ps), L.ptr(rel), L.ptr(moments), L.ptr(idx),
                                      L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(out), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf),
                                      L.ptr(stats), L.stream())
         L.check(rc, "cb_pt_layer_forward")
-        ctx.save_for_backward(rel, idx, xq, xk, xv, w2buf, abuf, bnbuf, *params)
+        ctx.save_for_backward(rel, idx, qkv, w2buf, abuf, bnbuf, *params)
         ctx.training = training
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        rel, idx, xq, xk, xv, w2buf, abuf, bnbuf = ctx.saved_tensors[:8]
-        params = ctx.saved_tensors[8:]
+        rel, idx, qkv, w2buf, abuf, bnbuf = ctx.saved_tensors[:6]
+        params = ctx.saved_tensors[6:]
         n, k = idx.shape
-        c = xq.shape[1]
+        c = qkv.shape[1] // 3
         cs = c // 8
-        dev = xq.device
+        dev = qkv.device
+        ld = 3 * c
+        xq, xk, xv = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
         gout = gout.contiguous()
-        gxq = torch.empty_like(xq)
-        gxk = torch.zeros_like(xk)
-        gxv = torch.zeros_like(xv)
+        gqkv = torch.zeros_like(qkv)                  # x_k / x_v blocks are scatter-add targets, x_q block is overwritten
+        gxq, gxk, gxv = gqkv[:, :c], gqkv[:, c:2 * c], gqkv[:, 2 * c:]
         lib = L.lib()
         lib.cb_pt_bwd_scratch_floats.restype = C.c_size_t
         scratch = torch.empty(lib.cb_pt_bwd_scratch_floats(C.c_int(n), C.c_int(k), C.c_int(c)), dtype=torch.float32, device=dev)
@@ -79,7 +83,7 @@ class PtAttentionFn(Function):
         sizes = [9, 3, 3, 3, c * 3, c, c, c, cs * c, cs, cs, cs, cs * cs, cs]
         gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         ps = _param_struct(params, (params[0],) * 6, 0.0, 0.0, ctx.training)   # running stats unused in backward
-        rc = lib.cb_pt_layer_backward(C.c_int(n), C.c_int(k), C.c_int(c), C.byref(ps), L.ptr(rel), L.ptr(idx), L.ptr(xq),
+        rc = lib.cb_pt_layer_backward(C.c_int(n), C.c_int(k), C.c_int(c), C.c_int(ld), C.byref(ps), L.ptr(rel), L.ptr(idx), L.ptr(xq),
                                       L.ptr(xk), L.ptr(xv), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf), L.ptr(gout),
                                       L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.stream())
         L.check(rc, "cb_pt_layer_backward")
@@ -88,10 +92,10 @@ class PtAttentionFn(Function):
         for sz, p in zip(sizes, params):
             grads.append(gbuf[o:o + sz].view_as(p))
             o += sz
-        return (None, None, None, gxq, gxk, gxv, None, None, None, None, *grads)
+        return (None, None, None, gqkv, None, None, None, None, *grads)
 
 
-def pt_attention(layer, lv, x_q, x_k, x_v):
+def pt_attention(layer, lv, qkv):
     lp, lw = layer.linear_p, layer.linear_w
     params = (lp[0].weight, lp[0].bias, lp[1].weight, lp[1].bias, lp[3].weight, lp[3].bias,
               lw[0].weight, lw[0].bias, lw[2].weight, lw[2].bias, lw[3].weight, lw[3].bias, lw[5].weight, lw[5].bias)
@@ -101,7 +105,7 @@ def pt_attention(layer, lv, x_q, x_k, x_v):
     if training:
         for bn in (lp[1], lw[0], lw[3]):
             bn.num_batches_tracked += 1
-    return PtAttentionFn.apply(lv.rel, lv.rel_mom, lv.knn, x_q, x_k, x_v, buffers, lp[1].momentum, lp[1].eps,
+    return PtAttentionFn.apply(lv.rel, lv.rel_mom, lv.knn, qkv, buffers, lp[1].momentum, lp[1].eps,
                                training, *params)
 
 
@@ -112,3 +116,58 @@ def pt_rel(p, idx):
     mom = torch.empty(9, dtype=torch.float64, device=p.device)
     L.call("cb_pt_rel", n, k, p, idx, rel, mom, L.stream())
     return rel, mom
+
+
+# ------------------------------------------------------------------------------------------------
+# fused TransitionDown (blocks.py:69-73): out = max_k relu(bn(Wxyz rel + z[idx])),  z = x Wf^T
+# ------------------------------------------------------------------------------------------------
+class TransitionDownFn(Function):
+    @staticmethod
+    def forward(ctx, rel, idx, z, wxyz, gamma, beta, rm, rv, momentum, eps, training):
+        m, k = idx.shape
+        c = z.shape[1]
+        dev = z.device
+        z, wxyz = z.contiguous(), wxyz.contiguous()
+        out = torch.empty((m, c), dtype=torch.float32, device=dev)
+        argk = torch.empty((m, c), dtype=torch.uint8, device=dev)
+        bnbuf = torch.empty(4 * c, dtype=torch.float32, device=dev)
+        stats = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        L.call("cb_td_forward", m, k, c, rel, idx, z, wxyz, gamma, beta, rm, rv, float(momentum), float(eps), int(training), out,
+               argk, bnbuf, stats, L.stream())
+        ctx.save_for_backward(rel, idx, z, wxyz, gamma, bnbuf, out, argk)
+        ctx.training = int(training)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rel, idx, z, wxyz, gamma, bnbuf, out, argk = ctx.saved_tensors
+        m, k = idx.shape
+        c = z.shape[1]
+        dev = z.device
+        gz = torch.zeros_like(z)
+        gw = torch.zeros_like(wxyz)
+        gg = torch.empty(c, dtype=torch.float32, device=dev)
+        gb = torch.empty(c, dtype=torch.float32, device=dev)
+        scratch = torch.empty(7 * c + 16, dtype=torch.float32, device=dev)
+        L.call("cb_td_backward", m, k, c, rel, idx, z, wxyz, gamma, ctx.training, bnbuf, out, argk, g.contiguous(), gz, gw, gg, gb,
+               scratch, L.stream())
+        return None, None, gz, gw, gg, gb, None, None, None, None, None
+
+
+def transition_down(td, x, prev_level, level):
+    """fused body of TransitionDown.forward for stride > 1"""
+    from .linear_ops import fast_linear
+    w = td.linear.weight
+    z = fast_linear(x, w[:, 3:].contiguous())
+    bn = td.bn
+    if td.training:
+        bn.num_batches_tracked += 1
+    return TransitionDownFn.apply(level.rel_down, level.down_idx, z, w[:, :3], bn.weight, bn.bias, bn.running_mean,
+                                  bn.running_var, bn.momentum, bn.eps, td.training)
+
+
+def td_rel(p_support, p_query, idx):
+    m, k = idx.shape
+    rel = torch.empty((m, k, 3), dtype=torch.float32, device=p_support.device)
+    L.call("cb_td_rel", m, k, p_support, p_query, idx, rel, L.stream())
+    return rel

@@ -141,6 +141,8 @@ int cb_interpolation_backward(int n, int c, int k, const float *grad_output, con
  * the reference's state_dict (linear weights row-major [out][in]).
  * Buffers (caller-allocated): w2buf, abuf (n,k,c/8) f32 and bnbuf (cb_pt_bnbuf_floats(c)) are saved
  * for backward; stats = cb_pt_stats_doubles(c) doubles of scratch.  c in {32,64,128,256,512}, k <= 32.
+ * ld = row stride (floats) of x_q / x_k / x_v and of their gradients: c for separate tensors, 3c when they are the
+ * three column blocks of one fused (n,3c) projection.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct CbPtLayer {
     const float *w1, *b1;                                   /* linear_p.0  (3,3),(3)   */
@@ -158,7 +160,7 @@ size_t cb_pt_bnbuf_floats(int c);
 size_t cb_pt_stats_doubles(int c);
 /* rel (n,k,3) = p[idx] - p[n] and its 9 moments (3 sums, 6 second moments) — once per level */
 int cb_pt_rel(int n, int k, const float *p, const int *idx, float *rel, double *moments, void *stream);
-int cb_pt_layer_forward(int n, int k, int c, const CbPtLayer *L, const float *rel, const double *moments,
+int cb_pt_layer_forward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const double *moments,
                         const int *idx, const float *xq, const float *xk, const float *xv, float *out,
                         float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream);
 
@@ -242,6 +244,22 @@ int cb_adaptive_weight_backward(int n, int k, int c, int n0, const float *query_
                                 float *grad_b, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a5  fused TransitionDown (stride > 1)          replaces the body of TransitionDown.forward, pytorch/model/blocks.py:69-73
+ *     out[m,c'] = max_k relu(bn( Wxyz (p[idx]-p_new) + z[idx] )),  z = x Wf^T  (the bias-free Linear(3+c -> c') applied
+ *     BEFORE the gather; W = [Wxyz | Wf]).  rel (m,k,3) from cb_td_rel.  argk (m,c') uint8 and bnbuf (4c' floats) are
+ *     saved for backward; stats = 2c' doubles of scratch.  Backward: grad_z (n,c') and grad_wxyz (c',3) must be
+ *     zero-filled by the caller; grad_bn_* are overwritten; scratch >= 2c' doubles + 3c' floats, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int cb_td_rel(int m, int k, const float *p_support, const float *p_query, const int *idx, float *rel, void *stream);
+int cb_td_forward(int m, int k, int c, const float *rel, const int *idx, const float *z, const float *wxyz,
+                  const float *bn_weight, const float *bn_bias, float *running_mean, float *running_var, float momentum,
+                  float eps, int training, float *out, unsigned char *argk, float *bnbuf, double *stats, void *stream);
+int cb_td_backward(int m, int k, int c, const float *rel, const int *idx, const float *z, const float *wxyz,
+                   const float *bn_weight, int training, const float *bnbuf, const float *out, const unsigned char *argk,
+                   const float *grad_out, float *grad_z, float *grad_wxyz, float *grad_bn_weight, float *grad_bn_bias,
+                   float *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * tall-skinny FP32 linear layers of the per-point MLPs (nn.Linear calls of blocks.py:33,72,76,108,
  * 127-131 and the heads' MLPs): Y = X W^T + b ; dX = G W ; dW = G^T X, db = sum G (dW/db overwritten).
  * ---------------------------------------------------------------------------------------------- */
@@ -254,7 +272,7 @@ int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float
  * [dW1 9][db1 3][dbn1_w 3][dbn1_b 3][dW2 3c][db2 c][dbn2_w c][dbn2_b c][dW3 c*c/8][db3 c/8][dbn3_w c/8]
  * [dbn3_b c/8][dW4 (c/8)^2][db4 c/8].  scratch: cb_pt_bwd_scratch_floats(n,k,c) floats, 16-byte aligned. */
 size_t cb_pt_bwd_scratch_floats(int n, int k, int c);
-int cb_pt_layer_backward(int n, int k, int c, const CbPtLayer *L, const float *rel, const int *idx,
+int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const int *idx,
                          const float *xq, const float *xk, const float *xv, const float *w2buf,
                          const float *abuf, const float *bnbuf, const float *grad_out, float *grad_xq,
                          float *grad_xk, float *grad_xv, float *grad_params, float *scratch, void *stream);

@@ -105,3 +105,41 @@ def test_skinny_linear(n, ci, co, bias):
     assert rel_err(got[2], w.grad.float()) < 1e-4
     if bias:
         assert rel_err(got[3], b.grad.float()) < 1e-4
+
+
+@pytest.mark.parametrize("c_in,c_out,n_list", [(32, 64, [4000, 2500]), (64, 128, [1200, 800]), (256, 512, [300, 200])])
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_transition_down(c_in, c_out, n_list, training):
+    """fused TransitionDown (linear-before-gather + BN + ReLU + max) vs the op-by-op path (blocks.py:69-73)"""
+    from contrastboundary_b200 import model, pointops, ptlayer, synthetic
+    b = synthetic.make_batch(len(n_list), n_list, 77)
+    prev, lv = model.Level(), model.Level()
+    prev.p = torch.from_numpy(b["points"]).cuda(); prev.o = torch.from_numpy(b["offset"]).cuda()
+    new_lens = [x // 4 for x in n_list]
+    lv.o = torch.tensor(np.cumsum(new_lens), dtype=torch.int32, device="cuda")
+    fidx = pointops.furthestsampling_known(prev.p, prev.o, lv.o, max(n_list), sum(new_lens))
+    lv.p = prev.p[fidx.long()].contiguous()
+    lv.down_idx, _ = pointops.knn_raw(16, prev.p, lv.p, prev.o, lv.o, True)
+    lv.rel_down = ptlayer.td_rel(prev.p, lv.p, lv.down_idx)
+    td = model.TransitionDown(c_in, c_out, 4, 16).cuda()
+    cases.deterministic_init(td, 5)
+    td.train(training)
+    torch.manual_seed(3)
+    x = torch.randn(prev.p.shape[0], c_in, device="cuda")
+    g = torch.randn(lv.p.shape[0], c_out, device="cuda")
+    res = {}
+    for fused in (False, True):
+        td.fused = fused
+        td.bn.running_mean.zero_().add_(0.05); td.bn.running_var.fill_(1.3)
+        td.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        out = td(xi, prev, lv)
+        out.backward(g)
+        res[fused] = (out.detach(), xi.grad.clone(), td.linear.weight.grad.clone(), td.bn.weight.grad.clone(), td.bn.bias.grad.clone(),
+                      td.bn.running_mean.clone(), td.bn.running_var.clone())
+    a, r = res[True], res[False]
+    assert rel_err(a[0], r[0]) < 2e-5
+    assert outlier_fraction(a[1], r[1], 2e-4) < 2e-2, rel_err(a[1], r[1])
+    assert rel_err(a[2], r[2]) < 2e-2 and rel_err(a[3], r[3]) < 2e-2 and rel_err(a[4], r[4]) < 2e-2
+    if training:
+        assert rel_err(a[5], r[5]) < 1e-4 and rel_err(a[6], r[6]) < 1e-4
