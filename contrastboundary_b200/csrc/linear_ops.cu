@@ -138,6 +138,75 @@ __global__ void __launch_bounds__(LG_THREADS) k_skinny_wgrad(int n, int ci, int 
     if (db && tid < co) atomicAdd(db + tid, accb);
 }
 
+// register-tiled wgrad for ci % 4 == 0 and co % 4 == 0: thread owns 4x4 patches of dW
+// (patch p -> outputs o in [4*(p / (ci/4)), +4), inputs i in [4*(p % (ci/4)), +4)); per staged row two LDS.128 feed 16 FMAs.
+template <int PPT>
+__global__ void __launch_bounds__(LG_THREADS) k_skinny_wgrad4(int n, int ci, int co, const float *__restrict__ X,
+                                                              const float *__restrict__ G, float *__restrict__ dW,
+                                                              float *__restrict__ db, int rows_per_block)
+{
+    extern __shared__ __align__(16) float wsm[];
+    float *Xs = wsm;                       // [WG_ROWS][ci]
+    float *Gs = wsm + WG_ROWS * ci;        // [WG_ROWS][co]
+    const int tid = threadIdx.x;
+    const int pci = ci >> 2, npatch = (co >> 2) * pci;
+    float acc[PPT][4][4];
+    int po[PPT], pi[PPT];
+#pragma unroll
+    for (int t = 0; t < PPT; t++) {
+        const int p = tid + LG_THREADS * t;
+        po[t] = p < npatch ? (p / pci) * 4 : -1;
+        pi[t] = p < npatch ? (p % pci) * 4 : 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[t][a][b] = 0.f;
+    }
+    float accb = 0.f;
+    const long long r_begin = (long long)blockIdx.x * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > n) r_end = n;
+    for (long long r0 = r_begin; r0 < r_end; r0 += WG_ROWS) {
+        const int rows = (int)((r_end - r0) < WG_ROWS ? (r_end - r0) : WG_ROWS);
+        {
+            const float4 *xs = reinterpret_cast<const float4 *>(X + r0 * ci);
+            const float4 *gs = reinterpret_cast<const float4 *>(G + r0 * co);
+            for (int e = tid; e < rows * ci / 4; e += LG_THREADS) reinterpret_cast<float4 *>(Xs)[e] = __ldg(xs + e);
+            for (int e = tid; e < rows * co / 4; e += LG_THREADS) reinterpret_cast<float4 *>(Gs)[e] = __ldg(gs + e);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < PPT; t++) {
+            if (po[t] >= 0) {
+                for (int r = 0; r < rows; r++) {
+                    const float4 g = *reinterpret_cast<const float4 *>(Gs + r * co + po[t]);
+                    const float4 x = *reinterpret_cast<const float4 *>(Xs + r * ci + pi[t]);
+                    const float gg[4] = {g.x, g.y, g.z, g.w}, xx[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) acc[t][a][b] = fmaf(gg[a], xx[b], acc[t][a][b]);
+                }
+            }
+        }
+        if (db && tid < co) {
+            float s = 0.f;
+            for (int r = 0; r < rows; r++) s += Gs[r * co + tid];
+            accb += s;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int t = 0; t < PPT; t++)
+        if (po[t] >= 0) {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) atomicAdd(dW + (size_t)(po[t] + a) * ci + pi[t] + b, acc[t][a][b]);
+        }
+    if (db && tid < co) atomicAdd(db + tid, accb);
+}
+
 extern "C" int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream)
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && X && W && Y, CB_EINVAL, "cb_linear_forward: bad arguments");
@@ -172,6 +241,21 @@ extern "C" int cb_linear_wgrad(int n, int ci, int co, const float *X, const floa
     blocks = (n + rpb - 1) / rpb;
     const size_t smem = (size_t)WG_ROWS * (ci + co) * sizeof(float);
     const int opt = (ci * co + LG_THREADS - 1) / LG_THREADS;
+    if (ci % 4 == 0 && co % 4 == 0 && ((uintptr_t)X | (uintptr_t)G) % 16 == 0) {
+        const int ppt = (ci * co / 16 + LG_THREADS - 1) / LG_THREADS;
+#define WG4_LAUNCH(P)                                                                                           \
+    do {                                                                                                        \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_skinny_wgrad4<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_skinny_wgrad4<P><<<blocks, LG_THREADS, smem, st>>>(n, ci, co, X, G, dW, db, rpb);                     \
+    } while (0)
+        if (ppt <= 1) WG4_LAUNCH(1);
+        else if (ppt <= 2) WG4_LAUNCH(2);
+        else WG4_LAUNCH(4);
+#undef WG4_LAUNCH
+        CB_COUNT(3);
+        CB_CUDA_CHECK("cb_linear_wgrad");
+        return CB_OK;
+    }
 #define WG_LAUNCH(O)                                                                                           \
     do {                                                                                                       \
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_skinny_wgrad<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -169,14 +169,24 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_softmax(int n, int k, int
         }
         // phase C: dW4[j][i] += sum_rows dw4[row][j] * v[row][i]
         const int rows = PB * k;
+        const int npairs = CS * CS;
+        if (npairs <= PT_THREADS) {
+            // few pairs (CS <= 16): every thread takes one pair and a strided subset of the tile's rows
+            const int pair = threadIdx.x % npairs, sub = threadIdx.x / npairs, nsub = PT_THREADS / npairs;
+            const int j = pair / CS, i = pair % CS;
+            float s = 0.f;
+            for (int r = sub; r < rows; r += nsub) s += sdw[r * CS + j] * sv[r * CS + i];
+            accw[0] += s;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            const int pair = threadIdx.x + e * PT_THREADS;
-            if (pair < CS * CS) {
-                const int j = pair / CS, i = pair % CS;
-                float s = 0.f;
-                for (int r = 0; r < rows; r++) s += sdw[r * CS + j] * sv[r * CS + i];
-                accw[e] += s;
+            for (int e = 0; e < 16; e++) {
+                const int pair = threadIdx.x + e * PT_THREADS;
+                if (pair < npairs) {
+                    const int j = pair / CS, i = pair % CS;
+                    float s = 0.f;
+                    for (int r = 0; r < rows; r++) s += sdw[r * CS + j] * sv[r * CS + i];
+                    accw[e] += s;
+                }
             }
         }
         __syncthreads();
@@ -187,10 +197,14 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_softmax(int n, int k, int
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * CS; i += PT_THREADS) atomicAdd(sums3 + i, (double)sacc[i]);
     for (int i = threadIdx.x; i < CS; i += PT_THREADS) atomicAdd(gb4 + i, sacc[2 * CS + i]);
+    if (CS * CS <= PT_THREADS) {
+        atomicAdd(gW4 + threadIdx.x % (CS * CS), accw[0]);
+    } else {
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const int pair = threadIdx.x + e * PT_THREADS;
-        if (pair < CS * CS) atomicAdd(gW4 + pair, accw[e]);
+        for (int e = 0; e < 16; e++) {
+            const int pair = threadIdx.x + e * PT_THREADS;
+            if (pair < CS * CS) atomicAdd(gW4 + pair, accw[e]);
+        }
     }
 }
 

@@ -23,7 +23,8 @@ class TrainStep:
         self.opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay,
                                    fused=self.device.type == "cuda")
         self.model.train()
-        self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None     # sampling chain
+        self.side2 = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None    # neighbour searches
         self._geo = {}
 
     # ------------------------------------------------------------------------------------------
@@ -38,7 +39,7 @@ class TrainStep:
         self.side.wait_stream(main)                      # the batch's H2D copies were enqueued on `main`
         with torch.cuda.stream(self.side):
             levels = build_geometry(batch["points"], batch["offset"], batch["offset_host"], self.cfg,
-                                    self.cfg.contrast is not None)
+                                    self.cfg.contrast is not None, knn_stream=self.side2)
             ev = torch.cuda.Event()
             ev.record(self.side)
         self._geo[id(batch)] = (levels, ev)

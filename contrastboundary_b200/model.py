@@ -13,6 +13,7 @@ forward of which 31 are exact repeats) and without any `.item()
 kernels of libcbops (ptlayer.py / cbl.py); `fused=False` keeps the reference's op-by-op math on
 top of the stand-alone pointops kernels (used for parity tests of the fused path).
 """
+import contextlib
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -86,7 +87,7 @@ def _lens(o_host):
     return [o_host[0]] + [o_host[i] - o_host[i - 1] for i in range(1, len(o_host))]
 
 
-def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
+def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True, knn_stream=None):
     """All sampling / neighbour searches of one forward.  p0 (n,3) f32, o0 (b) int32 cumulative ends,
     o0_host = the same offsets as a python list (known from collate; avoids device->host syncs)."""
     levels = []
@@ -105,26 +106,52 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
     flat = _upload_i32([v for oh_ in ohs[1:] for v in oh_], p0.device)
     b = len(o0_host)
     o_dev = [o0] + [flat[(l - 1) * b:l * b] for l in range(1, nl)]
-    p, o, oh = p0, o0, ohs[0]
+    # --- sampling chain (serial across levels) on the current stream; neighbour searches optionally on `knn_stream`
+    cur = torch.cuda.current_stream(p0.device)
+    use_b = knn_stream is not None
+    ready = []
+    p, o = p0, o0
     for l in range(nl):
         lv = Level()
         if l > 0:
             prev = levels[-1]
-            oh, o = ohs[l], o_dev[l]
-            fidx = pointops.furthestsampling_known(prev.p, prev.o, o, max(_lens(prev.o_host)), oh[-1])
+            o = o_dev[l]
+            fidx = pointops.furthestsampling_known(prev.p, prev.o, o, max(_lens(prev.o_host)), ohs[l][-1])
             p = prev.p[fidx.long(), :].contiguous()
             lv.fps_idx = fidx
+        lv.p, lv.o, lv.o_host, lv.n = p, o, ohs[l], p.shape[0]
+        levels.append(lv)
+        if use_b:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            ready.append(ev)
+    ctx = torch.cuda.stream(knn_stream) if use_b else contextlib.nullcontext()
+    with ctx:
+        _searches(levels, cfg, with_contrast, ready, knn_stream)
+    if use_b:
+        cur.wait_stream(knn_stream)
+    return levels
+
+
+def _searches(levels, cfg, with_contrast, ready, knn_stream):
+    nl = len(levels)
+    p0 = levels[0].p
+    for l in range(nl):
+        lv = levels[l]
+        if ready:
+            knn_stream.wait_event(ready[l])
+        p, o = lv.p, lv.o
+        if l > 0:
+            prev = levels[l - 1]
             # neighbours of the new points among the previous level (blocks.py:71)
             lv.down_idx, _ = pointops.knn_raw(cfg.nsample_backbone[l], prev.p, p, prev.o, o, True)
             if cfg.fused:
                 from . import ptlayer
                 lv.rel_down = ptlayer.td_rel(prev.p, p, lv.down_idx)
-        lv.p, lv.o, lv.o_host, lv.n = p, o, oh, p.shape[0]
         lv.knn, _ = pointops.knn_raw(cfg.nsample_backbone[l], p, p, o, o, True)          # blocks.py:34-35
         if cfg.fused:
             from . import ptlayer
             lv.rel, lv.rel_mom = ptlayer.pt_rel(p, lv.knn)
-        levels.append(lv)
     for l in range(nl - 1):
         # TransitionUp interpolation l+1 -> l, k=3 (blocks.py:108, pointops.py:164-178)
         fine, coarse = levels[l], levels[l + 1]
@@ -147,7 +174,6 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True):
                 # sub-scene labels: kr nearest full-resolution points (basic_operators.py:20-30)
                 lv.label_idx, _ = pointops.knn_raw(kr, levels[0].p, lv.p, levels[0].o, lv.o, True)
             lv.cbl_idx, _ = pointops.knn_raw(cfg.nsample[l], lv.p, lv.p, lv.o, lv.o, True)   # heads.py:192
-    return levels
 
 
 # ------------------------------------------------------------------------------------------------
