@@ -80,10 +80,17 @@ static int launch_skinny(int n, int K, int N, const float *A, const float *W, in
                          float *C, cudaStream_t st)
 {
     const int gx = (n + LG_BM - 1) / LG_BM;
-    if (N <= 16) k_skinny_gemm<1><<<dim3(gx, 1), LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
-    else if (N <= 32) k_skinny_gemm<2><<<dim3(gx, 1), LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
-    else if (N <= 64) k_skinny_gemm<4><<<dim3(gx, 1), LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
-    else k_skinny_gemm<8><<<dim3(gx, (N + 127) / 128), LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
+    // column tile: the width in {128, 64, 32, 16} with the fewest padded columns (ties -> wider)
+    int best = 128, waste = (N + 127) / 128 * 128 - N;
+    for (int nt = 64; nt >= 16; nt >>= 1) {
+        const int w = (N + nt - 1) / nt * nt - N;
+        if (w < waste) { waste = w; best = nt; }
+    }
+    const dim3 grid(gx, (N + best - 1) / best);
+    if (best == 16) k_skinny_gemm<1><<<grid, LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
+    else if (best == 32) k_skinny_gemm<2><<<grid, LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
+    else if (best == 64) k_skinny_gemm<4><<<grid, LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
+    else k_skinny_gemm<8><<<grid, LG_THREADS, 0, st>>>(n, K, N, A, W, ldw, transB, bias, C);
     return 0;
 }
 

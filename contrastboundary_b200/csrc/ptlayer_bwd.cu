@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, int ld,
     constexpr int RG = PT_THREADS / CT;            // row slots per block
     constexpr int TR = 64;                         // rows staged per iteration (TR / RG rows per thread)
     const PtSmall sp = pt_small_load(smalld);
-    __shared__ float sdw2[TR][CS];
+    __shared__ __align__(16) float sdw2[TR][CS];
     __shared__ float sg1[TR][3];
     __shared__ int sidx[TR];
     const int tr = threadIdx.x / CT;
@@ -296,10 +296,10 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, int ld,
                     const float uu = fmaxf(y2, 0.f);
                     float du = 0.f;
 #pragma unroll
-                    for (int i = 0; i < CS; i++) {
-                        const float d = sdw2[r][i];
-                        du += w3c[i] * d;
-                        acc[i] += d * uu;
+                    for (int i = 0; i < CS; i += 4) {
+                        const float4 d4 = *reinterpret_cast<const float4 *>(&sdw2[r][i]);   // one LDS.128 feeds 8 FMAs
+                        du += w3c[i] * d4.x + w3c[i + 1] * d4.y + w3c[i + 2] * d4.z + w3c[i + 3] * d4.w;
+                        acc[i] += d4.x * uu; acc[i + 1] += d4.y * uu; acc[i + 2] += d4.z * uu; acc[i + 3] += d4.w * uu;
                     }
                     const float dy2 = y2 > 0.f ? du : 0.f;
                     sa += dy2;

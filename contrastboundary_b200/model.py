@@ -134,37 +134,44 @@ def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True, knn_stre
 
 
 def _searches(levels, cfg, with_contrast, ready, knn_stream):
+    """every neighbour search of one forward.  One uniform grid per support level, shared by all the query sets
+    and K values that search it (the reference rebuilds nothing but also re-scans everything: brute force)."""
     nl = len(levels)
-    p0 = levels[0].p
+    n0 = levels[0].n
+    grids = []
     for l in range(nl):
         lv = levels[l]
         if ready:
             knn_stream.wait_event(ready[l])
+        grids.append(pointops.grid_for(lv.p, lv.o, 16, n0))
+    knn = pointops.knn_on_grid
+    for l in range(nl):
+        lv = levels[l]
         p, o = lv.p, lv.o
         if l > 0:
             prev = levels[l - 1]
             # neighbours of the new points among the previous level (blocks.py:71)
-            lv.down_idx, _ = pointops.knn_raw(cfg.nsample_backbone[l], prev.p, p, prev.o, o, True)
+            lv.down_idx, _ = knn(grids[l - 1], cfg.nsample_backbone[l], prev.p, p, prev.o, o)
             if cfg.fused:
                 from . import ptlayer
                 lv.rel_down = ptlayer.td_rel(prev.p, p, lv.down_idx)
-        lv.knn, _ = pointops.knn_raw(cfg.nsample_backbone[l], p, p, o, o, True)          # blocks.py:34-35
+        lv.knn, _ = knn(grids[l], cfg.nsample_backbone[l], p, p, o, o)                    # blocks.py:34-35
         if cfg.fused:
             from . import ptlayer
             lv.rel, lv.rel_mom = ptlayer.pt_rel(p, lv.knn)
     for l in range(nl - 1):
         # TransitionUp interpolation l+1 -> l, k=3 (blocks.py:108, pointops.py:164-178)
         fine, coarse = levels[l], levels[l + 1]
-        idx, dist = pointops.knn_raw(3, coarse.p, fine.p, coarse.o, fine.o, True)
+        idx, dist = knn(grids[l + 1], 3, coarse.p, fine.p, coarse.o, fine.o)
         dr = 1.0 / (dist + 1e-8)
         fine.up_idx, fine.up_w = idx, (dr / dr.sum(1, keepdim=True)).contiguous()
     for l in range(1, nl):
         # MultiHead nearest upsample l -> 0, k=1 (heads.py:44-51)
-        levels[l].head_idx, _ = pointops.knn_raw(1, levels[l].p, levels[0].p, levels[l].o, levels[0].o, True)
+        levels[l].head_idx, _ = knn(grids[l], 1, levels[l].p, levels[0].p, levels[l].o, levels[0].o)
     # dec5 per-scene mean (blocks.py:94-103)
     last = levels[-1]
     # scene id of every point of the last level, device-side (tensor-indexed assignment would sync the host)
-    last.scene_id = torch.searchsorted(last.o.long(), torch.arange(last.n, device=p0.device), right=True)
+    last.scene_id = torch.searchsorted(last.o.long(), torch.arange(last.n, device=last.p.device), right=True)
     if with_contrast and cfg.contrast is not None:
         kr = 1
         for l in range(nl):
@@ -172,8 +179,8 @@ def _searches(levels, cfg, with_contrast, ready, knn_stream):
             if l > 0:
                 kr *= cfg.nstride[l - 1]
                 # sub-scene labels: kr nearest full-resolution points (basic_operators.py:20-30)
-                lv.label_idx, _ = pointops.knn_raw(kr, levels[0].p, lv.p, levels[0].o, lv.o, True)
-            lv.cbl_idx, _ = pointops.knn_raw(cfg.nsample[l], lv.p, lv.p, lv.o, lv.o, True)   # heads.py:192
+                lv.label_idx, _ = knn(grids[0], kr, levels[0].p, lv.p, levels[0].o, lv.o)
+            lv.cbl_idx, _ = knn(grids[l], cfg.nsample[l], lv.p, lv.p, lv.o, lv.o)        # heads.py:192
 
 
 # ------------------------------------------------------------------------------------------------

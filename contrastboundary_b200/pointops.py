@@ -106,6 +106,30 @@ def knn_raw(nsample, xyz, new_xyz, offset, new_offset, sqrt_dist=True):
     return idx, dist
 
 
+def grid_for(xyz, offset, nsample_hint, m_max):
+    """build the search grid of a support set once (cb_grid_build); pass the result to knn_on_grid"""
+    n, b = xyz.shape[0], offset.shape[0]
+    nbytes = L.lib().cb_knn_workspace_bytes(n, int(m_max), b)
+    ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=xyz.device)
+    rc = L.lib().cb_grid_build(L.ptr(xyz), C.c_int(n), L.ptr(offset), C.c_int(b), C.c_int(int(nsample_hint)), L.ptr(ws),
+                               C.c_size_t(ws.numel()), L.stream())
+    L.check(rc, "cb_grid_build")
+    return ws
+
+
+def knn_on_grid(grid, nsample, xyz, new_xyz, offset, new_offset, sqrt_dist=True):
+    """same result as knn_raw, on a grid prebuilt by grid_for (one build, many query sets / K)"""
+    n, m, b = xyz.shape[0], new_xyz.shape[0], offset.shape[0]
+    dev = xyz.device
+    idx = torch.empty((m, nsample), dtype=torch.int32, device=dev)
+    dist = torch.empty((m, nsample), dtype=torch.float32, device=dev)
+    rc = L.lib().cb_knn_query_grid(C.c_int(m), C.c_int(int(nsample)), L.ptr(xyz), C.c_int(n), L.ptr(new_xyz), L.ptr(offset),
+                                   L.ptr(new_offset), C.c_int(b), L.ptr(idx), L.ptr(dist), C.c_int(1 if sqrt_dist else 0),
+                                   L.ptr(grid), C.c_size_t(grid.numel()), L.stream())
+    L.check(rc, "cb_knn_query_grid")
+    return idx, dist
+
+
 class KNNQuery(Function):
     @staticmethod
     def forward(ctx, nsample, xyz, new_xyz, offset, new_offset):
