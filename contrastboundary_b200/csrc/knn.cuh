@@ -175,30 +175,44 @@ __device__ __forceinline__ cb_key cb_shfl_xor_key(cb_key k, int m)
 // Compare-exchange networks on (d bits, idx) pairs.  Only the distance is compared; on equal distances
 // both lanes keep their own element (ties are re-done by the exact replay anyway), which keeps the
 // multiset intact with a single 32-bit compare per stage.
-__device__ __forceinline__ void cb_cmpx(unsigned &d, unsigned &i, int j, bool keep_min)
+// `flip` is 0 for a lane that keeps the minimum of the pair and 0xffffffff for one that keeps the maximum
+// (a > b  <=>  ~a < ~b for unsigned), so one compare serves both directions.
+__device__ __forceinline__ void cb_cmpx(unsigned &d, unsigned &i, int j, unsigned flip)
 {
     const unsigned pd = __shfl_xor_sync(CB_FULL_MASK, d, j), pi = __shfl_xor_sync(CB_FULL_MASK, i, j);
-    const bool take = keep_min ? (pd < d) : (pd > d);
+    const bool take = (pd ^ flip) < (d ^ flip);
     d = take ? pd : d;
     i = take ? pi : i;
+}
+// per-lane direction masks of the 15-stage sort (bit s) and the 5-stage merge, computed once per thread
+__device__ __forceinline__ unsigned cb_sort_dirs(int lane)
+{
+    unsigned m = 0;
+    int s = 0;
+    for (int size = 2; size <= 32; size <<= 1) {
+        const bool up = size == 32 ? true : ((lane & size) == 0);
+        for (int j = size >> 1; j > 0; j >>= 1, s++)
+            if ((((lane & j) == 0) == up) == false) m |= 1u << s;       // bit set -> keep max
+    }
+    return m;
 }
 // ascending bitonic merge of a bitonic 32-sequence held one key per lane
 __device__ __forceinline__ cb_key cb_bitonic_merge32(cb_key k, int lane)
 {
     unsigned d = (unsigned)(k >> 32), i = (unsigned)k;
 #pragma unroll
-    for (int j = 16; j > 0; j >>= 1) cb_cmpx(d, i, j, (lane & j) == 0);
+    for (int j = 16; j > 0; j >>= 1) cb_cmpx(d, i, j, (lane & j) ? 0xffffffffu : 0u);
     return ((cb_key)d << 32) | i;
 }
 // full ascending bitonic sort of 32 keys
-__device__ __forceinline__ cb_key cb_bitonic_sort32(cb_key k, int lane)
+__device__ __forceinline__ cb_key cb_bitonic_sort32(cb_key k, unsigned dirs)
 {
     unsigned d = (unsigned)(k >> 32), i = (unsigned)k;
+    int s = 0;
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {
-        const bool up = size == 32 ? true : ((lane & size) == 0);
 #pragma unroll
-        for (int j = size >> 1; j > 0; j >>= 1) cb_cmpx(d, i, j, ((lane & j) == 0) == up);
+        for (int j = size >> 1; j > 0; j >>= 1, s++) cb_cmpx(d, i, j, 0u - ((dirs >> s) & 1u));
     }
     return ((cb_key)d << 32) | i;
 }
@@ -210,10 +224,12 @@ struct CbTopKB {
     float thr;          // pre-filter threshold: (K+1)-th smallest (entry min(K, 32*KPL-1))
     float tie_val;      // only needed when K == 32*KPL: a dropped / evicted value equal to the then-last entry
     int K, lane, cap_e;
+    unsigned dirs;
 
     __device__ __forceinline__ void init(int K_, int lane_, int pad_idx)
     {
         K = K_; lane = lane_;
+        dirs = cb_sort_dirs(lane_);
         cap_e = K < 32 * KPL - 1 ? K : 32 * KPL - 1;
 #pragma unroll
         for (int j = 0; j < KPL; j++) key[j] = cb_make_key(1e10f, pad_idx);
@@ -274,7 +290,7 @@ struct CbTopKB {
                 }
             }
         } else {
-            c = cb_bitonic_sort32(c, lane);
+            c = cb_bitonic_sort32(c, dirs);
             // merge into register 0, carry the upper half into the next register
 #pragma unroll
             for (int j = 0; j < KPL; j++) {
@@ -358,7 +374,8 @@ __device__ __forceinline__ bool cb_grid_search(TK &tk, const CbScene &sc, float 
     r0 = max(r0, max(-cz, cz - (sc.nz - 1)));
     if (r0 > CB_KNN_MAX_RING) return false;
 
-    for (int r = r0;; r++) {
+    const int r_first = max(r0, 1);     // first pass = the whole (2r+1)^3 block (cells nearer than r0 lie outside the grid)
+    for (int r = r_first;; r++) {
         // rows (y,z) of shell r that fall inside the grid
         const int ya = max(cy - r, 0), yb = min(cy + r, sc.ny - 1);
         const int za = max(cz - r, 0), zb = min(cz + r, sc.nz - 1);
@@ -371,7 +388,7 @@ __device__ __forceinline__ bool cb_grid_search(TK &tk, const CbScene &sc, float 
                 const int y = ya + row % wy, z = za + row / wy;
                 const int dy = y - cy, dz = z - cz;
                 const int rowbase = sc.cell_base + (z * sc.ny + y) * sc.nx;
-                const bool outer = (abs(dy) == r) || (abs(dz) == r);
+                const bool outer = (r == r_first) || (abs(dy) == r) || (abs(dz) == r);
                 if (outer) {
                     const int xa = max(cx - r, 0), xb = min(cx + r, sc.nx - 1);
                     if (xa <= xb) {

@@ -13,7 +13,7 @@
 #include "knn.cuh"
 
 #define KG_WARPS 8
-static int g_kg_chunk_bytes = 2048;    // bytes per TMA chunk (two chunks are in flight per warp)
+static int g_kg_chunk_bytes = 4096;    // bytes per TMA chunk (two chunks are in flight per warp)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
