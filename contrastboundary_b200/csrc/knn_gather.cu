@@ -13,7 +13,8 @@
 #include "knn.cuh"
 
 #define KG_WARPS 8
-static int g_kg_chunk_bytes = 4096;    // bytes per TMA chunk (two chunks are in flight per warp)
+static int g_kg_chunk_bytes = 4096;
+static int g_kg_ws = 1;              // 1 = warp-specialised kernel for K <= 64 (cb_knn_gather_set_mode)    // bytes per TMA chunk (two chunks are in flight per warp)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -156,6 +157,163 @@ __global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int 
     if (lane == 0) bulk_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised variant (K <= 64): 7 SEARCH warps per CTA run the ring search back to back and push
+// (query, K neighbour indices) records into a shared-memory queue; 1 COPY warp pops them and drives the TMA
+// engine through a ring of KGW_NS slabs with KGW_LA chunks of loads always in flight ahead of the stores.
+// Search warps never wait for memory traffic, the copy warp never searches: the kernel runs at
+// max(search issue time, HBM write time) instead of their per-warp sum.
+// ---------------------------------------------------------------------------------------------
+#define KGW_SEARCH 7
+#define KGW_NS 8          // slabs in the ring
+#define KGW_LA 4          // chunks of loads in flight ahead of the store cursor
+#define KGW_QN 16         // queue slots
+
+template <int KPL>
+__global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, int R, int slab_bytes,
+                                                       const float *__restrict__ new_xyz, const float *__restrict__ feat,
+                                                       const int *__restrict__ new_offset, int b, int self_query,
+                                                       const CbScene *__restrict__ scenes, const int *__restrict__ cells,
+                                                       const float4 *__restrict__ sorted, int *__restrict__ idx,
+                                                       float *__restrict__ dist2, float *__restrict__ grouped,
+                                                       CbGridHeader *hdr, int *flagged)
+{
+    extern __shared__ __align__(128) unsigned char kg_smem[];
+    __shared__ CbWarpScratch scratch[KGW_SEARCH];
+    __shared__ __align__(8) unsigned long long full_bar[KGW_NS];
+    __shared__ int q_entry[KGW_QN][1 + 32 * KPL];
+    __shared__ volatile int q_seq[KGW_QN];
+    __shared__ int q_tail;
+    __shared__ volatile int q_head;
+    __shared__ volatile int producers_done;
+    __shared__ int ch_q[KGW_NS], ch_e0[KGW_NS], ch_rows[KGW_NS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x < KGW_QN) q_seq[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        q_tail = 0; q_head = 0; producers_done = 0;
+        for (int s = 0; s < KGW_NS; s++) mbar_init(smem_u32(&full_bar[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned row_bytes = (unsigned)c * 4u;
+    if (wib < KGW_SEARCH) {
+        // ------------------------------ search warps ------------------------------
+        const int stride = gridDim.x * KGW_SEARCH;
+        for (int w = blockIdx.x * KGW_SEARCH + wib; w < m; w += stride) {
+            int q = w;
+            float qx, qy, qz;
+            if (self_query) {
+                const float4 p = __ldg(sorted + w);
+                q = __float_as_int(p.w); qx = p.x; qy = p.y; qz = p.z;
+            } else {
+                qx = __ldg(new_xyz + 3 * q); qy = __ldg(new_xyz + 3 * q + 1); qz = __ldg(new_xyz + 3 * q + 2);
+            }
+            const int s = cb_scene_of(q, new_offset, b);
+            const CbScene sc = scenes[s];
+            typename CbTopKSel<KPL>::type tk;
+            tk.init(K, lane, sc.start);
+            bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+            if (ok && tk.has_tie()) ok = false;
+            if (!ok) {
+                if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const int e = j * 32 + lane;
+                if (e < K) {
+                    idx[(size_t)q * K + e] = tk.out_i(j);
+                    dist2[(size_t)q * K + e] = tk.out_d(j);
+                }
+            }
+            // enqueue (q, idx[0..K))
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(&q_tail, 1);
+                while (t - q_head >= KGW_QN) { }            // queue full: wait for the copy warp
+            }
+            t = __shfl_sync(CB_FULL_MASK, t, 0);
+            const int slot = t % KGW_QN;
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const int e = j * 32 + lane;
+                if (e < K) q_entry[slot][1 + e] = tk.out_i(j);
+            }
+            if (lane == 0) q_entry[slot][0] = q;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) q_seq[slot] = t + 1;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd((int *)&producers_done, 1); }
+    } else {
+        // ------------------------------ copy warp ------------------------------
+        const unsigned slab0 = smem_u32(kg_smem);
+        const int nchunks = (K + R - 1) / R;
+        unsigned phase_bits = 0;          // bit s = parity to wait for on slab s
+        int itemA = 0, chunkA = 0;        // issue cursor: item (queue sequence number) and chunk within it
+        int gA = 0, gB = 0;               // global chunk counters: issued / stored
+        bool haveA = false;               // item at itemA is available (published)
+        for (;;) {
+            // ---- issue loads while fewer than KGW_LA chunks are in flight
+            bool progressed = false;
+            while (gA - gB < KGW_LA) {
+                if (!haveA) {
+                    const int slot = itemA % KGW_QN;
+                    if (q_seq[slot] != itemA + 1) break;                 // nothing published yet
+                    __threadfence_block();
+                    haveA = true;
+                }
+                const int slot = itemA % KGW_QN;
+                const int sl = gA % KGW_NS;
+                if (gA >= KGW_NS) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(KGW_NS - KGW_LA - 1) : "memory");
+                    __syncwarp();
+                }
+                const int e0 = chunkA * R;
+                const int rows = min(R, K - e0);
+                const unsigned bar = smem_u32(&full_bar[sl]);
+                if (lane == 0) {
+                    mbar_expect_tx(bar, (unsigned)rows * row_bytes);
+                    ch_q[sl] = q_entry[slot][0]; ch_e0[sl] = e0; ch_rows[sl] = rows;
+                }
+                __syncwarp();
+                if (lane < rows)
+                    bulk_g2s(slab0 + (unsigned)sl * (unsigned)slab_bytes + (unsigned)lane * row_bytes,
+                             feat + (size_t)q_entry[slot][1 + e0 + lane] * c, row_bytes, bar);
+                gA++;
+                progressed = true;
+                if (++chunkA == nchunks) {           // all chunks of this item issued: release its queue slot
+                    chunkA = 0; itemA++; haveA = false;
+                    __syncwarp();
+                    if (lane == 0) q_head = itemA;
+                }
+            }
+            // ---- store the oldest chunk in flight
+            if (gB < gA) {
+                const int sl = gB % KGW_NS;
+                mbar_wait(smem_u32(&full_bar[sl]), (phase_bits >> sl) & 1u);
+                phase_bits ^= 1u << sl;
+                if (lane == 0)
+                    bulk_s2g(grouped + ((size_t)ch_q[sl] * K + ch_e0[sl]) * c, slab0 + (unsigned)sl * (unsigned)slab_bytes,
+                             (unsigned)ch_rows[sl] * row_bytes);
+                __syncwarp();
+                gB++;
+                progressed = true;
+            }
+            if (!progressed) {
+                // nothing in flight and nothing published: finished when every producer is done and the queue is drained
+                if (producers_done == KGW_SEARCH) {
+                    __threadfence_block();
+                    const int tail = *((volatile int *)&q_tail);
+                    if (itemA >= tail && gB == gA) break;
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+}
+
 // generic gather of the rows of flagged queries (after the exact replay rewrote their idx)
 __global__ void k_regather_flagged(int K, int c, const float *__restrict__ feat, const int *__restrict__ idx,
                                    float *__restrict__ grouped, const CbGridHeader *hdr, const int *__restrict__ flagged)
@@ -187,6 +345,29 @@ static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const 
     if (per_sm < 1) per_sm = 1;
     int blocks = 148 * per_sm;
     if (blocks > (m + KG_WARPS - 1) / KG_WARPS) blocks = (m + KG_WARPS - 1) / KG_WARPS;
+    if (nsample <= 64 && g_kg_ws) {
+        // warp-specialised kernel: chunk = R rows with R <= 32, R * row_bytes <= chunk bytes
+        const size_t smem_ws = (size_t)KGW_NS * slab;
+        int per = (int)((220 * 1024) / (smem_ws + 8192));
+        if (per > 4) per = 4;
+        if (per < 1) per = 1;
+        int blocks_ws = 148 * per;
+        if (blocks_ws > (m + KGW_SEARCH - 1) / KGW_SEARCH) blocks_ws = (m + KGW_SEARCH - 1) / KGW_SEARCH;
+        if (nsample <= 32) {
+            cudaFuncSetAttribute(k_knn_gather_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+            k_knn_gather_ws<1><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, self_query,
+                                                                v.scenes, v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged);
+        } else {
+            cudaFuncSetAttribute(k_knn_gather_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+            k_knn_gather_ws<2><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, self_query,
+                                                                v.scenes, v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged);
+        }
+        cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
+        k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
+        CB_COUNT(4);
+        CB_CUDA_CHECK("cb_knn_gather");
+        return CB_OK;
+    }
 #define KG_LAUNCH(KPL)                                                                                              \
     do {                                                                                                            \
         cudaFuncSetAttribute(k_knn_gather<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
@@ -210,6 +391,8 @@ static bool kg_tma_ok(int c, int nsample, const float *feat, const float *groupe
 {
     return (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 && (size_t)c * 4 <= 16384;
 }
+
+extern "C" int cb_knn_gather_set_mode(int warp_specialised) { g_kg_ws = warp_specialised ? 1 : 0; return g_kg_ws; }
 
 extern "C" int cb_knn_gather_set_chunk_bytes(int bytes)
 {
