@@ -13,8 +13,8 @@
 #include "knn.cuh"
 
 #define KG_WARPS 8
-static int g_kg_chunk_bytes = 4096;
-static int g_kg_ws = 1;              // 1 = warp-specialised kernel for K <= 64 (cb_knn_gather_set_mode)    // bytes per TMA chunk (two chunks are in flight per warp)
+static int g_kg_chunk_bytes = 8192;
+static int g_kg_ws = 3;              // 0 one-warp TMA | 1,2,3 warp-specialised TMA rings (8/4, 12/8, 6/4) | 4 direct register copy    // bytes per TMA chunk (two chunks are in flight per warp)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -165,11 +165,9 @@ __global__ void __launch_bounds__(KG_WARPS * 32) k_knn_gather(int m, int K, int 
 // max(search issue time, HBM write time) instead of their per-warp sum.
 // ---------------------------------------------------------------------------------------------
 #define KGW_SEARCH 7
-#define KGW_NS 8          // slabs in the ring
-#define KGW_LA 4          // chunks of loads in flight ahead of the store cursor
 #define KGW_QN 16         // queue slots
 
-template <int KPL>
+template <int KPL, int KGW_NS, int KGW_LA>
 __global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, int R, int slab_bytes,
                                                        const float *__restrict__ new_xyz, const float *__restrict__ feat,
                                                        const int *__restrict__ new_offset, int b, int self_query,
@@ -314,6 +312,86 @@ __global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct variant: every warp searches and then copies its K rows itself with 16-byte register moves
+// (U rows = up to 16 independent LDG.128 per lane in flight, streaming STG.128 to the contiguous
+// grouped[q] block).  No shared-memory staging, so 32 warps per SM keep both the search issue slots and
+// the memory pipes busy; the TMA variants above trade that for zero register traffic.
+// ---------------------------------------------------------------------------------------------
+template <int KPL, int T /* float4 per lane per row = ceil(c / 128) */>
+__global__ void __launch_bounds__(256, 4) k_knn_gather_direct(int m, int K, int c, const float *__restrict__ new_xyz,
+                                                              const float *__restrict__ feat,
+                                                              const int *__restrict__ new_offset, int b, int self_query,
+                                                              const CbScene *__restrict__ scenes,
+                                                              const int *__restrict__ cells,
+                                                              const float4 *__restrict__ sorted, int *__restrict__ idx,
+                                                              float *__restrict__ dist2, float *__restrict__ grouped,
+                                                              CbGridHeader *hdr, int *flagged)
+{
+    __shared__ CbWarpScratch scratch[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int cv = c >> 2;                         // float4 per row
+    constexpr int U = T == 1 ? 8 : (T == 2 ? 8 : 4);     // rows in flight
+    const int total_warps = gridDim.x * 8;
+    for (int w = blockIdx.x * 8 + wib; w < m; w += total_warps) {
+        int q = w;
+        float qx, qy, qz;
+        if (self_query) {
+            const float4 p = __ldg(sorted + w);
+            q = __float_as_int(p.w); qx = p.x; qy = p.y; qz = p.z;
+        } else {
+            qx = __ldg(new_xyz + 3 * q); qy = __ldg(new_xyz + 3 * q + 1); qz = __ldg(new_xyz + 3 * q + 2);
+        }
+        const int s = cb_scene_of(q, new_offset, b);
+        const CbScene sc = scenes[s];
+        typename CbTopKSel<KPL>::type tk;
+        tk.init(K, lane, sc.start);
+        bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+        if (ok && tk.has_tie()) ok = false;
+        if (!ok) {
+            if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < KPL; j++) {
+            const int e = j * 32 + lane;
+            if (e < K) {
+                idx[(size_t)q * K + e] = tk.out_i(j);
+                dist2[(size_t)q * K + e] = tk.out_d(j);
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(grouped + (size_t)q * K * c);
+        for (int e0 = 0; e0 < K; e0 += U) {
+            float4 v[U][T];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int e = e0 + u;
+                int nb = 0;
+#pragma unroll
+                for (int j = 0; j < KPL; j++) {
+                    const int t = __shfl_sync(CB_FULL_MASK, tk.out_i(j), e & 31);
+                    if ((e >> 5) == j) nb = t;
+                }
+                const float4 *src = reinterpret_cast<const float4 *>(feat + (size_t)nb * c);
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const int f = lane + 32 * t;
+                    if (e < K && f < cv) v[u][t] = __ldg(src + f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int e = e0 + u;
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const int f = lane + 32 * t;
+                    if (e < K && f < cv) __stcs(dst + (size_t)e * cv + f, v[u][t]);
+                }
+            }
+        }
+    }
+}
+
 // generic gather of the rows of flagged queries (after the exact replay rewrote their idx)
 __global__ void k_regather_flagged(int K, int c, const float *__restrict__ feat, const int *__restrict__ idx,
                                    float *__restrict__ grouped, const CbGridHeader *hdr, const int *__restrict__ flagged)
@@ -345,23 +423,44 @@ static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const 
     if (per_sm < 1) per_sm = 1;
     int blocks = 148 * per_sm;
     if (blocks > (m + KG_WARPS - 1) / KG_WARPS) blocks = (m + KG_WARPS - 1) / KG_WARPS;
+    if (nsample <= 64 && g_kg_ws == 4 && c <= 512) {
+        int blocks_d = 148 * 4;
+        if (blocks_d > (m + 7) / 8) blocks_d = (m + 7) / 8;
+#define KGD_LAUNCH(KPL, T)                                                                                          \
+    k_knn_gather_direct<KPL, T><<<blocks_d, 256, 0, st>>>(m, nsample, c, new_xyz, feat, new_offset, b, self_query, v.scenes, \
+                                                          v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged)
+        const int T = (c / 4 + 31) / 32;
+        if (nsample <= 32) { if (T <= 1) KGD_LAUNCH(1, 1); else if (T == 2) KGD_LAUNCH(1, 2); else KGD_LAUNCH(1, 4); }
+        else { if (T <= 1) KGD_LAUNCH(2, 1); else if (T == 2) KGD_LAUNCH(2, 2); else KGD_LAUNCH(2, 4); }
+#undef KGD_LAUNCH
+        cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
+        k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
+        CB_COUNT(4);
+        CB_CUDA_CHECK("cb_knn_gather");
+        return CB_OK;
+    }
     if (nsample <= 64 && g_kg_ws) {
-        // warp-specialised kernel: chunk = R rows with R <= 32, R * row_bytes <= chunk bytes
-        const size_t smem_ws = (size_t)KGW_NS * slab;
-        int per = (int)((220 * 1024) / (smem_ws + 8192));
+        // warp-specialised kernel: ring of NS slabs, LA chunks in flight (mode 1: 8/4, mode 2: 12/8, mode 3: 6/4)
+        const int ns = g_kg_ws == 2 ? 12 : (g_kg_ws == 3 ? 6 : 8);
+        const size_t smem_ws = (size_t)ns * slab;
+        int per = (int)(233472 / (smem_ws + 6400 + 1024));     // 228 KB of shared memory per SM, 1 KB reserved per CTA
         if (per > 4) per = 4;
         if (per < 1) per = 1;
         int blocks_ws = 148 * per;
         if (blocks_ws > (m + KGW_SEARCH - 1) / KGW_SEARCH) blocks_ws = (m + KGW_SEARCH - 1) / KGW_SEARCH;
+#define KGW_LAUNCH(KPL, NS, LA)                                                                                      \
+    do {                                                                                                             \
+        cudaFuncSetAttribute(k_knn_gather_ws<KPL, NS, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); \
+        k_knn_gather_ws<KPL, NS, LA><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, \
+                                                                      self_query, v.scenes, v.cells, v.sorted, idx, dist2,  \
+                                                                      grouped, v.hdr, v.flagged);                          \
+    } while (0)
         if (nsample <= 32) {
-            cudaFuncSetAttribute(k_knn_gather_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
-            k_knn_gather_ws<1><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, self_query,
-                                                                v.scenes, v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged);
+            if (g_kg_ws == 2) KGW_LAUNCH(1, 12, 8); else if (g_kg_ws == 3) KGW_LAUNCH(1, 6, 4); else KGW_LAUNCH(1, 8, 4);
         } else {
-            cudaFuncSetAttribute(k_knn_gather_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
-            k_knn_gather_ws<2><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, self_query,
-                                                                v.scenes, v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged);
+            if (g_kg_ws == 2) KGW_LAUNCH(2, 12, 8); else if (g_kg_ws == 3) KGW_LAUNCH(2, 6, 4); else KGW_LAUNCH(2, 8, 4);
         }
+#undef KGW_LAUNCH
         cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
         k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
         CB_COUNT(4);
@@ -392,7 +491,7 @@ static bool kg_tma_ok(int c, int nsample, const float *feat, const float *groupe
     return (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 && (size_t)c * 4 <= 16384;
 }
 
-extern "C" int cb_knn_gather_set_mode(int warp_specialised) { g_kg_ws = warp_specialised ? 1 : 0; return g_kg_ws; }
+extern "C" int cb_knn_gather_set_mode(int mode) { g_kg_ws = (mode >= 0 && mode <= 4) ? mode : 1; return g_kg_ws; }
 
 extern "C" int cb_knn_gather_set_chunk_bytes(int bytes)
 {

@@ -82,7 +82,8 @@ int cb_knn_gather_grid(int m, int nsample, int c, const float *xyz, int n, const
                        float *grouped, void *grid, size_t grid_bytes, void *stream);
 float cb_knn_set_occupancy(float factor);       /* tuning knob: target points per occupied grid cell = factor * K (default 0.45) */
 int cb_knn_gather_set_chunk_bytes(int bytes);
-int cb_knn_gather_set_mode(int warp_specialised);   /* tuning knob: 1 (default) = search warps + TMA copy warp, 0 = one warp does both */   /* tuning knob: bytes per TMA chunk (default 2048); returns the value in use */
+int cb_knn_gather_set_mode(int mode);   /* tuning knob: 3 (default) = 7 search warps + 1 TMA copy warp per CTA (6-slab ring);
+                                           0 = every warp searches and copies (TMA); 1,2 = other ring depths; 4 = register copy */   /* tuning knob: bytes per TMA chunk (default 2048); returns the value in use */
 
 /* ------------------------------------------------------------------------------------------------
  * a2  farthest point sampling             replaces furthestsampling_cuda_launcher
