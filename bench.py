@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--no-pipeline", action="store_true", help="compute each batch's geometry inside its own step (no look-ahead)")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python (stream mode) instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -227,7 +228,6 @@ def run_ours(args):
     _lib.lib()   # fail loudly if libcbops.so is missing
 
     cfg = model.CBLConfig()
-    ts = engine.TrainStep(cfg, dev, ddp=ddp, seed=0)
     npool = 3
     host = [engine.host_batch_from_numpy(synthetic.make_batch(SCENES_PER_GPU, POINTS_PER_SCENE, 5000 + 97 * rank + i))
             for i in range(npool)]
@@ -254,51 +254,97 @@ def run_ours(args):
         return float(t.item())
 
     pipeline = not args.no_pipeline
+    nwarm = max(args.warmup, 3)
+    mode, graph_error, ts = "stream", None, None
+    if not args.no_graph:
+        # whole-step CUDA graphs (engine.GraphTrainStep): 2 eager steps, capture, then replays
+        ts = engine.GraphTrainStep(cfg, dev, ddp=ddp, seed=0)
+        for w in range(nwarm + 2):
+            ts.step(dev_batches[w % npool])
+        ok = torch.tensor([0 if ts.graph_error else 1], device=dev)
+        if ddp:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            mode = "graph"
+        else:
+            graph_error = ts.graph_error or "capture failed on another rank"
+            print("bench.py: CUDA-graph capture failed, falling back to stream mode: %s" % graph_error, file=sys.stderr)
+            ts = None
+            torch.cuda.empty_cache()
 
-    def step_resident(s):
-        # geometry of batch s+1 (FPS + all neighbour searches) runs on a side stream during step s
-        ts.step(dev_batches[s % npool], next_batch=dev_batches[(s + 1) % npool] if pipeline else None)
+    if mode == "graph":
+        def step_plain(s):
+            ts.step(dev_batches[s % npool])
 
-    def step_plain(s):
-        ts.step(dev_batches[s % npool])
+        def step_resident(s):
+            # geometry graph of batch s+1 replays on the side stream while the network graph of batch s replays
+            ts.step(dev_batches[s % npool], next_batch=dev_batches[(s + 1) % npool] if pipeline else None)
 
-    e2e_next = {}
+        def step_e2e(s):
+            # pinned HOST batches: each batch is copied host->device exactly once (into the graph's static slot)
+            loss = ts.step(host[s % npool], next_batch=host[(s + 1) % npool] if pipeline else None)
+            loss_host.copy_(loss, non_blocking=True)             # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
 
-    def step_e2e(s):
-        cur = e2e_next.pop("b", None)
-        if cur is None:
-            cur = engine.to_device(host[s % npool], dev)
-        nxt = None
+        t_plain = timed(step_plain, args.steps)                  # reference point: no look-ahead
+        for w in range(npool):
+            step_resident(w)                                     # primes the pipeline: slot holds batch 0's geometry
+        clocks = Clocks(local)
+        if rank == 0:
+            clocks.start()
+        t_val = timed(step_resident, args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        launches = int(ts.launches_per_step or 0)
+        for w in range(npool):
+            step_e2e(w)
+        t_e2e = timed(step_e2e, args.steps)
+    else:
+        ts = engine.TrainStep(cfg, dev, ddp=ddp, seed=0)
+
+        def step_resident(s):
+            # geometry of batch s+1 (FPS + all neighbour searches) runs on a side stream during step s
+            ts.step(dev_batches[s % npool], next_batch=dev_batches[(s + 1) % npool] if pipeline else None)
+
+        def step_plain(s):
+            ts.step(dev_batches[s % npool])
+
+        e2e_next = {}
+
+        def step_e2e(s):
+            cur = e2e_next.pop("b", None)
+            if cur is None:
+                cur = engine.to_device(host[s % npool], dev)
+            nxt = None
+            if pipeline:
+                nxt = engine.to_device(host[(s + 1) % npool], dev)   # H2D of ONE batch per step (the next one), from pinned memory
+                e2e_next["b"] = nxt
+            loss = ts.step(cur, next_batch=nxt)
+            loss_host.copy_(loss, non_blocking=True)             # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
+
+        for w in range(nwarm):
+            step_plain(w)
+        t_plain = timed(step_plain, args.steps)                  # reference point: no look-ahead
         if pipeline:
-            nxt = engine.to_device(host[(s + 1) % npool], dev)   # H2D of ONE batch per step (the next one), from pinned memory
-            e2e_next["b"] = nxt
-        loss = ts.step(cur, next_batch=nxt)
-        loss_host.copy_(loss, non_blocking=True)             # D2H of the step's result
-        torch.cuda.current_stream().synchronize()
-
-    for w in range(max(args.warmup, 3)):
-        step_plain(w)
-    t_plain = timed(step_plain, args.steps)                  # reference point: no look-ahead
-    if pipeline:
-        ts.prefetch_geometry(dev_batches[0])                 # prologue: batch 0's geometry (outside the timed region)
-        step_resident(0); step_resident(1); step_resident(2)
-        ts.prefetch_geometry(dev_batches[0]) if id(dev_batches[0]) not in ts._geo else None
-    lc0 = _lib.launch_count()
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
-    t_val = timed(step_resident, args.steps)
-    launches = (_lib.launch_count() - lc0) // max(args.steps, 1)
-    clk = clocks.stop() if rank == 0 else None
-    ts._geo.clear()
-    for w in range(2):
-        step_e2e(w)
-    e2e_next.clear(); ts._geo.clear()
-    if pipeline:
-        first = engine.to_device(host[0], dev)
-        e2e_next["b"] = first
-        ts.prefetch_geometry(first)
-    t_e2e = timed(step_e2e, args.steps)
+            ts.prefetch_geometry(dev_batches[0])                 # prologue: batch 0's geometry (outside the timed region)
+            step_resident(0); step_resident(1); step_resident(2)
+            ts.prefetch_geometry(dev_batches[0]) if id(dev_batches[0]) not in ts._geo else None
+        lc0 = _lib.launch_count()
+        clocks = Clocks(local)
+        if rank == 0:
+            clocks.start()
+        t_val = timed(step_resident, args.steps)
+        launches = (_lib.launch_count() - lc0) // max(args.steps, 1)
+        clk = clocks.stop() if rank == 0 else None
+        ts._geo.clear()
+        for w in range(2):
+            step_e2e(w)
+        e2e_next.clear(); ts._geo.clear()
+        if pipeline:
+            first = engine.to_device(host[0], dev)
+            e2e_next["b"] = first
+            ts.prefetch_geometry(first)
+        t_e2e = timed(step_e2e, args.steps)
     pts_per_step = world * SCENES_PER_GPU * POINTS_PER_SCENE
     line = {
         "metric": METRIC, "value": pts_per_step * args.steps / t_val, "unit": "points/s", "n_gpus": world,
@@ -308,6 +354,9 @@ def run_ours(args):
                                f"S3DIS-shape scenes per GPU, K=16 (stage 0: 8), C=32->512, CBL nsample [36,24,24,24,24]",
                    "global_batch_scenes": world * SCENES_PER_GPU, "parallelism": f"dp{world}",
                    "fused": bool(cfg.fused),
+                   "launch_mode": ("CUDA graphs: geometry graph + network(fwd+loss+bwd) graph per slot, 2 slots; optimizer"
+                                   + (" and ONE NCCL all-reduce of the packed gradient" if ddp else "") + " outside the graphs")
+                   if mode == "graph" else "stream mode (every kernel issued from Python)" + (", graph capture failed: " + graph_error if graph_error else ""),
                    "geometry_pipeline": ("look-ahead 1: FPS + neighbour searches of batch t+1 run on a side stream during step t "
                                          "(every batch's geometry is computed exactly once, inside the timed region)") if pipeline else "off",
                    "ms_per_step_without_lookahead": 1e3 * t_plain / args.steps,

@@ -87,10 +87,13 @@ class SizeT:
 
 
 _ws_cache = {}
+WS_NO_CACHE = False      # set while a CUDA graph is being captured: every capture owns its workspaces (graph pool memory)
 
 
 def workspace(nbytes, device, tag="default"):
     """Cached, 256-byte aligned byte workspace per (device, stream, tag); grows monotonically."""
+    if WS_NO_CACHE:
+        return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream().cuda_stream, tag)
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:

@@ -375,18 +375,25 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
         const float qx = new_xyz[3 * q], qy = new_xyz[3 * q + 1], qz = new_xyz[3 * q + 2];
         for (int k = t; k < K; k += CB_REPLAY_THREADS) { hd[k] = 1e10f; hi[k] = start; }
         __syncthreads();
-        for (int base = start; base < end; base += CB_REPLAY_BATCH) {
+        // Graded batches (256, 512, ... 4096 candidates): a batch is pre-filtered against the heap root at its start,
+        // which is 1e10 for the first one — keeping that one small keeps the serial pass of thread 0 short
+        // (expected survivors of a batch of s candidates after p scanned ones: s * K / p).
+        int pt = 1;
+        for (int base = start; base < end;) {
             const float root = hd[0];
-            const int i0 = base + t * CB_REPLAY_PER_THREAD;
+            const int i0 = base + t * pt;
             float d[CB_REPLAY_PER_THREAD];
             int npass = 0;
 #pragma unroll
             for (int u = 0; u < CB_REPLAY_PER_THREAD; u++) {
                 const int i = i0 + u;
                 d[u] = 3.0e38f;
-                if (i < end) d[u] = cb_sqdist_mode(dist_mode, qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+                if (u < pt && i < end)
+                    d[u] = cb_sqdist_mode(dist_mode, qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
                 npass += d[u] < root;
             }
+            base += CB_REPLAY_THREADS * pt;
+            if (pt < CB_REPLAY_PER_THREAD) pt <<= 1;
             // block exclusive scan of npass (thread order == index order)
             int inc = npass;
 #pragma unroll

@@ -93,3 +93,210 @@ def host_batch_from_numpy(b, pin=True):
         t = {k: v.pin_memory() for k, v in t.items()}
     t["offset_host"] = [int(x) for x in b["offset"]]
     return t
+
+
+# ------------------------------------------------------------------------------------------------------
+# Whole-step CUDA graphs.
+#
+# A training step of this network is ~1400 kernel launches, most of them a few microseconds long: issued
+# one by one from Python the HOST is the bottleneck (tools/host_bound.py).  Shapes are static for a given
+# tuple of scene sizes, and no kernel of libcbops needs a host decision (tie replays, boundary masks and
+# flagged-query lists are all device-side), so the step is captured ONCE per batch signature into two CUDA
+# graphs per slot and replayed:
+#     geo[s]  coordinates of slot s -> every level's sampling / neighbour search / relative positions
+#     net[s]  inputs + geometry of slot s -> forward, Loss, backward, gradients packed into one flat buffer
+# Two slots alternate: while net[s] trains on batch t (main stream), geo[1-s] builds the geometry of batch
+# t+1 (side stream) — the same look-ahead as TrainStep.prefetch_geometry, now without any launch overhead.
+# The optimiser (and, data-parallel, ONE NCCL all-reduce of the flat gradient) stays outside the graphs, so a
+# learning-rate schedule needs no re-capture.
+# ------------------------------------------------------------------------------------------------------
+class _Slot:
+    def __init__(self):
+        self.inputs = None      # static device tensors: points, features, point_labels, offset (+ offset_host list)
+        self.o_flat = None
+        self.levels = None
+        self.geo = self.net = None
+        self.loss = None
+        self.ev_geo = None
+        self.holds = None       # the batch (dict object) whose data / geometry the slot currently holds
+
+
+class GraphTrainStep(TrainStep):
+    """TrainStep whose step() replays captured CUDA graphs.  Same numerics (the captured work IS TrainStep's
+    work); falls back to TrainStep's stream mode for batch signatures it could not capture."""
+
+    def __init__(self, cfg: CBLConfig = None, device="cuda", ddp=False, eager_warmup=2, max_signatures=2, **kw):
+        # data parallel here = one all-reduce of the packed gradient after the graph; no DDP wrapper
+        super().__init__(cfg, device, ddp=False, **kw)
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if (ddp and dist.is_initialized()) else 1
+        if self.world > 1:                       # replicas must start from identical parameters (DDP does this itself)
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, 0)
+        self.eager_warmup = eager_warmup
+        self.max_signatures = max_signatures
+        self._sigs = {}            # signature -> [slot0, slot1] | None (capture failed)
+        self._eager_done = 0
+        self._net_pool = self._geo_pool = None
+        self.flat = None
+        self._gparams = None
+        self.launches_per_step = None
+        self.graph_error = None
+        self._packed = False       # True while every p.grad is a view of self.flat
+
+    # -- eager (stream-mode) step that also averages gradients across ranks -----------------------------
+    def _set_packed(self, flag):
+        if flag == self._packed:
+            return
+        for p in self.model.parameters():
+            p.grad = None
+        if flag:
+            o = 0
+            for p in self._gparams:
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+        self._packed = flag
+
+    def _eager_step(self, batch):
+        batch = to_device(batch, self.device)
+        self._set_packed(False)
+        self.opt.zero_grad(set_to_none=True)
+        self._geo.clear()
+        out, stages = self.model(batch, None)
+        loss = self.criterion(out, batch["point_labels"], stages)
+        loss.sum().backward()
+        if self.world > 1:
+            import torch.distributed as dist
+            gs = [p.grad for p in self.model.parameters() if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in gs])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            o = 0
+            for g in gs:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+        self.opt.step()
+        return loss.detach()
+
+    # -- capture ------------------------------------------------------------------------------------------
+    def _static_inputs(self, batch, sig):
+        n, b = sig[-1], len(sig)
+        dev = self.device
+        return {"points": torch.empty((n, 3), dtype=torch.float32, device=dev),
+                "features": torch.empty((n, batch["features"].shape[1]), dtype=torch.float32, device=dev),
+                "point_labels": torch.empty((n,), dtype=batch["point_labels"].dtype, device=dev),
+                "offset": torch.tensor(list(sig), dtype=torch.int32, device=dev),
+                "offset_host": list(sig)}
+
+    def _capture(self, batch, sig):
+        from . import _lib as L
+        from .model import level_offsets_host
+        dev = self.device
+        params = [p for p in self.model.parameters()] + [p for p in self.criterion.parameters()]
+        if self._gparams is None:
+            # parameters that receive a gradient (known from the eager warm-up steps); the rest keep grad None
+            self._gparams = [p for p in params if p.grad is not None]
+            self.flat = torch.zeros(sum(p.numel() for p in self._gparams), dtype=torch.float32, device=dev)
+        ohs = level_offsets_host(list(sig), self.cfg)
+        slots = [_Slot(), _Slot()]
+        for sl in slots:
+            sl.inputs = self._static_inputs(batch, sig)
+            for k in ("points", "features", "point_labels"):
+                sl.inputs[k].copy_(batch[k], non_blocking=True)       # valid data for the capture-time warm run
+            sl.o_flat = torch.tensor([v for oh_ in ohs[1:] for v in oh_], dtype=torch.int32, device=dev)
+            sl.ev_geo = torch.cuda.Event()
+        torch.cuda.synchronize(dev)
+        lc0 = L.launch_count()
+        L.WS_NO_CACHE = True
+        try:
+            for sl in slots:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._geo_pool):
+                    sl.levels = build_geometry(sl.inputs["points"], sl.inputs["offset"], sl.inputs["offset_host"], self.cfg,
+                                               self.cfg.contrast is not None, knn_stream=self.side2, o_flat=sl.o_flat)
+                sl.geo = g
+                if self._geo_pool is None:
+                    self._geo_pool = g.pool()
+            lc1 = L.launch_count()
+            for sl in slots:
+                sl.geo.replay()                                        # real geometry for the net capture's shapes
+            torch.cuda.synchronize(dev)
+            for sl in slots:
+                for p in params:
+                    p.grad = None
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._net_pool):
+                    out, stages = self.model(sl.inputs, sl.levels)
+                    loss = self.criterion(out, sl.inputs["point_labels"], stages)
+                    loss.sum().backward()
+                    torch.cat([p.grad.reshape(-1) for p in self._gparams], out=self.flat)
+                    sl.loss = loss.detach()
+                sl.net = g
+                if self._net_pool is None:
+                    self._net_pool = g.pool()
+            lc2 = L.launch_count()
+        finally:
+            L.WS_NO_CACHE = False
+        for p in params:
+            p.grad = None
+        self._packed = False
+        self.launches_per_step = (lc1 - lc0) // 2 + (lc2 - lc1) // 2
+        return slots
+
+    # -- replay -------------------------------------------------------------------------------------------
+    def _load(self, sl, batch):
+        # a geometry replay of this slot that was never consumed may still be reading the inputs
+        torch.cuda.current_stream(self.device).wait_event(sl.ev_geo)
+        for k in ("points", "features", "point_labels"):
+            sl.inputs[k].copy_(batch[k], non_blocking=True)            # H2D from pinned memory, or D2D
+        sl.holds = batch
+
+    def _launch_geo(self, sl):
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)                                    # inputs copied; previous reader of sl.levels done
+        with torch.cuda.stream(self.side):
+            sl.geo.replay()
+            sl.ev_geo.record(self.side)
+
+    def step(self, batch, update=True, next_batch=None):
+        """batch / next_batch: dicts of DEVICE or pinned-HOST tensors (+ offset_host).  Returns the loss vector."""
+        sig = tuple(int(v) for v in batch["offset_host"])
+        slots = self._sigs.get(sig, False)
+        if slots is False:
+            if self._eager_done < self.eager_warmup or not update:
+                self._eager_done += 1
+                return self._eager_step(batch)
+            slots = None
+            if len(self._sigs) < self.max_signatures:
+                try:
+                    slots = self._capture(batch, sig)
+                except Exception as e:                                  # keep training in stream mode
+                    self.graph_error = repr(e)
+                    try:
+                        torch.cuda.synchronize(self.device)
+                    except Exception:
+                        pass
+                    for p in self.model.parameters():
+                        p.grad = None
+                    self._packed = False
+            self._sigs[sig] = slots
+        if slots is None or not update:
+            return self._eager_step(batch)
+        self._set_packed(True)                                          # the optimiser reads the packed gradient
+        cur = next((s for s in slots if s.holds is batch), None)
+        if cur is None:
+            cur = slots[0]
+            self._load(cur, batch)
+            self._launch_geo(cur)
+        if next_batch is not None and tuple(int(v) for v in next_batch["offset_host"]) == sig:
+            other = slots[1] if cur is slots[0] else slots[0]
+            self._load(other, next_batch)
+            self._launch_geo(other)
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(cur.ev_geo)
+        cur.net.replay()
+        cur.holds = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        self.opt.step()
+        return cur.loss.clone()

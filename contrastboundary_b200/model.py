@@ -87,23 +87,31 @@ def _lens(o_host):
     return [o_host[0]] + [o_host[i] - o_host[i - 1] for i in range(1, len(o_host))]
 
 
-def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True, knn_stream=None):
+def level_offsets_host(o0_host, cfg: CBLConfig):
+    """host-known cumulative scene ends of every level (TransitionDown: per-scene floor(n_b / stride), blocks.py:64-67)"""
+    ohs = [list(o0_host)]
+    for l in range(1, len(cfg.planes)):
+        acc, cur = 0, []
+        for x in _lens(ohs[-1]):
+            acc += x // cfg.stride[l]
+            cur.append(acc)
+        ohs.append(cur)
+    return ohs
+
+
+def build_geometry(p0, o0, o0_host, cfg: CBLConfig, with_contrast=True, knn_stream=None, o_flat=None):
     """All sampling / neighbour searches of one forward.  p0 (n,3) f32, o0 (b) int32 cumulative ends,
-    o0_host = the same offsets as a python list (known from collate; avoids device->host syncs)."""
+    o0_host = the same offsets as a python list (known from collate; avoids device->host syncs).
+    o_flat: optional DEVICE int32 tensor holding the offsets of levels 1.. back to back (a caller that captures this
+    function in a CUDA graph uploads them once, outside the capture)."""
     levels = []
     nl = len(cfg.planes)
     # host-known scene sizes of every level (TransitionDown: per-scene floor(n_b / stride), blocks.py:64-67).
     # All small H2D uploads happen HERE, before the first kernel is enqueued: a pageable host->device copy is
     # synchronous with the host in stream order, so doing it between kernels would stall the launching thread
     # for the whole FPS chain and defeat the geometry/compute overlap.
-    ohs = [list(o0_host)]
-    for l in range(1, nl):
-        acc, cur = 0, []
-        for x in _lens(ohs[-1]):
-            acc += x // cfg.stride[l]
-            cur.append(acc)
-        ohs.append(cur)
-    flat = _upload_i32([v for oh_ in ohs[1:] for v in oh_], p0.device)
+    ohs = level_offsets_host(o0_host, cfg)
+    flat = o_flat if o_flat is not None else _upload_i32([v for oh_ in ohs[1:] for v in oh_], p0.device)
     b = len(o0_host)
     o_dev = [o0] + [flat[(l - 1) * b:l * b] for l in range(1, nl)]
     # --- sampling chain (serial across levels) on the current stream; neighbour searches optionally on `knn_stream`
