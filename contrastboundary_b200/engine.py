@@ -137,7 +137,7 @@ class GraphTrainStep(TrainStep):
         self.max_signatures = max_signatures
         self._sigs = {}            # signature -> [slot0, slot1] | None (capture failed)
         self._eager_done = 0
-        self._net_pool = self._geo_pool = None
+        self._net_pool = None      # net[0] / net[1] replay back to back on one stream: they may share temporaries
         self.flat = None
         self._gparams = None
         self.launches_per_step = None
@@ -177,6 +177,23 @@ class GraphTrainStep(TrainStep):
         self.opt.step()
         return loss.detach()
 
+    def stream_loss_and_grad(self, batch):
+        """test hook: stream-mode forward + backward on the CURRENT parameters, no update.
+        Returns (loss vector, packed gradient in the order of the graph's flat buffer)."""
+        batch = to_device(batch, self.device)
+        was = self._packed
+        self._set_packed(False)
+        self.opt.zero_grad(set_to_none=True)
+        out, stages = self.model(batch, None)
+        loss = self.criterion(out, batch["point_labels"], stages)
+        loss.sum().backward()
+        ps = self._gparams if self._gparams is not None else [p for p in self.model.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        for p in self.model.parameters():
+            p.grad = None
+        self._set_packed(was)
+        return loss.detach(), flat
+
     # -- capture ------------------------------------------------------------------------------------------
     def _static_inputs(self, batch, sig):
         n, b = sig[-1], len(sig)
@@ -209,13 +226,13 @@ class GraphTrainStep(TrainStep):
         L.WS_NO_CACHE = True
         try:
             for sl in slots:
+                # NO pool sharing between the two geometry graphs: geo[1-s] replays while net[s] still reads the
+                # outputs of geo[s]; in a shared pool the temporaries of one graph may alias the outputs of the other
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self._geo_pool):
+                with torch.cuda.graph(g):
                     sl.levels = build_geometry(sl.inputs["points"], sl.inputs["offset"], sl.inputs["offset_host"], self.cfg,
                                                self.cfg.contrast is not None, knn_stream=self.side2, o_flat=sl.o_flat)
                 sl.geo = g
-                if self._geo_pool is None:
-                    self._geo_pool = g.pool()
             lc1 = L.launch_count()
             for sl in slots:
                 sl.geo.replay()                                        # real geometry for the net capture's shapes

@@ -14,30 +14,28 @@ def _batches(n, sizes, seed0):
 
 
 def test_graph_step_matches_stream_step():
+    """On the SAME parameters, a replayed step must give the loss and the gradient of the stream-mode step.
+    (Two separately trained engines are not compared: the deepest level of these small scenes has 28 points, and
+    train-mode BatchNorm over 28 rows amplifies the run-to-run noise of float atomics within two SGD steps.)"""
     dev = torch.device("cuda", 0)
     host = _batches(3, [4096, 3072], 700)
     devb = [engine.to_device(h, dev) for h in host]
-    kw = dict(lr=0.01, momentum=0.9, weight_decay=1e-4, seed=3)
-    ref = engine.TrainStep(model.CBLConfig(), dev, **kw)
-    gts = engine.GraphTrainStep(model.CBLConfig(), dev, eager_warmup=2, **kw)
-    losses_ref, losses_g = [], []
+    gts = engine.GraphTrainStep(model.CBLConfig(), dev, eager_warmup=2, lr=0.01, momentum=0.9, weight_decay=1e-4, seed=3)
     for s in range(8):
-        losses_ref.append(ref.step(devb[s % 3]).cpu().numpy())
-        # steps 0-1 eager, step 2 captures; from step 4 on with look-ahead; step 6 feeds a pinned HOST batch
+        # steps 0-1 eager, step 2 captures; steps 4-5 with look-ahead; step 6 feeds a pinned HOST batch
         nxt = devb[(s + 1) % 3] if s in (4, 5) else None
         cur = host[s % 3] if s == 6 else devb[s % 3]
-        losses_g.append(gts.step(cur, next_batch=nxt).cpu().numpy())
+        l_ref, g_ref = gts.stream_loss_and_grad(devb[s % 3])
+        l = gts.step(cur, next_batch=nxt)
+        assert torch.isfinite(l).all(), (s, l)
+        np.testing.assert_allclose(l.cpu().numpy(), l_ref.cpu().numpy(), rtol=2e-4, atol=1e-6, err_msg=f"loss, step {s}")
+        if s >= 2:
+            g = gts.flat
+            rel = float((g - g_ref).norm() / g_ref.norm().clamp(min=1e-20))
+            assert rel < 2e-3, (s, rel)         # float atomics + ReLU-flip noise (DESIGN.md §3), far below a wrong gradient
     assert gts.graph_error is None, gts.graph_error
     assert gts.launches_per_step and gts.launches_per_step > 100
     assert all(sl.net is not None for sl in gts._sigs[tuple(host[0]["offset_host"])])
-    for s, (a, b) in enumerate(zip(losses_ref, losses_g)):
-        assert np.all(np.isfinite(b)), (s, b)
-        # float atomics make both engines run-to-run noisy at the 1e-6 level; 8 SGD steps amplify that a little
-        np.testing.assert_allclose(b, a, rtol=5e-3, atol=2e-4, err_msg=f"step {s}")
-    # parameters after 8 steps agree too
-    pa = torch.cat([p.detach().reshape(-1) for p in ref.model.parameters()])
-    pb = torch.cat([p.detach().reshape(-1) for p in gts.model.parameters()])
-    assert float((pa - pb).abs().max()) < 5e-3 * max(1.0, float(pa.abs().max()))
 
 
 def test_graph_step_other_signature_falls_back_or_captures():
