@@ -19,6 +19,8 @@
 namespace cg = cooperative_groups;
 
 #define FPS_THREADS 1024
+static int g_fps_mode = 0;
+static int g_fps_ws_min = 8192;
 
 struct FpsCand {
     unsigned d;   // distance bits (non-negative floats order like unsigned ints)
@@ -314,6 +316,228 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket(const float4 *__restrict
     for (int i = tid; i < ns; i += 1024) tmp[__float_as_int(__ldg(sorted + S0 + i).w)] = md[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster variant of the bucket-pruned FPS: one thread-block CLUSTER of CL CTAs per scene.
+//
+// The single-CTA kernel above spends most of an iteration waiting: every refreshed bucket is a 32-point load from
+// global memory (L2 latency), followed by a __syncthreads and a second reduction level.  Here each CTA owns a
+// contiguous 1/CL of the cell-sorted points and keeps BOTH their coordinates and their running min-distances in
+// its shared memory (20 B per point, <= 10752 points per CTA), so a refresh is LDS -> math -> STS.  The arg-max
+// is ONE all-to-all step: every warp of the cluster sends its candidate (distance bits, ~priority, x, y, z, index:
+// 24 B) straight into the slot arrays of all CL CTAs with st.async (distributed shared memory), whose completion is
+// counted by the receiver's mbarrier (complete_tx); each CTA then reduces the CL*32 slots redundantly.  No
+// __syncthreads, no cluster barrier and no global-memory access inside the iteration.
+// Tie rule: identical to the kernels above (priority = reference thread/stride order).
+// ---------------------------------------------------------------------------------------------
+#define FPSC_MAX_PER_CTA 10752
+
+__device__ __forceinline__ unsigned fps_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned fps_mapa(unsigned addr, unsigned rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restrict__ sorted, const float *__restrict__ xyz,
+                                                           const int *__restrict__ offset, const int *__restrict__ new_offset,
+                                                           float *__restrict__ tmp, int *__restrict__ idx, int logB, int cap)
+{
+    extern __shared__ __align__(16) unsigned char fps_sm[];
+    float4 *spt = reinterpret_cast<float4 *>(fps_sm);            // cap points (x, y, z, original index bits)
+    float *md = reinterpret_cast<float *>(spt + cap);            // cap running min distances
+    __shared__ __align__(16) uint4 slotA[2][CL * 32];            // (d bits, ~priority, x, y)
+    __shared__ __align__(8) uint2 slotB[2][CL * 32];             // (z, original index)
+    __shared__ __align__(8) unsigned long long bar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int bid = blockIdx.x / CL;
+    const int S0 = bid == 0 ? 0 : offset[bid - 1], S1 = offset[bid];
+    const int start_m = bid == 0 ? 0 : new_offset[bid - 1], end_m = new_offset[bid];
+    const int ns = S1 - S0;
+    const int Bref = 1 << logB;
+    const unsigned S = (unsigned)((ns + Bref - 1) >> logB);
+    const int base = (int)rank * cap;                            // my chunk of the sorted order: [base, base + cnt)
+    const int cnt = max(0, min(cap, ns - base));
+    const int nbl = (cnt + 31) >> 5;                             // my buckets (<= 336 -> at most 11 per warp, 1 per lane)
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&bar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // stage my points
+    for (int i = tid; i < cnt; i += 1024) {
+        const float4 p = __ldg(sorted + S0 + base + i);
+        spt[i] = p;
+        md[i] = tmp[__float_as_int(p.w)];
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    float lox = 3.0e38f, loy = 3.0e38f, loz = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f, hiz = -3.0e38f;
+    unsigned bd = 0u, bp = 0u;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    int bo = S0;
+    auto priority = [&](int orig) -> unsigned {
+        const unsigned r = (unsigned)(orig - S0);
+        const unsigned tt = r & (unsigned)(Bref - 1);
+        const unsigned brev = logB ? (__brev(tt) >> (32 - logB)) : 0u;
+        return ~(brev * S + (r >> logB));
+    };
+    auto refresh = [&](int bl, int owner, float sx, float sy, float sz, bool init) {
+        const int i = (bl << 5) + lane;
+        const bool valid = i < cnt;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) p = spt[i];
+        const int orig = __float_as_int(p.w);
+        float m = 0.f;
+        if (valid) {
+            m = md[i];
+            if (!init) {
+                m = fminf(cb_sqdist(p.x, p.y, p.z, sx, sy, sz), m);
+                md[i] = m;
+            }
+        }
+        const unsigned db = valid ? __float_as_uint(fmaxf(m, 0.f)) : 0u;
+        const unsigned np = valid ? priority(orig) : 0u;
+        const unsigned wd = __reduce_max_sync(CB_FULL_MASK, db);
+        const unsigned wp = __reduce_max_sync(CB_FULL_MASK, db == wd ? np : 0u);
+        const int src = __ffs(__ballot_sync(CB_FULL_MASK, db == wd && np == wp)) - 1;
+        const float cx = __shfl_sync(CB_FULL_MASK, p.x, src), cy = __shfl_sync(CB_FULL_MASK, p.y, src),
+                    cz = __shfl_sync(CB_FULL_MASK, p.z, src);
+        const int co = __shfl_sync(CB_FULL_MASK, orig, src);
+        float mnx = 0, mny = 0, mnz = 0, mxx = 0, mxy = 0, mxz = 0;
+        if (init) {
+            const unsigned big = 0xffffffffu;
+            mnx = cb_ord2f(__reduce_min_sync(CB_FULL_MASK, valid ? cb_f2ord(p.x) : big));
+            mny = cb_ord2f(__reduce_min_sync(CB_FULL_MASK, valid ? cb_f2ord(p.y) : big));
+            mnz = cb_ord2f(__reduce_min_sync(CB_FULL_MASK, valid ? cb_f2ord(p.z) : big));
+            mxx = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.x) : 0u));
+            mxy = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.y) : 0u));
+            mxz = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.z) : 0u));
+        }
+        if (lane == owner) {
+            bd = wd; bp = wp; bx = cx; by = cy; bz = cz; bo = co;
+            if (init) { lox = mnx; loy = mny; loz = mnz; hix = mxx; hiy = mxy; hiz = mxz; }
+        }
+    };
+    // local bucket bl = warp + 32 * owner is owned by lane `owner` of warp `warp`
+#pragma unroll 1
+    for (int owner = 0; owner < 32; owner++) {
+        const int bl = warp + 32 * owner;
+        if (bl < nbl) refresh(bl, owner, 0.f, 0.f, 0.f, true);
+    }
+    int old = S0;
+    float sx = __ldg(xyz + 3 * old), sy = __ldg(xyz + 3 * old + 1), sz = __ldg(xyz + 3 * old + 2);
+    if (rank == 0 && tid == 0 && end_m > start_m) idx[start_m] = old;      // sampling_cuda_kernel.cu:39
+    // remote addresses of my warp's slot and of the barriers in CTA `lane` (lanes < CL send)
+    const unsigned my_slot = rank * 32u + (unsigned)warp;
+    unsigned rA = 0, rB = 0, rbar = 0;
+    if (lane < CL) {
+        rA = fps_mapa(fps_smem_u32(&slotA[0][my_slot]), (unsigned)lane);
+        rB = fps_mapa(fps_smem_u32(&slotB[0][my_slot]), (unsigned)lane);
+        rbar = fps_mapa(fps_smem_u32(&bar[0]), (unsigned)lane);
+    }
+    const unsigned bar_local = fps_smem_u32(&bar[0]);
+    const int iters = (ns > 0 && end_m > start_m) ? end_m - start_m - 1 : 0;     // uniform across the cluster
+    for (int it = 0; it < iters; it++) {
+        const int par = it & 1;
+        // 1. can my bucket change?  (box distance, with a 1e-4 safety margin for fp32 rounding)
+        {
+            const float dx = fmaxf(fmaxf(lox - sx, sx - hix), 0.f), dy = fmaxf(fmaxf(loy - sy, sy - hiy), 0.f),
+                        dz = fmaxf(fmaxf(loz - sz, sz - hiz), 0.f);
+            const float lb = (dx * dx + dy * dy + dz * dz) * 0.9999f;
+            unsigned touched = __ballot_sync(CB_FULL_MASK, bd != 0u && lb < __uint_as_float(bd));
+            while (touched) {
+                const int owner = __ffs(touched) - 1;
+                touched &= touched - 1;
+                refresh(warp + 32 * owner, owner, sx, sy, sz, false);
+            }
+        }
+        // 2. warp arg-max over the buckets its lanes own
+        {
+            const unsigned wd = __reduce_max_sync(CB_FULL_MASK, bd);
+            const unsigned wp = __reduce_max_sync(CB_FULL_MASK, bd == wd ? bp : 0u);
+            const int src = __ffs(__ballot_sync(CB_FULL_MASK, bd == wd && bp == wp)) - 1;
+            const unsigned cx = __float_as_uint(__shfl_sync(CB_FULL_MASK, bx, src)), cy = __float_as_uint(__shfl_sync(CB_FULL_MASK, by, src)),
+                           cz = __float_as_uint(__shfl_sync(CB_FULL_MASK, bz, src));
+            const unsigned co = (unsigned)__shfl_sync(CB_FULL_MASK, bo, src);
+            // 3. all-to-all: lane r sends this warp's candidate to CTA r
+            if (lane < CL) {
+                const unsigned a = rA + (unsigned)par * (unsigned)sizeof(slotA[0]);
+                const unsigned b2 = rB + (unsigned)par * (unsigned)sizeof(slotB[0]);
+                const unsigned mb = rbar + (unsigned)par * 8u;
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                             ::"r"(a), "r"(wd), "r"(wp), "r"(cx), "r"(cy), "r"(mb) : "memory");
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                             ::"r"(b2), "r"(cz), "r"(co), "r"(mb) : "memory");
+            }
+        }
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local + (unsigned)par * 8u),
+                         "r"((unsigned)(CL * 32 * 24)) : "memory");
+        // 4. wait for the CL*32 candidates of this iteration
+        {
+            const unsigned mb = bar_local + (unsigned)par * 8u, parity = (unsigned)(it >> 1) & 1u;
+            unsigned ok;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+            } while (!ok);
+        }
+        // 5. cluster arg-max (every warp of every CTA redundantly, on its own copy of the slots)
+        {
+            uint4 best = slotA[par][lane];
+            int bc = 0;
+#pragma unroll
+            for (int c = 1; c < CL; c++) {
+                const uint4 t = slotA[par][c * 32 + lane];
+                if (t.x > best.x || (t.x == best.x && t.y > best.y)) { best = t; bc = c; }
+            }
+            const unsigned wd = __reduce_max_sync(CB_FULL_MASK, best.x);
+            const unsigned wp = __reduce_max_sync(CB_FULL_MASK, best.x == wd ? best.y : 0u);
+            const int src = __ffs(__ballot_sync(CB_FULL_MASK, best.x == wd && best.y == wp)) - 1;
+            const int sidx = __shfl_sync(CB_FULL_MASK, bc * 32 + lane, src);
+            const uint2 zb = slotB[par][sidx];
+            sx = __uint_as_float(__shfl_sync(CB_FULL_MASK, best.z, src));
+            sy = __uint_as_float(__shfl_sync(CB_FULL_MASK, best.w, src));
+            sz = __uint_as_float(zb.x);
+            old = (int)zb.y;
+        }
+        if (rank == 0 && tid == 0) idx[start_m + 1 + it] = old;
+    }
+    // leave the running min-distance where the reference leaves it
+    __syncthreads();
+    for (int i = tid; i < cnt; i += 1024) tmp[__float_as_int(spt[i].w)] = md[i];
+    // no CTA may exit while a peer could still write into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CL>
+static cudaError_t launch_fps_bucket_cl(int b, int cap, const float4 *sorted, const float *xyz, const int *offset,
+                                        const int *new_offset, float *tmp, int *idx, int logB, cudaStream_t st)
+{
+    const size_t smem = (size_t)cap * 20;
+    cudaError_t e = cudaFuncSetAttribute(k_fps_bucket_cl<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * CL));
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_fps_bucket_cl<CL>, sorted, xyz, offset, new_offset, tmp, idx, logB, cap);
+}
+
 template <int CL, int PPT>
 static cudaError_t launch_fps(int b, const float *xyz, const int *offset, const int *new_offset, float *tmp, int *idx,
                               int logB, cudaStream_t st)
@@ -371,7 +595,7 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
                                        const int *new_offset, float *tmp, int *idx, void *workspace,
                                        size_t workspace_bytes, void *stream)
 {
-    if (!workspace || n_max <= 8192 || n_max > FPSB_MAX_POINTS)
+    if (!workspace || n_max <= g_fps_ws_min || n_max > (g_fps_mode == 1 ? FPSB_MAX_POINTS : 8 * FPSC_MAX_PER_CTA))
         return cb_furthest_sampling(b, n_max, xyz, offset, new_offset, tmp, idx, stream);
     CB_REQUIRE(b > 0 && n >= 0 && xyz && offset && new_offset && tmp && idx, CB_EINVAL, "cb_furthest_sampling_ws: bad arguments");
     CbGridView v;
@@ -384,12 +608,42 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
     int pow_2 = (int)(log((double)n_max) / log(2.0));
     if (pow_2 > 10) pow_2 = 10;
     if (pow_2 < 0) pow_2 = 0;
+    if (g_fps_mode != 1) {
+        // cluster variant: the smallest cluster whose CTAs hold their share of the largest scene in shared memory
+        int cl = 2;
+        while (cl < 8 && (n_max + cl - 1) / cl > FPSC_MAX_PER_CTA) cl <<= 1;
+        if (cl < 4 && g_fps_mode == 0) cl = 4;                 // more CTAs = fewer buckets per warp; 4 is the sweet spot
+        const int cap = (((n_max + cl - 1) / cl) + 31) / 32 * 32;
+        if (cap <= FPSC_MAX_PER_CTA) {
+            cudaError_t e = cl == 2 ? launch_fps_bucket_cl<2>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st)
+                          : cl == 4 ? launch_fps_bucket_cl<4>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st)
+                                    : launch_fps_bucket_cl<8>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st);
+            if (e != cudaSuccess) {
+                cb_set_error("cb_furthest_sampling_ws: %s", cudaGetErrorString(e));
+                (void)cudaGetLastError();
+                return CB_ECUDA;
+            }
+            CB_COUNT(1);
+            CB_CUDA_CHECK("cb_furthest_sampling_ws");
+            return CB_OK;
+        }
+    }
+    CB_REQUIRE(n_max <= FPSB_MAX_POINTS, CB_EUNSUPPORTED, "cb_furthest_sampling_ws: n_max=%d", n_max);
     const size_t smem = (size_t)n_max * sizeof(float);
     cudaFuncSetAttribute(k_fps_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_fps_bucket<<<b, 1024, smem, st>>>(v.sorted, xyz, offset, new_offset, tmp, idx, pow_2);
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_furthest_sampling_ws");
     return CB_OK;
+}
+
+// developer knobs: mode 0 = cluster bucket kernel (default), 1 = single-CTA bucket kernel, 2 = cluster kernel with the
+// smallest cluster that fits; ws_min = scenes up to this size use the register-resident kernels
+extern "C" int cb_fps_set_mode(int mode, int ws_min)
+{
+    if (mode >= 0 && mode <= 2) g_fps_mode = mode;
+    if (ws_min >= 1024) g_fps_ws_min = ws_min;
+    return g_fps_mode;
 }
 
 extern "C" int cb_debug_fps(int enable, unsigned long long *out8)

@@ -96,10 +96,14 @@ int cb_knn_gather_set_mode(int mode);   /* tuning knob: 3 (default) = 7 search w
 int cb_furthest_sampling(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
                          float *tmp, int *idx, void *stream);
 /* same results; with a workspace (>= cb_knn_workspace_bytes(n, 0, b), 256-byte aligned) scenes of
- * 8192 < n_max <= 49152 points use the bucket-pruned kernel (grid-sorted supports, min-distances in
- * shared memory, O(n/j) work in iteration j instead of O(n)). */
+ * 8192 < n_max <= 86016 points use the bucket-pruned kernels (grid-sorted supports, O(n/j) work in iteration j
+ * instead of O(n)): a thread-block cluster per scene with points and min-distances resident in the cluster's
+ * shared memory and a distributed-shared-memory all-to-all arg-max (default), or the single-CTA variant. */
 int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n, const int *offset, const int *new_offset,
                             float *tmp, int *idx, void *workspace, size_t workspace_bytes, void *stream);
+/* developer knob: mode 0 cluster bucket kernel (default) | 1 single-CTA bucket kernel | 2 smallest cluster that fits;
+ * ws_min: scenes up to this many points use the register-resident kernels.  Returns the mode in force. */
+int cb_fps_set_mode(int mode, int ws_min);
 
 /* ------------------------------------------------------------------------------------------------
  * a3  grouping                            replaces grouping_{forward,backward}_cuda_launcher

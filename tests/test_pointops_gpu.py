@@ -152,9 +152,18 @@ def test_fps_stage_sizes(lens):
     xyz = np.concatenate(pts, 0)
     off = cases.cumsum_i32(lens)
     noff = cases.fps_new_offset(off, 4 if max(lens) <= 40960 else 64)
-    idx = pointops.furthestsampling(t(xyz), t(off), t(noff)).cpu().numpy()
     oi = oracle.furthestsampling(xyz, off, noff)
-    assert np.array_equal(idx, oi)
+    from contrastboundary_b200 import _lib as L
+    try:
+        # 0 = cluster bucket kernel (distributed shared memory), 1 = single-CTA bucket kernel, 2 = smallest cluster that fits
+        for mode in (0, 1, 2):
+            L.lib().cb_fps_set_mode(mode, 8192)
+            if mode == 1 and max(lens) > 49152:
+                continue
+            idx = pointops.furthestsampling(t(xyz), t(off), t(noff)).cpu().numpy()
+            assert np.array_equal(idx, oi), f"mode {mode}: first mismatch at {np.flatnonzero(idx != oi)[:5]}"
+    finally:
+        L.lib().cb_fps_set_mode(0, 8192)
 
 
 def test_gather_ops_forward_backward(golden):
