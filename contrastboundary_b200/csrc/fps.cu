@@ -319,15 +319,16 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket(const float4 *__restrict
 // ---------------------------------------------------------------------------------------------
 // Cluster variant of the bucket-pruned FPS: one thread-block CLUSTER of CL CTAs per scene.
 //
-// The single-CTA kernel above spends most of an iteration waiting: every refreshed bucket is a 32-point load from
-// global memory (L2 latency), followed by a __syncthreads and a second reduction level.  Here each CTA owns a
-// contiguous 1/CL of the cell-sorted points and keeps BOTH their coordinates and their running min-distances in
-// its shared memory (20 B per point, <= 10752 points per CTA), so a refresh is LDS -> math -> STS.  The arg-max
-// is ONE all-to-all step: every warp of the cluster sends its candidate (distance bits, ~priority, x, y, z, index:
-// 24 B) straight into the slot arrays of all CL CTAs with st.async (distributed shared memory), whose completion is
-// counted by the receiver's mbarrier (complete_tx); each CTA then reduces the CL*32 slots redundantly.  No
-// __syncthreads, no cluster barrier and no global-memory access inside the iteration.
-// Tie rule: identical to the kernels above (priority = reference thread/stride order).
+// The single-CTA kernel above runs 32 warps that all execute the same serial chain (box tests -> refresh ->
+// warp arg-max -> __syncthreads -> CTA arg-max) — eight warps per scheduler compete for issue slots, every
+// refreshed bucket is a 32-point load from global memory (L2 latency), and the arg-max has two levels.
+// Here each CTA owns a contiguous 1/CL of the cell-sorted points and keeps BOTH their coordinates and their
+// running min-distances in its shared memory (20 B per point), runs only W = 4 (or 8) warps — one or two per
+// scheduler, a lane owns up to S buckets — and the arg-max is ONE all-to-all step: every warp of the cluster sends
+// its candidate (distance bits, ~priority, x, y, z, index: 24 B) straight into the slot arrays of all CL CTAs with
+// st.async (distributed shared memory), whose arrival is counted by the receiver's mbarrier (complete_tx); each
+// warp then reduces the CL*W slots redundantly.  No __syncthreads, no cluster barrier and no global-memory access
+// inside the iteration.  Tie rule: identical to the kernels above (priority = reference thread/stride order).
 // ---------------------------------------------------------------------------------------------
 #define FPSC_MAX_PER_CTA 10752
 
@@ -339,16 +340,18 @@ __device__ __forceinline__ unsigned fps_mapa(unsigned addr, unsigned rank)
     return r;
 }
 
-template <int CL>
-__global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restrict__ sorted, const float *__restrict__ xyz,
-                                                           const int *__restrict__ offset, const int *__restrict__ new_offset,
-                                                           float *__restrict__ tmp, int *__restrict__ idx, int logB, int cap)
+template <int CL, int W, int S>
+__global__ void __launch_bounds__(W * 32, 1) k_fps_bucket_cl(const float4 *__restrict__ sorted, const float *__restrict__ xyz,
+                                                             const int *__restrict__ offset, const int *__restrict__ new_offset,
+                                                             float *__restrict__ tmp, int *__restrict__ idx, int logB, int cap)
 {
+    constexpr int NT = W * 32, NSLOT = CL * W;
+    static_assert(NSLOT <= 64, "slot reduction handles at most 64 warps per cluster");
     extern __shared__ __align__(16) unsigned char fps_sm[];
     float4 *spt = reinterpret_cast<float4 *>(fps_sm);            // cap points (x, y, z, original index bits)
     float *md = reinterpret_cast<float *>(spt + cap);            // cap running min distances
-    __shared__ __align__(16) uint4 slotA[2][CL * 32];            // (d bits, ~priority, x, y)
-    __shared__ __align__(8) uint2 slotB[2][CL * 32];             // (z, original index)
+    __shared__ __align__(16) uint4 slotA[2][NSLOT];              // (d bits, ~priority, x, y)
+    __shared__ __align__(8) uint2 slotB[2][NSLOT];               // (z, original index)
     __shared__ __align__(8) unsigned long long bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned rank;
@@ -358,18 +361,17 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
     const int start_m = bid == 0 ? 0 : new_offset[bid - 1], end_m = new_offset[bid];
     const int ns = S1 - S0;
     const int Bref = 1 << logB;
-    const unsigned S = (unsigned)((ns + Bref - 1) >> logB);
+    const unsigned SS = (unsigned)((ns + Bref - 1) >> logB);
     const int base = (int)rank * cap;                            // my chunk of the sorted order: [base, base + cnt)
     const int cnt = max(0, min(cap, ns - base));
-    const int nbl = (cnt + 31) >> 5;                             // my buckets (<= 336 -> at most 11 per warp, 1 per lane)
+    const int nbl = (cnt + 31) >> 5;                             // my buckets (<= W * 32 * S)
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&bar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&bar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // stage my points
-    for (int i = tid; i < cnt; i += 1024) {
+    for (int i = tid; i < cnt; i += NT) {                        // stage my points
         const float4 p = __ldg(sorted + S0 + base + i);
         spt[i] = p;
         md[i] = tmp[__float_as_int(p.w)];
@@ -377,17 +379,23 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-    float lox = 3.0e38f, loy = 3.0e38f, loz = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f, hiz = -3.0e38f;
-    unsigned bd = 0u, bp = 0u;
-    float bx = 0.f, by = 0.f, bz = 0.f;
-    int bo = S0;
+    float lox[S], loy[S], loz[S], hix[S], hiy[S], hiz[S];
+    unsigned bd[S], bp[S];
+    float bx[S], by[S], bz[S];
+    int bo[S];
+#pragma unroll
+    for (int t = 0; t < S; t++) {
+        lox[t] = loy[t] = loz[t] = 3.0e38f; hix[t] = hiy[t] = hiz[t] = -3.0e38f;
+        bd[t] = 0u; bp[t] = 0u; bx[t] = by[t] = bz[t] = 0.f; bo[t] = S0;
+    }
     auto priority = [&](int orig) -> unsigned {
         const unsigned r = (unsigned)(orig - S0);
         const unsigned tt = r & (unsigned)(Bref - 1);
         const unsigned brev = logB ? (__brev(tt) >> (32 - logB)) : 0u;
-        return ~(brev * S + (r >> logB));
+        return ~(brev * SS + (r >> logB));
     };
-    auto refresh = [&](int bl, int owner, float sx, float sy, float sz, bool init) {
+    // refresh local bucket bl (owned by slot t of lane `owner`) against sample (sx,sy,sz); init: build the box instead
+    auto refresh = [&](int bl, int owner, int t, float sx, float sy, float sz, bool init) {
         const int i = (bl << 5) + lane;
         const bool valid = i < cnt;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -420,21 +428,27 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
             mxz = cb_ord2f(__reduce_max_sync(CB_FULL_MASK, valid ? cb_f2ord(p.z) : 0u));
         }
         if (lane == owner) {
-            bd = wd; bp = wp; bx = cx; by = cy; bz = cz; bo = co;
-            if (init) { lox = mnx; loy = mny; loz = mnz; hix = mxx; hiy = mxy; hiz = mxz; }
+#pragma unroll
+            for (int tt = 0; tt < S; tt++)
+                if (tt == t) {
+                    bd[tt] = wd; bp[tt] = wp; bx[tt] = cx; by[tt] = cy; bz[tt] = cz; bo[tt] = co;
+                    if (init) { lox[tt] = mnx; loy[tt] = mny; loz[tt] = mnz; hix[tt] = mxx; hiy[tt] = mxy; hiz[tt] = mxz; }
+                }
         }
     };
-    // local bucket bl = warp + 32 * owner is owned by lane `owner` of warp `warp`
+    // local bucket bl = warp + W * (owner + 32 * t) is owned by slot t of lane `owner` of warp `warp`
 #pragma unroll 1
-    for (int owner = 0; owner < 32; owner++) {
-        const int bl = warp + 32 * owner;
-        if (bl < nbl) refresh(bl, owner, 0.f, 0.f, 0.f, true);
-    }
+    for (int t = 0; t < S; t++)
+#pragma unroll 1
+        for (int owner = 0; owner < 32; owner++) {
+            const int bl = warp + W * (owner + 32 * t);
+            if (bl < nbl) refresh(bl, owner, t, 0.f, 0.f, 0.f, true);
+        }
     int old = S0;
     float sx = __ldg(xyz + 3 * old), sy = __ldg(xyz + 3 * old + 1), sz = __ldg(xyz + 3 * old + 2);
     if (rank == 0 && tid == 0 && end_m > start_m) idx[start_m] = old;      // sampling_cuda_kernel.cu:39
     // remote addresses of my warp's slot and of the barriers in CTA `lane` (lanes < CL send)
-    const unsigned my_slot = rank * 32u + (unsigned)warp;
+    const unsigned my_slot = rank * (unsigned)W + (unsigned)warp;
     unsigned rA = 0, rB = 0, rbar = 0;
     if (lane < CL) {
         rA = fps_mapa(fps_smem_u32(&slotA[0][my_slot]), (unsigned)lane);
@@ -443,28 +457,44 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
     }
     const unsigned bar_local = fps_smem_u32(&bar[0]);
     const int iters = (ns > 0 && end_m > start_m) ? end_m - start_m - 1 : 0;     // uniform across the cluster
+    const int dbg = g_fps_dbg_on;
+    long long t_start = 0, t_refresh = 0, t_xchg = 0;
+    unsigned long long n_touched = 0;
+    unsigned max_touched = 0;
+    if (dbg) t_start = clock64();
     for (int it = 0; it < iters; it++) {
         const int par = it & 1;
-        // 1. can my bucket change?  (box distance, with a 1e-4 safety margin for fp32 rounding)
-        {
-            const float dx = fmaxf(fmaxf(lox - sx, sx - hix), 0.f), dy = fmaxf(fmaxf(loy - sy, sy - hiy), 0.f),
-                        dz = fmaxf(fmaxf(loz - sz, sz - hiz), 0.f);
+        // 1. which of my buckets can change?  (box distance, with a 1e-4 safety margin for fp32 rounding)
+        const long long c0 = dbg ? clock64() : 0;
+#pragma unroll
+        for (int t = 0; t < S; t++) {
+            const float dx = fmaxf(fmaxf(lox[t] - sx, sx - hix[t]), 0.f), dy = fmaxf(fmaxf(loy[t] - sy, sy - hiy[t]), 0.f),
+                        dz = fmaxf(fmaxf(loz[t] - sz, sz - hiz[t]), 0.f);
             const float lb = (dx * dx + dy * dy + dz * dz) * 0.9999f;
-            unsigned touched = __ballot_sync(CB_FULL_MASK, bd != 0u && lb < __uint_as_float(bd));
+            unsigned touched = __ballot_sync(CB_FULL_MASK, bd[t] != 0u && lb < __uint_as_float(bd[t]));
+            if (dbg) { n_touched += __popc(touched); max_touched = max(max_touched, (unsigned)__popc(touched)); }
             while (touched) {
                 const int owner = __ffs(touched) - 1;
                 touched &= touched - 1;
-                refresh(warp + 32 * owner, owner, sx, sy, sz, false);
+                refresh(warp + W * (owner + 32 * t), owner, t, sx, sy, sz, false);
             }
         }
+        if (dbg) t_refresh += clock64() - c0;
+        const long long c1 = dbg ? clock64() : 0;
         // 2. warp arg-max over the buckets its lanes own
         {
-            const unsigned wd = __reduce_max_sync(CB_FULL_MASK, bd);
-            const unsigned wp = __reduce_max_sync(CB_FULL_MASK, bd == wd ? bp : 0u);
-            const int src = __ffs(__ballot_sync(CB_FULL_MASK, bd == wd && bp == wp)) - 1;
-            const unsigned cx = __float_as_uint(__shfl_sync(CB_FULL_MASK, bx, src)), cy = __float_as_uint(__shfl_sync(CB_FULL_MASK, by, src)),
-                           cz = __float_as_uint(__shfl_sync(CB_FULL_MASK, bz, src));
-            const unsigned co = (unsigned)__shfl_sync(CB_FULL_MASK, bo, src);
+            unsigned md_ = bd[0], mp_ = bp[0];
+            float mx = bx[0], my = by[0], mz = bz[0];
+            int mo = bo[0];
+#pragma unroll
+            for (int t = 1; t < S; t++)
+                if (bd[t] > md_ || (bd[t] == md_ && bp[t] > mp_)) { md_ = bd[t]; mp_ = bp[t]; mx = bx[t]; my = by[t]; mz = bz[t]; mo = bo[t]; }
+            const unsigned wd = __reduce_max_sync(CB_FULL_MASK, md_);
+            const unsigned wp = __reduce_max_sync(CB_FULL_MASK, md_ == wd ? mp_ : 0u);
+            const int src = __ffs(__ballot_sync(CB_FULL_MASK, md_ == wd && mp_ == wp)) - 1;
+            const unsigned cx = __float_as_uint(__shfl_sync(CB_FULL_MASK, mx, src)), cy = __float_as_uint(__shfl_sync(CB_FULL_MASK, my, src)),
+                           cz = __float_as_uint(__shfl_sync(CB_FULL_MASK, mz, src));
+            const unsigned co = (unsigned)__shfl_sync(CB_FULL_MASK, mo, src);
             // 3. all-to-all: lane r sends this warp's candidate to CTA r
             if (lane < CL) {
                 const unsigned a = rA + (unsigned)par * (unsigned)sizeof(slotA[0]);
@@ -478,8 +508,8 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
         }
         if (tid == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local + (unsigned)par * 8u),
-                         "r"((unsigned)(CL * 32 * 24)) : "memory");
-        // 4. wait for the CL*32 candidates of this iteration
+                         "r"((unsigned)(NSLOT * 24)) : "memory");
+        // 4. wait for the CL*W candidates of this iteration
         {
             const unsigned mb = bar_local + (unsigned)par * 8u, parity = (unsigned)(it >> 1) & 1u;
             unsigned ok;
@@ -488,20 +518,21 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
                              : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
             } while (!ok);
         }
+        if (dbg) t_xchg += clock64() - c1;
         // 5. cluster arg-max (every warp of every CTA redundantly, on its own copy of the slots)
         {
-            uint4 best = slotA[par][lane];
-            int bc = 0;
-#pragma unroll
-            for (int c = 1; c < CL; c++) {
-                const uint4 t = slotA[par][c * 32 + lane];
-                if (t.x > best.x || (t.x == best.x && t.y > best.y)) { best = t; bc = c; }
+            uint4 best = make_uint4(0u, 0u, 0u, 0u);
+            int bs = lane;
+            if (lane < NSLOT) best = slotA[par][lane];
+            if (NSLOT > 32 && lane + 32 < NSLOT) {
+                const uint4 t = slotA[par][lane + 32];
+                if (t.x > best.x || (t.x == best.x && t.y > best.y)) { best = t; bs = lane + 32; }
             }
             const unsigned wd = __reduce_max_sync(CB_FULL_MASK, best.x);
             const unsigned wp = __reduce_max_sync(CB_FULL_MASK, best.x == wd ? best.y : 0u);
             const int src = __ffs(__ballot_sync(CB_FULL_MASK, best.x == wd && best.y == wp)) - 1;
-            const int sidx = __shfl_sync(CB_FULL_MASK, bc * 32 + lane, src);
-            const uint2 zb = slotB[par][sidx];
+            const int sidx = __shfl_sync(CB_FULL_MASK, bs, src);
+            const uint2 zb = slotB[par][sidx < NSLOT ? sidx : 0];
             sx = __uint_as_float(__shfl_sync(CB_FULL_MASK, best.z, src));
             sy = __uint_as_float(__shfl_sync(CB_FULL_MASK, best.w, src));
             sz = __uint_as_float(zb.x);
@@ -509,23 +540,33 @@ __global__ void __launch_bounds__(1024, 1) k_fps_bucket_cl(const float4 *__restr
         }
         if (rank == 0 && tid == 0) idx[start_m + 1 + it] = old;
     }
+    if (dbg && lane == 0) {
+        atomicAdd(&g_fps_dbg[0], n_touched);
+        atomicMax(&g_fps_dbg[5], (unsigned long long)max_touched);
+        if (warp == 0 && bid == 0 && rank == 0) {
+            g_fps_dbg[1] = (unsigned long long)iters;
+            g_fps_dbg[2] = (unsigned long long)(clock64() - t_start);
+            g_fps_dbg[3] = (unsigned long long)t_refresh;
+            g_fps_dbg[4] = (unsigned long long)t_xchg;
+        }
+    }
     // leave the running min-distance where the reference leaves it
     __syncthreads();
-    for (int i = tid; i < cnt; i += 1024) tmp[__float_as_int(spt[i].w)] = md[i];
+    for (int i = tid; i < cnt; i += NT) tmp[__float_as_int(spt[i].w)] = md[i];
     // no CTA may exit while a peer could still write into its shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int CL>
+template <int CL, int W, int S>
 static cudaError_t launch_fps_bucket_cl(int b, int cap, const float4 *sorted, const float *xyz, const int *offset,
                                         const int *new_offset, float *tmp, int *idx, int logB, cudaStream_t st)
 {
     const size_t smem = (size_t)cap * 20;
-    cudaError_t e = cudaFuncSetAttribute(k_fps_bucket_cl<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_fps_bucket_cl<CL, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * CL));
-    cfg.blockDim = dim3(1024);
+    cfg.blockDim = dim3(W * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -535,7 +576,19 @@ static cudaError_t launch_fps_bucket_cl(int b, int cap, const float4 *sorted, co
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_fps_bucket_cl<CL>, sorted, xyz, offset, new_offset, tmp, idx, logB, cap);
+    return cudaLaunchKernelEx(&cfg, k_fps_bucket_cl<CL, W, S>, sorted, xyz, offset, new_offset, tmp, idx, logB, cap);
+}
+
+// slots per lane for `cap` points per CTA and W warps
+template <int CL, int W>
+static cudaError_t launch_fps_bucket_cl_s(int b, int cap, const float4 *sorted, const float *xyz, const int *offset,
+                                          const int *new_offset, float *tmp, int *idx, int logB, cudaStream_t st)
+{
+    const int buckets = (cap + 31) / 32, s = (buckets + W * 32 - 1) / (W * 32);
+    if (s <= 1) return launch_fps_bucket_cl<CL, W, 1>(b, cap, sorted, xyz, offset, new_offset, tmp, idx, logB, st);
+    if (s == 2) return launch_fps_bucket_cl<CL, W, 2>(b, cap, sorted, xyz, offset, new_offset, tmp, idx, logB, st);
+    if (s == 3) return launch_fps_bucket_cl<CL, W, 3>(b, cap, sorted, xyz, offset, new_offset, tmp, idx, logB, st);
+    return cudaErrorInvalidValue;
 }
 
 template <int CL, int PPT>
@@ -609,15 +662,17 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
     if (pow_2 > 10) pow_2 = 10;
     if (pow_2 < 0) pow_2 = 0;
     if (g_fps_mode != 1) {
-        // cluster variant: the smallest cluster whose CTAs hold their share of the largest scene in shared memory
-        int cl = 2;
-        while (cl < 8 && (n_max + cl - 1) / cl > FPSC_MAX_PER_CTA) cl <<= 1;
-        if (cl < 4 && g_fps_mode == 0) cl = 4;                 // more CTAs = fewer buckets per warp; 4 is the sweet spot
+        // cluster variant.  mode 0: 8 CTAs x 4 warps | 2: 4 CTAs x 4 warps | 3: 8 CTAs x 8 warps | 4: 4 CTAs x 8 warps
+        int cl = (g_fps_mode == 2 || g_fps_mode == 4) ? 4 : 8;
+        const int w = (g_fps_mode == 3 || g_fps_mode == 4) ? 8 : 4;
+        if ((n_max + cl - 1) / cl > FPSC_MAX_PER_CTA) cl = 8;
         const int cap = (((n_max + cl - 1) / cl) + 31) / 32 * 32;
         if (cap <= FPSC_MAX_PER_CTA) {
-            cudaError_t e = cl == 2 ? launch_fps_bucket_cl<2>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st)
-                          : cl == 4 ? launch_fps_bucket_cl<4>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st)
-                                    : launch_fps_bucket_cl<8>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st);
+            cudaError_t e;
+            if (cl == 8 && w == 4) e = launch_fps_bucket_cl_s<8, 4>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st);
+            else if (cl == 8) e = launch_fps_bucket_cl_s<8, 8>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st);
+            else if (w == 4) e = launch_fps_bucket_cl_s<4, 4>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st);
+            else e = launch_fps_bucket_cl_s<4, 8>(b, cap, v.sorted, xyz, offset, new_offset, tmp, idx, pow_2, st);
             if (e != cudaSuccess) {
                 cb_set_error("cb_furthest_sampling_ws: %s", cudaGetErrorString(e));
                 (void)cudaGetLastError();
@@ -637,11 +692,12 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
     return CB_OK;
 }
 
-// developer knobs: mode 0 = cluster bucket kernel (default), 1 = single-CTA bucket kernel, 2 = cluster kernel with the
-// smallest cluster that fits; ws_min = scenes up to this size use the register-resident kernels
+// developer knobs: mode 0 = cluster bucket kernel, 8 CTAs x 4 warps (default), 1 = single-CTA bucket kernel,
+// 2 / 3 / 4 = cluster kernel with 4x4 / 8x8 / 4x8 (CTAs x warps); ws_min = scenes up to this size use the
+// register-resident kernels
 extern "C" int cb_fps_set_mode(int mode, int ws_min)
 {
-    if (mode >= 0 && mode <= 2) g_fps_mode = mode;
+    if (mode >= 0 && mode <= 4) g_fps_mode = mode;
     if (ws_min >= 1024) g_fps_ws_min = ws_min;
     return g_fps_mode;
 }

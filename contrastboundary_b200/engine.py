@@ -133,7 +133,7 @@ class GraphTrainStep(TrainStep):
         if self.world > 1:                       # replicas must start from identical parameters (DDP does this itself)
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, 0)
-        self.eager_warmup = eager_warmup
+        self.eager_warmup = max(1, eager_warmup)
         self.max_signatures = max_signatures
         self._sigs = {}            # signature -> [slot0, slot1] | None (capture failed)
         self._eager_done = 0
@@ -165,6 +165,9 @@ class GraphTrainStep(TrainStep):
         out, stages = self.model(batch, None)
         loss = self.criterion(out, batch["point_labels"], stages)
         loss.sum().backward()
+        if self._gparams is None:
+            # parameters that receive a gradient (the rest keep grad None, as in stream mode)
+            self._gparams = [p for p in self.model.parameters() if p.grad is not None]
         if self.world > 1:
             import torch.distributed as dist
             gs = [p.grad for p in self.model.parameters() if p.grad is not None]
@@ -209,9 +212,8 @@ class GraphTrainStep(TrainStep):
         from .model import level_offsets_host
         dev = self.device
         params = [p for p in self.model.parameters()] + [p for p in self.criterion.parameters()]
-        if self._gparams is None:
-            # parameters that receive a gradient (known from the eager warm-up steps); the rest keep grad None
-            self._gparams = [p for p in params if p.grad is not None]
+        if self.flat is None:
+            assert self._gparams, "GraphTrainStep needs at least one stream-mode step before the capture"
             self.flat = torch.zeros(sum(p.numel() for p in self._gparams), dtype=torch.float32, device=dev)
         ohs = level_offsets_host(list(sig), self.cfg)
         slots = [_Slot(), _Slot()]

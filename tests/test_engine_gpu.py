@@ -26,13 +26,16 @@ def test_graph_step_matches_stream_step():
         nxt = devb[(s + 1) % 3] if s in (4, 5) else None
         cur = host[s % 3] if s == 6 else devb[s % 3]
         l_ref, g_ref = gts.stream_loss_and_grad(devb[s % 3])
+        _, g_ref2 = gts.stream_loss_and_grad(devb[s % 3])
         l = gts.step(cur, next_batch=nxt)
         assert torch.isfinite(l).all(), (s, l)
         np.testing.assert_allclose(l.cpu().numpy(), l_ref.cpu().numpy(), rtol=2e-4, atol=1e-6, err_msg=f"loss, step {s}")
         if s >= 2:
-            g = gts.flat
-            rel = float((g - g_ref).norm() / g_ref.norm().clamp(min=1e-20))
-            assert rel < 2e-3, (s, rel)         # float atomics + ReLU-flip noise, far below a wrong gradient
+            # noise floor = two stream-mode evaluations of the same gradient (float atomics + ReLU-flip noise, amplified
+            # by BatchNorm over the 28 points of the deepest level); the replayed gradient must sit at that floor
+            floor = float((g_ref2 - g_ref).norm() / g_ref.norm().clamp(min=1e-20))
+            rel = float((gts.flat - g_ref).norm() / g_ref.norm().clamp(min=1e-20))
+            assert rel < max(1e-3, 4.0 * floor), (s, rel, floor)
     assert gts.graph_error is None, gts.graph_error
     assert gts.launches_per_step and gts.launches_per_step > 100
     assert all(sl.net is not None for sl in gts._sigs[tuple(host[0]["offset_host"])])
