@@ -464,6 +464,11 @@ __global__ void __launch_bounds__(W * 32, 1) k_fps_bucket_cl(const float4 *__res
     if (dbg) t_start = clock64();
     for (int it = 0; it < iters; it++) {
         const int par = it & 1;
+        // arm this iteration's barrier first (its phase cannot complete before this arrival, however early the
+        // candidates of faster warps land)
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local + (unsigned)par * 8u),
+                         "r"((unsigned)(NSLOT * 24)) : "memory");
         // 1. which of my buckets can change?  (box distance, with a 1e-4 safety margin for fp32 rounding)
         const long long c0 = dbg ? clock64() : 0;
 #pragma unroll
@@ -506,15 +511,12 @@ __global__ void __launch_bounds__(W * 32, 1) k_fps_bucket_cl(const float4 *__res
                              ::"r"(b2), "r"(cz), "r"(co), "r"(mb) : "memory");
             }
         }
-        if (tid == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local + (unsigned)par * 8u),
-                         "r"((unsigned)(NSLOT * 24)) : "memory");
         // 4. wait for the CL*W candidates of this iteration
         {
             const unsigned mb = bar_local + (unsigned)par * 8u, parity = (unsigned)(it >> 1) & 1u;
             unsigned ok;
             do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
             } while (!ok);
         }
@@ -522,21 +524,20 @@ __global__ void __launch_bounds__(W * 32, 1) k_fps_bucket_cl(const float4 *__res
         // 5. cluster arg-max (every warp of every CTA redundantly, on its own copy of the slots)
         {
             uint4 best = make_uint4(0u, 0u, 0u, 0u);
-            int bs = lane;
-            if (lane < NSLOT) best = slotA[par][lane];
+            uint2 bestB = make_uint2(0u, (unsigned)S0);
+            if (lane < NSLOT) { best = slotA[par][lane]; bestB = slotB[par][lane]; }
             if (NSLOT > 32 && lane + 32 < NSLOT) {
                 const uint4 t = slotA[par][lane + 32];
-                if (t.x > best.x || (t.x == best.x && t.y > best.y)) { best = t; bs = lane + 32; }
+                const uint2 tb = slotB[par][lane + 32];
+                if (t.x > best.x || (t.x == best.x && t.y > best.y)) { best = t; bestB = tb; }
             }
             const unsigned wd = __reduce_max_sync(CB_FULL_MASK, best.x);
             const unsigned wp = __reduce_max_sync(CB_FULL_MASK, best.x == wd ? best.y : 0u);
             const int src = __ffs(__ballot_sync(CB_FULL_MASK, best.x == wd && best.y == wp)) - 1;
-            const int sidx = __shfl_sync(CB_FULL_MASK, bs, src);
-            const uint2 zb = slotB[par][sidx < NSLOT ? sidx : 0];
             sx = __uint_as_float(__shfl_sync(CB_FULL_MASK, best.z, src));
             sy = __uint_as_float(__shfl_sync(CB_FULL_MASK, best.w, src));
-            sz = __uint_as_float(zb.x);
-            old = (int)zb.y;
+            sz = __uint_as_float(__shfl_sync(CB_FULL_MASK, bestB.x, src));
+            old = (int)__shfl_sync(CB_FULL_MASK, bestB.y, src);
         }
         if (rank == 0 && tid == 0) idx[start_m + 1 + it] = old;
     }
@@ -662,9 +663,9 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
     if (pow_2 > 10) pow_2 = 10;
     if (pow_2 < 0) pow_2 = 0;
     if (g_fps_mode != 1) {
-        // cluster variant.  mode 0: 8 CTAs x 4 warps | 2: 4 CTAs x 4 warps | 3: 8 CTAs x 8 warps | 4: 4 CTAs x 8 warps
+        // cluster variant.  mode 0: 8 CTAs x 8 warps | 2: 4 CTAs x 4 warps | 3: 8 CTAs x 4 warps | 4: 4 CTAs x 8 warps
         int cl = (g_fps_mode == 2 || g_fps_mode == 4) ? 4 : 8;
-        const int w = (g_fps_mode == 3 || g_fps_mode == 4) ? 8 : 4;
+        const int w = (g_fps_mode == 3 || g_fps_mode == 2) ? 4 : 8;
         if ((n_max + cl - 1) / cl > FPSC_MAX_PER_CTA) cl = 8;
         const int cap = (((n_max + cl - 1) / cl) + 31) / 32 * 32;
         if (cap <= FPSC_MAX_PER_CTA) {
@@ -692,8 +693,8 @@ extern "C" int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n
     return CB_OK;
 }
 
-// developer knobs: mode 0 = cluster bucket kernel, 8 CTAs x 4 warps (default), 1 = single-CTA bucket kernel,
-// 2 / 3 / 4 = cluster kernel with 4x4 / 8x8 / 4x8 (CTAs x warps); ws_min = scenes up to this size use the
+// developer knobs: mode 0 = cluster bucket kernel, 8 CTAs x 8 warps (default), 1 = single-CTA bucket kernel,
+// 2 / 3 / 4 = cluster kernel with 4x4 / 8x4 / 4x8 (CTAs x warps); ws_min = scenes up to this size use the
 // register-resident kernels
 extern "C" int cb_fps_set_mode(int mode, int ws_min)
 {

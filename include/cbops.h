@@ -101,8 +101,8 @@ int cb_furthest_sampling(int b, int n_max, const float *xyz, const int *offset, 
  * shared memory and a distributed-shared-memory all-to-all arg-max (default), or the single-CTA variant. */
 int cb_furthest_sampling_ws(int b, int n_max, const float *xyz, int n, const int *offset, const int *new_offset,
                             float *tmp, int *idx, void *workspace, size_t workspace_bytes, void *stream);
-/* developer knob: mode 0 cluster bucket kernel, 8 CTAs x 4 warps (default) | 1 single-CTA bucket kernel |
- * 2 / 3 / 4 cluster kernel with 4x4 / 8x8 / 4x8 (CTAs x warps);
+/* developer knob: mode 0 cluster bucket kernel, 8 CTAs x 8 warps (default) | 1 single-CTA bucket kernel |
+ * 2 / 3 / 4 cluster kernel with 4x4 / 8x4 / 4x8 (CTAs x warps);
  * ws_min: scenes up to this many points use the register-resident kernels.  Returns the mode in force. */
 int cb_fps_set_mode(int mode, int ws_min);
 

@@ -155,7 +155,7 @@ def test_fps_stage_sizes(lens):
     oi = oracle.furthestsampling(xyz, off, noff)
     from contrastboundary_b200 import _lib as L
     try:
-        # 0 = cluster bucket kernel (distributed shared memory, 8 CTAs x 4 warps), 1 = single-CTA bucket kernel,
+        # 0 = cluster bucket kernel (distributed shared memory, 8 CTAs x 8 warps), 1 = single-CTA bucket kernel,
         # 2 / 3 / 4 = other cluster shapes
         for mode in (0, 1, 2, 3, 4):
             L.lib().cb_fps_set_mode(mode, 8192)

@@ -13,7 +13,7 @@ for mode in (1, 0, 2, 3, 4):
     pointops.furthestsampling_known(p, o, no, 40960, 40960); torch.cuda.synchronize()
     L.lib().cb_debug_fps(C.c_int(0), out)
     it = out[1]
-    print("mode", mode, "(1 = single CTA; cluster CTAs x warps: 0 = 8x4, 2 = 4x4, 3 = 8x8, 4 = 4x8): iterations", it, "touched buckets total (4 scenes)", out[0],
+    print("mode", mode, "(1 = single CTA; cluster CTAs x warps: 0 = 8x8, 2 = 4x4, 3 = 8x4, 4 = 4x8): iterations", it, "touched buckets total (4 scenes)", out[0],
           "per iter per scene", out[0] / 4 / max(it, 1), "max per warp-iteration", out[5])
     print("   cycles/iter (warp0)", out[2] / max(it, 1), " refresh cycles/iter (warp0)", out[3] / max(it, 1),
           " exchange (send + wait) cycles/iter", out[4] / max(it, 1))
