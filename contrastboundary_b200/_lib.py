@@ -33,6 +33,8 @@ def lib():
         for name in ("cb_cbl_workspace_bytes",):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t
+        if os.environ.get("CB_FPS_MODE"):        # developer knob (profilers that cannot launch cluster kernels): see cbops.h
+            _lib.cb_fps_set_mode(C.c_int(int(os.environ["CB_FPS_MODE"])), C.c_int(8192))
     return _lib
 
 
