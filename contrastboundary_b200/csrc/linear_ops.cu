@@ -214,10 +214,22 @@ __global__ void __launch_bounds__(LG_THREADS) k_skinny_wgrad4(int n, int ci, int
     if (db && tid < co) atomicAdd(db + tid, accb);
 }
 
+// tensor-core (3xTF32) variants, tc_gemm.cu
+int cb_tc_enabled();
+void cb_tc_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, cudaStream_t st);
+void cb_tc_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, cudaStream_t st);
+void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, cudaStream_t st);
+
 extern "C" int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream)
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && X && W && Y, CB_EINVAL, "cb_linear_forward: bad arguments");
     if (n == 0) return CB_OK;
+    if (cb_tc_enabled()) {
+        cb_tc_linear_forward(n, ci, co, X, W, b, Y, (cudaStream_t)stream);
+        CB_COUNT(1);
+        CB_CUDA_CHECK("cb_linear_forward");
+        return CB_OK;
+    }
     launch_skinny(n, ci, co, X, W, ci, 1, b, Y, (cudaStream_t)stream);
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_linear_forward");
@@ -228,6 +240,12 @@ extern "C" int cb_linear_dgrad(int n, int ci, int co, const float *G, const floa
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && G && W && dX, CB_EINVAL, "cb_linear_dgrad: bad arguments");
     if (n == 0) return CB_OK;
+    if (cb_tc_enabled()) {
+        cb_tc_linear_dgrad(n, ci, co, G, W, dX, (cudaStream_t)stream);
+        CB_COUNT(1);
+        CB_CUDA_CHECK("cb_linear_dgrad");
+        return CB_OK;
+    }
     launch_skinny(n, co, ci, G, W, ci, 0, nullptr, dX, (cudaStream_t)stream);
     CB_COUNT(1);
     CB_CUDA_CHECK("cb_linear_dgrad");
@@ -237,11 +255,18 @@ extern "C" int cb_linear_dgrad(int n, int ci, int co, const float *G, const floa
 extern "C" int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, void *stream)
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && X && G && dW, CB_EINVAL, "cb_linear_wgrad: bad arguments");
-    CB_REQUIRE(ci * co <= 64 * LG_THREADS && co <= LG_THREADS, CB_EUNSUPPORTED, "cb_linear_wgrad: ci*co=%d too large", ci * co);
+    CB_REQUIRE(cb_tc_enabled() || (ci * co <= 64 * LG_THREADS && co <= LG_THREADS), CB_EUNSUPPORTED,
+               "cb_linear_wgrad: ci*co=%d too large for the SIMT kernel", ci * co);
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)ci * co, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)co, st);
     if (n == 0) return CB_OK;
+    if (cb_tc_enabled()) {
+        cb_tc_linear_wgrad(n, ci, co, X, G, dW, db, st);
+        CB_COUNT(3);
+        CB_CUDA_CHECK("cb_linear_wgrad");
+        return CB_OK;
+    }
     int blocks = 148 * 4;
     int rpb = (n + blocks - 1) / blocks;
     rpb = (rpb + WG_ROWS - 1) / WG_ROWS * WG_ROWS;

@@ -1,0 +1,252 @@
+// tc_gemm.cu — tall-skinny FP32 linear layers on the tensor cores with 3xTF32 error compensation.
+// Same operators as linear_ops.cu (reference: the nn.Linear calls of pytorch/model/blocks.py:33,72,76,108,127-131
+// and the heads' MLPs), used for the shapes that dominate the step (n >= 8192 rows, 6..512 channels).
+//
+// Why tensor cores for an HBM-bound problem: the FP32 SIMT kernels of linear_ops.cu need ~3 issue slots per FMA
+// (LDS + FFMA + address math) and run 4-6x above the HBM time of these shapes; on the tensor pipe the math is
+// free and the kernels become memory-bound.  Why 3xTF32: parity with the FP32 reference is 1e-4 on features and
+// loss, a plain TF32 product (10-bit mantissa) does not hold it through 40 layers.  Every operand x is split into
+// hi = tf32(x) and lo = tf32(x - hi); a*b ~= hi*hi + lo*hi + hi*lo with FP32 accumulation (the lo*lo term is
+// below FP32 rounding), which keeps the product error at ~2^-21 relative.
+//   forward : Y[n,co]  = X[n,ci] W[co,ci]^T + b          (A row-major, B = W as stored: "col" operand)
+//   dgrad   : dX[n,ci] = G[n,co] W[co,ci]                (B row-major [K][N], transposed while staging)
+//   wgrad   : dW[co,ci] = G^T X, db[co] = sum_rows G     (reduction over rows: split over blocks, float atomics)
+// Instruction: mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 (operands staged in shared memory by the
+// block; no tcgen05/TMEM here on purpose: tiles are 128 x {32,64} x 32 and the kernels are bandwidth-bound).
+#include "common.cuh"
+
+#define TG_BM 128
+#define TG_BK 32
+#define TG_LDS 36          // padded k-stride of the staged tiles: bank = (4*row + k) mod 32 -> conflict-free fragments
+#define TG_THREADS 256
+
+__device__ __forceinline__ unsigned tg_tf32(float x)
+{
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tg_split(float x, unsigned &hi, unsigned &lo)
+{
+    hi = tg_tf32(x);
+    lo = tg_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void tg_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C[n x N] = A[n x K] * B (+ bias).  TRANS_B: B[k][j] = W[j*ldw + k] (forward), else W[k*ldw + j] (dgrad).
+// Block: 128 rows x BN columns (BN = 32 | 64), 8 warps x 16 rows; blockIdx.y tiles N.
+template <int BN, bool TRANS_B>
+__global__ void __launch_bounds__(TG_THREADS) k_tc_gemm(int n, int K, int N, const float *__restrict__ A,
+                                                        const float *__restrict__ W, int ldw,
+                                                        const float *__restrict__ bias, float *__restrict__ C)
+{
+    constexpr int NTILE = BN / 8;
+    __shared__ __align__(16) float As[TG_BM][TG_LDS];
+    __shared__ __align__(16) unsigned Bh[BN][TG_LDS];
+    __shared__ __align__(16) unsigned Bl[BN][TG_LDS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long row0 = (long long)blockIdx.x * TG_BM;
+    const int col0 = blockIdx.y * BN;
+    const bool vecA = (K % 4 == 0) && (((uintptr_t)A & 15) == 0);
+    float acc[NTILE][4];
+#pragma unroll
+    for (int j = 0; j < NTILE; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += TG_BK) {
+        // ---- stage A chunk (128 x 32)
+        if (vecA) {
+#pragma unroll
+            for (int i = 0; i < (TG_BM * TG_BK / 4) / TG_THREADS; i++) {
+                const int e = tid + i * TG_THREADS;
+                const int r = e >> 3, kq = (e & 7) * 4;
+                const long long row = row0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < n && k0 + kq < K) v = __ldg(reinterpret_cast<const float4 *>(A + row * K + k0 + kq));
+                *reinterpret_cast<float4 *>(&As[r][kq]) = v;
+            }
+        } else {
+            for (int e = tid; e < TG_BM * TG_BK; e += TG_THREADS) {
+                const int r = e >> 5, kk = e & 31;
+                const long long row = row0 + r;
+                As[r][kk] = (row < n && k0 + kk < K) ? __ldg(A + row * K + k0 + kk) : 0.f;
+            }
+        }
+        // ---- stage B chunk (BN x 32), split into hi / lo once for the whole block
+        if (TRANS_B) {
+            for (int e = tid; e < BN * TG_BK; e += TG_THREADS) {
+                const int j = e >> 5, kk = e & 31;
+                float v = 0.f;
+                if (col0 + j < N && k0 + kk < K) v = __ldg(W + (size_t)(col0 + j) * ldw + k0 + kk);
+                unsigned hi, lo;
+                tg_split(v, hi, lo);
+                Bh[j][kk] = hi; Bl[j][kk] = lo;
+            }
+        } else {
+            for (int e = tid; e < BN * TG_BK; e += TG_THREADS) {
+                const int kk = e / BN, j = e % BN;           // coalesced along j in global memory
+                float v = 0.f;
+                if (col0 + j < N && k0 + kk < K) v = __ldg(W + (size_t)(k0 + kk) * ldw + col0 + j);
+                unsigned hi, lo;
+                tg_split(v, hi, lo);
+                Bh[j][kk] = hi; Bl[j][kk] = lo;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < TG_BK; ks += 8) {
+            unsigned ah[4], al[4];
+            tg_split(As[warp * 16 + g][ks + t], ah[0], al[0]);
+            tg_split(As[warp * 16 + g + 8][ks + t], ah[1], al[1]);
+            tg_split(As[warp * 16 + g][ks + t + 4], ah[2], al[2]);
+            tg_split(As[warp * 16 + g + 8][ks + t + 4], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < NTILE; j++) {
+                const unsigned bh0 = Bh[j * 8 + g][ks + t], bh1 = Bh[j * 8 + g][ks + t + 4];
+                const unsigned bl0 = Bl[j * 8 + g][ks + t], bl1 = Bl[j * 8 + g][ks + t + 4];
+                tg_mma(acc[j], al, bh0, bh1);      // small terms first
+                tg_mma(acc[j], ah, bl0, bl1);
+                tg_mma(acc[j], ah, bh0, bh1);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> row g+8
+#pragma unroll
+    for (int j = 0; j < NTILE; j++) {
+        const int col = col0 + j * 8 + 2 * t;
+        float b0 = 0.f, b1 = 0.f;
+        if (bias) { if (col < N) b0 = __ldg(bias + col); if (col + 1 < N) b1 = __ldg(bias + col + 1); }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const long long row = row0 + warp * 16 + g + 8 * h;
+            if (row >= n) continue;
+            float *dst = C + row * N + col;
+            const float v0 = acc[j][2 * h] + b0, v1 = acc[j][2 * h + 1] + b1;
+            if (col + 1 < N && ((N & 1) == 0)) *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
+            else { if (col < N) dst[0] = v0; if (col + 1 < N) dst[1] = v1; }
+        }
+    }
+}
+
+// wgrad: dW[co][ci] += sum_{rows of this block} G[row][co] * X[row][ci]   (A = G^T: M = co, B = X: N = ci, K = rows)
+// Block tile 64 (co) x 64 (ci); warps 4 (co) x 2 (ci): each 16 x 32.  blockIdx.y / z tile co / ci, blockIdx.x = row chunk.
+#define TW_T 64
+#define TW_LDS 72          // (72 mod 32) = 8: bank = (8*k + m) mod 32 -> conflict-free fragments
+__global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, const float *__restrict__ X,
+                                                         const float *__restrict__ G, float *__restrict__ dW,
+                                                         float *__restrict__ db, int rows_per_block)
+{
+    __shared__ __align__(16) float Gs[TG_BK][TW_LDS];
+    __shared__ __align__(16) float Xs[TG_BK][TW_LDS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int m0 = blockIdx.y * TW_T, n0 = blockIdx.z * TW_T;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    float accb = 0.f;
+    const long long r_begin = (long long)blockIdx.x * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > n) r_end = n;
+    const bool vec = (ci % 4 == 0) && (co % 4 == 0) && ((((uintptr_t)X | (uintptr_t)G) & 15) == 0);
+    for (long long r0 = r_begin; r0 < r_end; r0 += TG_BK) {
+        // stage 32 rows x 64 columns of G and of X (zero beyond the edges)
+        if (vec) {
+            for (int e = tid; e < TG_BK * (TW_T / 4); e += TG_THREADS) {
+                const int r = e >> 4, q = (e & 15) * 4;
+                const long long row = r0 + r;
+                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), xv = gv;
+                if (row < r_end) {
+                    if (m0 + q < co) gv = __ldg(reinterpret_cast<const float4 *>(G + row * co + m0 + q));
+                    if (n0 + q < ci) xv = __ldg(reinterpret_cast<const float4 *>(X + row * ci + n0 + q));
+                }
+                *reinterpret_cast<float4 *>(&Gs[r][q]) = gv;
+                *reinterpret_cast<float4 *>(&Xs[r][q]) = xv;
+            }
+        } else {
+            for (int e = tid; e < TG_BK * TW_T; e += TG_THREADS) {
+                const int r = e >> 6, q = e & 63;
+                const long long row = r0 + r;
+                Gs[r][q] = (row < r_end && m0 + q < co) ? __ldg(G + row * co + m0 + q) : 0.f;
+                Xs[r][q] = (row < r_end && n0 + q < ci) ? __ldg(X + row * ci + n0 + q) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < TG_BK; ks += 8) {
+            unsigned ah[4], al[4];
+            tg_split(Gs[ks + t][wm * 16 + g], ah[0], al[0]);
+            tg_split(Gs[ks + t][wm * 16 + g + 8], ah[1], al[1]);
+            tg_split(Gs[ks + t + 4][wm * 16 + g], ah[2], al[2]);
+            tg_split(Gs[ks + t + 4][wm * 16 + g + 8], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                unsigned bh0, bl0, bh1, bl1;
+                tg_split(Xs[ks + t][wn * 32 + j * 8 + g], bh0, bl0);
+                tg_split(Xs[ks + t + 4][wn * 32 + j * 8 + g], bh1, bl1);
+                tg_mma(acc[j], al, bh0, bh1);
+                tg_mma(acc[j], ah, bl0, bl1);
+                tg_mma(acc[j], ah, bh0, bh1);
+            }
+        }
+        if (db && blockIdx.z == 0 && tid < TW_T) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < TG_BK; r++) s += Gs[r][tid];
+            accb += s;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + wm * 16 + g + 8 * h, c = n0 + wn * 32 + j * 8 + 2 * t;
+            if (m < co) {
+                if (c < ci) atomicAdd(dW + (size_t)m * ci + c, acc[j][2 * h]);
+                if (c + 1 < ci) atomicAdd(dW + (size_t)m * ci + c + 1, acc[j][2 * h + 1]);
+            }
+        }
+    if (db && blockIdx.z == 0 && tid < TW_T && m0 + tid < co) atomicAdd(db + m0 + tid, accb);
+}
+
+static int g_tc_enabled = 1;
+extern "C" int cb_linear_set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; return g_tc_enabled; }
+int cb_tc_enabled() { return g_tc_enabled; }
+
+template <bool TRANS_B>
+static void tc_launch(int n, int K, int N, const float *A, const float *W, int ldw, const float *bias, float *C, cudaStream_t st)
+{
+    const int gx = (n + TG_BM - 1) / TG_BM;
+    // column tiles of 64 (or 32 when that wastes fewer padded columns); the A tile of further column tiles comes from L2
+    const int w64 = (N + 63) / 64 * 64 - N, w32 = (N + 31) / 32 * 32 - N;
+    if (N <= 32 || w32 < w64) k_tc_gemm<32, TRANS_B><<<dim3(gx, (N + 31) / 32), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
+    else k_tc_gemm<64, TRANS_B><<<dim3(gx, (N + 63) / 64), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
+}
+
+void cb_tc_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, cudaStream_t st)
+{
+    tc_launch<true>(n, ci, co, X, W, ci, b, Y, st);
+}
+void cb_tc_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, cudaStream_t st)
+{
+    tc_launch<false>(n, co, ci, G, W, ci, nullptr, dX, st);
+}
+// dW and db must be zero-filled by the caller
+void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, cudaStream_t st)
+{
+    const int ty = (co + TW_T - 1) / TW_T, tz = (ci + TW_T - 1) / TW_T;
+    int blocks = (148 * 2) / (ty * tz);
+    if (blocks < 8) blocks = 8;
+    int rpb = (n + blocks - 1) / blocks;
+    rpb = (rpb + TG_BK - 1) / TG_BK * TG_BK;
+    blocks = (n + rpb - 1) / rpb;
+    k_tc_wgrad<<<dim3(blocks, ty, tz), TG_THREADS, 0, st>>>(n, ci, co, X, G, dW, db, rpb);
+}

@@ -10,7 +10,15 @@ from . import _lib as L
 
 MIN_ROWS = 8192        # below this cuBLAS is fine (and launch latency dominates anyway)
 MAX_CO = 512
-MAX_WGRAD = 16384      # ci*co handled by the custom wgrad kernel
+MAX_WGRAD = 16384      # ci*co handled by the SIMT wgrad kernel (the tensor-core kernel has no limit)
+TENSOR_CORES = True    # 3xTF32 tensor-core kernels (tc_gemm.cu); False = FP32 SIMT kernels (linear_ops.cu)
+
+
+def set_tensor_cores(flag):
+    global TENSOR_CORES
+    TENSOR_CORES = bool(flag)
+    import ctypes as C
+    L.lib().cb_linear_set_tensor_cores(C.c_int(1 if flag else 0))
 
 
 class _SkinnyLinearFn(Function):
@@ -35,7 +43,7 @@ class _SkinnyLinearFn(Function):
             gx = torch.empty_like(x)
             L.call("cb_linear_dgrad", n, ci, co, g, weight, gx, L.stream())
         if ctx.needs_input_grad[1]:
-            if ci * co <= MAX_WGRAD and co <= 256:
+            if TENSOR_CORES or (ci * co <= MAX_WGRAD and co <= 256):
                 gw = torch.empty_like(weight)
                 gb = torch.empty(co, dtype=torch.float32, device=x.device) if ctx.has_bias else None
                 L.call("cb_linear_wgrad", n, ci, co, x, g, gw, gb, L.stream())

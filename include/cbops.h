@@ -273,6 +273,10 @@ int cb_td_backward(int m, int k, int c, const float *rel, const int *idx, const 
 int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream);
 int cb_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, void *stream);
 int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, void *stream);
+/* 1 (default): the three calls above run on the tensor cores with 3xTF32 error compensation (hi/lo operand split,
+ * FP32 accumulate; tc_gemm.cu) and are HBM-bound; 0: exact-FP32 SIMT kernels (and the ci*co <= 16384 limit of the SIMT
+ * wgrad).  Returns the setting in force. */
+int cb_linear_set_tensor_cores(int on);
 
 /* backward of cb_pt_layer_forward.  grad_xk / grad_xv (n,c) and grad_params must be ZERO-FILLED by the
  * caller (scatter / accumulation targets); grad_xq is overwritten.  grad_params layout (floats):

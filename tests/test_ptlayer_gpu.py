@@ -83,9 +83,22 @@ def test_fused_layer_matches_unfused(c, k, n_list, training):
             assert rel_err(bf1[name], bf0[name]) < 1e-4, f"buffer {name}"
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("n,ci,co,bias", [(20000, 32, 32, True), (163840, 6, 32, False), (50000, 35, 64, False),
-                                         (16384, 67, 128, False), (30000, 160, 13, True), (9000, 131, 256, False)])
-def test_skinny_linear(n, ci, co, bias):
+                                         (16384, 67, 128, False), (30000, 160, 13, True), (9000, 131, 256, False),
+                                         (40960, 64, 192, True), (10240, 128, 384, True), (8200, 256, 96, False)])
+def test_skinny_linear(n, ci, co, bias, tensor_cores):
+    """tall-skinny linear layers vs float64: the 3xTF32 tensor-core kernels must hold the same FP32-level error
+    as the exact-FP32 SIMT kernels"""
+    from contrastboundary_b200 import linear_ops
+    linear_ops.set_tensor_cores(tensor_cores)
+    try:
+        _skinny_linear_case(n, ci, co, bias)
+    finally:
+        linear_ops.set_tensor_cores(True)
+
+
+def _skinny_linear_case(n, ci, co, bias):
     from contrastboundary_b200 import linear_ops
     torch.manual_seed(n % 97)
     x = torch.randn(n, ci, device="cuda", requires_grad=True)
