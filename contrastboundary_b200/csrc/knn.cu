@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
 // block evaluates distances in index order, thread 0 runs the reference's heap
 // (knnquery_cuda_kernel.cu:21-48,91-110) in shared memory.
 // ---------------------------------------------------------------------------------------------
-#define CB_REPLAY_THREADS 256
-#define CB_REPLAY_PER_THREAD 16
+#define CB_REPLAY_THREADS 1024
+#define CB_REPLAY_PER_THREAD 4
 #define CB_REPLAY_BATCH (CB_REPLAY_THREADS * CB_REPLAY_PER_THREAD)
 // The heap replay itself is serial (the reference's result under ties is defined by its heap
 // history), but only candidates with d2 < root are ever inserted and the root never grows.  So the
@@ -378,22 +378,24 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
         // Graded batches (256, 512, ... 4096 candidates): a batch is pre-filtered against the heap root at its start,
         // which is 1e10 for the first one — keeping that one small keeps the serial pass of thread 0 short
         // (expected survivors of a batch of s candidates after p scanned ones: s * K / p).
-        int pt = 1;
+        int bs = 256;                       // batch size: 256, 512, ... CB_REPLAY_BATCH
         for (int base = start; base < end;) {
             const float root = hd[0];
+            const int pt = bs >= CB_REPLAY_THREADS ? bs / CB_REPLAY_THREADS : 1;
             const int i0 = base + t * pt;
+            const int lim = min(end, base + bs);
             float d[CB_REPLAY_PER_THREAD];
             int npass = 0;
 #pragma unroll
             for (int u = 0; u < CB_REPLAY_PER_THREAD; u++) {
                 const int i = i0 + u;
                 d[u] = 3.0e38f;
-                if (u < pt && i < end)
+                if (u < pt && i < lim)
                     d[u] = cb_sqdist_mode(dist_mode, qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
                 npass += d[u] < root;
             }
-            base += CB_REPLAY_THREADS * pt;
-            if (pt < CB_REPLAY_PER_THREAD) pt <<= 1;
+            base += bs;
+            if (bs < CB_REPLAY_BATCH) bs <<= 1;
             // block exclusive scan of npass (thread order == index order)
             int inc = npass;
 #pragma unroll
@@ -403,8 +405,18 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
             }
             if (lane == 31) warp_cnt[w] = inc;
             __syncthreads();
-            int woff = 0;
-            for (int k = 0; k < w; k++) woff += warp_cnt[k];
+            // exclusive offset of this warp = sum of the counts of the warps before it (second-level warp scan)
+            int woff;
+            {
+                const int wc = lane < CB_REPLAY_THREADS / 32 ? warp_cnt[lane] : 0;
+                int winc = wc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(CB_FULL_MASK, winc, o);
+                    if (lane >= o) winc += v;
+                }
+                woff = __shfl_sync(CB_FULL_MASK, winc - wc, w);
+            }
             if (t == CB_REPLAY_THREADS - 1) s_total = woff + inc;
             int pos = woff + inc - npass;
 #pragma unroll

@@ -39,97 +39,114 @@ __device__ __forceinline__ void tg_mma(float (&d)[4], const unsigned (&a)[4], un
 }
 
 // C[n x N] = A[n x K] * B (+ bias).  TRANS_B: B[k][j] = W[j*ldw + k] (forward), else W[k*ldw + j] (dgrad).
-// Block: 128 rows x BN columns (BN = 32 | 64), 8 warps x 16 rows; blockIdx.y tiles N.
+// Block: 128 rows x BN columns (BN = 32 | 64), 8 warps x 16 rows; blockIdx.y tiles N.  Persistent over row tiles:
+// the A chunk of the NEXT (tile, k-chunk) is prefetched into registers while the current one is multiplied, and
+// the (hi, lo)-split B tile stays resident in shared memory when K <= 32 (the common case: one k-chunk).
 template <int BN, bool TRANS_B>
-__global__ void __launch_bounds__(TG_THREADS) k_tc_gemm(int n, int K, int N, const float *__restrict__ A,
-                                                        const float *__restrict__ W, int ldw,
-                                                        const float *__restrict__ bias, float *__restrict__ C)
+__global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, const float *__restrict__ A,
+                                                           const float *__restrict__ W, int ldw,
+                                                           const float *__restrict__ bias, float *__restrict__ C)
 {
     constexpr int NTILE = BN / 8;
+    constexpr int APT = (TG_BM * TG_BK / 4) / TG_THREADS;     // float4 of the A chunk per thread (4)
     __shared__ __align__(16) float As[TG_BM][TG_LDS];
     __shared__ __align__(16) unsigned Bh[BN][TG_LDS];
     __shared__ __align__(16) unsigned Bl[BN][TG_LDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const long long row0 = (long long)blockIdx.x * TG_BM;
     const int col0 = blockIdx.y * BN;
     const bool vecA = (K % 4 == 0) && (((uintptr_t)A & 15) == 0);
-    float acc[NTILE][4];
-#pragma unroll
-    for (int j = 0; j < NTILE; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const int nchunks = (K + TG_BK - 1) / TG_BK;
+    const long long ntiles = ((long long)n + TG_BM - 1) / TG_BM;
 
-    for (int k0 = 0; k0 < K; k0 += TG_BK) {
-        // ---- stage A chunk (128 x 32)
-        if (vecA) {
+    auto loadA = [&](long long tile, int chunk, float4 (&pa)[APT]) {
 #pragma unroll
-            for (int i = 0; i < (TG_BM * TG_BK / 4) / TG_THREADS; i++) {
-                const int e = tid + i * TG_THREADS;
-                const int r = e >> 3, kq = (e & 7) * 4;
-                const long long row = row0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < n && k0 + kq < K) v = __ldg(reinterpret_cast<const float4 *>(A + row * K + k0 + kq));
-                *reinterpret_cast<float4 *>(&As[r][kq]) = v;
-            }
-        } else {
-            for (int e = tid; e < TG_BM * TG_BK; e += TG_THREADS) {
-                const int r = e >> 5, kk = e & 31;
-                const long long row = row0 + r;
-                As[r][kk] = (row < n && k0 + kk < K) ? __ldg(A + row * K + k0 + kk) : 0.f;
-            }
+        for (int i = 0; i < APT; i++) {
+            const int e = tid + i * TG_THREADS;
+            const int r = e >> 3, kq = (e & 7) * 4;
+            const long long row = tile * TG_BM + r;
+            pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < n && chunk * TG_BK + kq < K) pa[i] = __ldg(reinterpret_cast<const float4 *>(A + row * K + chunk * TG_BK + kq));
         }
-        // ---- stage B chunk (BN x 32), split into hi / lo once for the whole block
-        if (TRANS_B) {
-            for (int e = tid; e < BN * TG_BK; e += TG_THREADS) {
-                const int j = e >> 5, kk = e & 31;
-                float v = 0.f;
-                if (col0 + j < N && k0 + kk < K) v = __ldg(W + (size_t)(col0 + j) * ldw + k0 + kk);
-                unsigned hi, lo;
-                tg_split(v, hi, lo);
-                Bh[j][kk] = hi; Bl[j][kk] = lo;
-            }
-        } else {
-            for (int e = tid; e < BN * TG_BK; e += TG_THREADS) {
-                const int kk = e / BN, j = e % BN;           // coalesced along j in global memory
-                float v = 0.f;
-                if (col0 + j < N && k0 + kk < K) v = __ldg(W + (size_t)(k0 + kk) * ldw + col0 + j);
-                unsigned hi, lo;
-                tg_split(v, hi, lo);
-                Bh[j][kk] = hi; Bl[j][kk] = lo;
-            }
+    };
+    auto stageB = [&](int chunk) {
+        const int k0 = chunk * TG_BK;
+        for (int e = tid; e < BN * TG_BK; e += TG_THREADS) {
+            int j, kk;
+            if (TRANS_B) { j = e >> 5; kk = e & 31; }
+            else { kk = e / BN; j = e % BN; }                    // coalesced along j in global memory
+            float v = 0.f;
+            if (col0 + j < N && k0 + kk < K)
+                v = TRANS_B ? __ldg(W + (size_t)(col0 + j) * ldw + k0 + kk) : __ldg(W + (size_t)(k0 + kk) * ldw + col0 + j);
+            unsigned hi, lo;
+            tg_split(v, hi, lo);
+            Bh[j][kk] = hi; Bl[j][kk] = lo;
         }
-        __syncthreads();
+    };
+
+    float4 pa[APT];
+    long long tile = blockIdx.x;
+    if (nchunks == 1) stageB(0);
+    if (vecA && tile < ntiles) loadA(tile, 0, pa);
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TG_BM;
+        float acc[NTILE][4];
 #pragma unroll
-        for (int ks = 0; ks < TG_BK; ks += 8) {
-            unsigned ah[4], al[4];
-            tg_split(As[warp * 16 + g][ks + t], ah[0], al[0]);
-            tg_split(As[warp * 16 + g + 8][ks + t], ah[1], al[1]);
-            tg_split(As[warp * 16 + g][ks + t + 4], ah[2], al[2]);
-            tg_split(As[warp * 16 + g + 8][ks + t + 4], ah[3], al[3]);
+        for (int j = 0; j < NTILE; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int chunk = 0; chunk < nchunks; chunk++) {
+            if (vecA) {
 #pragma unroll
-            for (int j = 0; j < NTILE; j++) {
-                const unsigned bh0 = Bh[j * 8 + g][ks + t], bh1 = Bh[j * 8 + g][ks + t + 4];
-                const unsigned bl0 = Bl[j * 8 + g][ks + t], bl1 = Bl[j * 8 + g][ks + t + 4];
-                tg_mma(acc[j], al, bh0, bh1);      // small terms first
-                tg_mma(acc[j], ah, bl0, bl1);
-                tg_mma(acc[j], ah, bh0, bh1);
+                for (int i = 0; i < APT; i++) {
+                    const int e = tid + i * TG_THREADS;
+                    *reinterpret_cast<float4 *>(&As[e >> 3][(e & 7) * 4]) = pa[i];
+                }
+            } else {
+                const int k0 = chunk * TG_BK;
+                for (int e = tid; e < TG_BM * TG_BK; e += TG_THREADS) {
+                    const int r = e >> 5, kk = e & 31;
+                    const long long row = row0 + r;
+                    As[r][kk] = (row < n && k0 + kk < K) ? __ldg(A + row * K + k0 + kk) : 0.f;
+                }
             }
+            if (nchunks > 1) stageB(chunk);
+            __syncthreads();
+            if (vecA) {                                      // prefetch the next chunk (of this or of the next tile)
+                if (chunk + 1 < nchunks) loadA(tile, chunk + 1, pa);
+                else if (tile + gridDim.x < ntiles) loadA(tile + gridDim.x, 0, pa);
+            }
+#pragma unroll
+            for (int ks = 0; ks < TG_BK; ks += 8) {
+                unsigned ah[4], al[4];
+                tg_split(As[warp * 16 + g][ks + t], ah[0], al[0]);
+                tg_split(As[warp * 16 + g + 8][ks + t], ah[1], al[1]);
+                tg_split(As[warp * 16 + g][ks + t + 4], ah[2], al[2]);
+                tg_split(As[warp * 16 + g + 8][ks + t + 4], ah[3], al[3]);
+#pragma unroll
+                for (int j = 0; j < NTILE; j++) {
+                    const unsigned bh0 = Bh[j * 8 + g][ks + t], bh1 = Bh[j * 8 + g][ks + t + 4];
+                    const unsigned bl0 = Bl[j * 8 + g][ks + t], bl1 = Bl[j * 8 + g][ks + t + 4];
+                    tg_mma(acc[j], al, bh0, bh1);      // small terms first
+                    tg_mma(acc[j], ah, bl0, bl1);
+                    tg_mma(acc[j], ah, bh0, bh1);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    // ---- epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> row g+8
+        // ---- epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> row g+8
 #pragma unroll
-    for (int j = 0; j < NTILE; j++) {
-        const int col = col0 + j * 8 + 2 * t;
-        float b0 = 0.f, b1 = 0.f;
-        if (bias) { if (col < N) b0 = __ldg(bias + col); if (col + 1 < N) b1 = __ldg(bias + col + 1); }
+        for (int j = 0; j < NTILE; j++) {
+            const int col = col0 + j * 8 + 2 * t;
+            float b0 = 0.f, b1 = 0.f;
+            if (bias) { if (col < N) b0 = __ldg(bias + col); if (col + 1 < N) b1 = __ldg(bias + col + 1); }
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const long long row = row0 + warp * 16 + g + 8 * h;
-            if (row >= n) continue;
-            float *dst = C + row * N + col;
-            const float v0 = acc[j][2 * h] + b0, v1 = acc[j][2 * h + 1] + b1;
-            if (col + 1 < N && ((N & 1) == 0)) *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
-            else { if (col < N) dst[0] = v0; if (col + 1 < N) dst[1] = v1; }
+            for (int h = 0; h < 2; h++) {
+                const long long row = row0 + warp * 16 + g + 8 * h;
+                if (row >= n) continue;
+                float *dst = C + row * N + col;
+                const float v0 = acc[j][2 * h] + b0, v1 = acc[j][2 * h + 1] + b1;
+                if (col + 1 < N && ((N & 1) == 0)) *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
+                else { if (col < N) dst[0] = v0; if (col + 1 < N) dst[1] = v1; }
+            }
         }
     }
 }
@@ -156,19 +173,31 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
     long long r_end = r_begin + rows_per_block;
     if (r_end > n) r_end = n;
     const bool vec = (ci % 4 == 0) && (co % 4 == 0) && ((((uintptr_t)X | (uintptr_t)G) & 15) == 0);
+    constexpr int WPT = (TG_BK * (TW_T / 4)) / TG_THREADS;       // float4 per thread and matrix (2)
+    float4 pg[WPT], px[WPT];
+    auto prefetch = [&](long long r0) {
+#pragma unroll
+        for (int i = 0; i < WPT; i++) {
+            const int e = tid + i * TG_THREADS;
+            const int r = e >> 4, q = (e & 15) * 4;
+            const long long row = r0 + r;
+            pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            px[i] = pg[i];
+            if (row < r_end) {
+                if (m0 + q < co) pg[i] = __ldg(reinterpret_cast<const float4 *>(G + row * co + m0 + q));
+                if (n0 + q < ci) px[i] = __ldg(reinterpret_cast<const float4 *>(X + row * ci + n0 + q));
+            }
+        }
+    };
+    if (vec && r_begin < r_end) prefetch(r_begin);
     for (long long r0 = r_begin; r0 < r_end; r0 += TG_BK) {
         // stage 32 rows x 64 columns of G and of X (zero beyond the edges)
         if (vec) {
-            for (int e = tid; e < TG_BK * (TW_T / 4); e += TG_THREADS) {
-                const int r = e >> 4, q = (e & 15) * 4;
-                const long long row = r0 + r;
-                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), xv = gv;
-                if (row < r_end) {
-                    if (m0 + q < co) gv = __ldg(reinterpret_cast<const float4 *>(G + row * co + m0 + q));
-                    if (n0 + q < ci) xv = __ldg(reinterpret_cast<const float4 *>(X + row * ci + n0 + q));
-                }
-                *reinterpret_cast<float4 *>(&Gs[r][q]) = gv;
-                *reinterpret_cast<float4 *>(&Xs[r][q]) = xv;
+#pragma unroll
+            for (int i = 0; i < WPT; i++) {
+                const int e = tid + i * TG_THREADS;
+                *reinterpret_cast<float4 *>(&Gs[e >> 4][(e & 15) * 4]) = pg[i];
+                *reinterpret_cast<float4 *>(&Xs[e >> 4][(e & 15) * 4]) = px[i];
             }
         } else {
             for (int e = tid; e < TG_BK * TW_T; e += TG_THREADS) {
@@ -179,6 +208,7 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
             }
         }
         __syncthreads();
+        if (vec && r0 + TG_BK < r_end) prefetch(r0 + TG_BK);
 #pragma unroll
         for (int ks = 0; ks < TG_BK; ks += 8) {
             unsigned ah[4], al[4];
@@ -224,11 +254,16 @@ int cb_tc_enabled() { return g_tc_enabled; }
 template <bool TRANS_B>
 static void tc_launch(int n, int K, int N, const float *A, const float *W, int ldw, const float *bias, float *C, cudaStream_t st)
 {
-    const int gx = (n + TG_BM - 1) / TG_BM;
+    const int ntiles = (n + TG_BM - 1) / TG_BM;
     // column tiles of 64 (or 32 when that wastes fewer padded columns); the A tile of further column tiles comes from L2
     const int w64 = (N + 63) / 64 * 64 - N, w32 = (N + 31) / 32 * 32 - N;
-    if (N <= 32 || w32 < w64) k_tc_gemm<32, TRANS_B><<<dim3(gx, (N + 31) / 32), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
-    else k_tc_gemm<64, TRANS_B><<<dim3(gx, (N + 63) / 64), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
+    const bool use32 = N <= 32 || w32 < w64;
+    const int gy = use32 ? (N + 31) / 32 : (N + 63) / 64;
+    int gx = (148 * 2 + gy - 1) / gy;                        // persistent: ~2 CTAs per SM in total
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    if (use32) k_tc_gemm<32, TRANS_B><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
+    else k_tc_gemm<64, TRANS_B><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
 }
 
 void cb_tc_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, cudaStream_t st)
