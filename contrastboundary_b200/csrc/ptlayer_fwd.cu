@@ -437,6 +437,11 @@ extern "C" int cb_pt_rel(int n, int k, const float *p, const int *idx, float *re
     return CB_OK;
 }
 
+int cb_pt_mma_enabled();
+void cb_pt_w2_mma(int c, int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
+                  const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3, const float *b3,
+                  float *w2out, double *stats, cudaStream_t st);
+
 template <int C>
 static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *rel, const double *moments, const int *idx,
                         const float *xq, const float *xk, const float *xv, float *out, float *w2buf, float *abuf,
@@ -455,9 +460,14 @@ static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *r
         k_pt_w0_stats<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, stats2);
     k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(stats2, rows, C, L->bn2_weight, L->bn2_bias, L->bn2_running_mean,
                                                     L->bn2_running_var, L->momentum, L->eps, L->training, bn2);
-    const size_t smem = (size_t)CS * C * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_w2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_pt_w2<C><<<grid, PT_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3);
+    if (cb_pt_mma_enabled() && ld % 2 == 0) {
+        // tensor cores (3xTF32), ptlayer_mma.cu
+        cb_pt_w2_mma(C, n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3, st);
+    } else {
+        const size_t smem = (size_t)CS * C * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_w2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_pt_w2<C><<<grid, PT_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3);
+    }
     k_bn_finalize<<<1, 128, 0, st>>>(stats3, rows, CS, L->bn3_weight, L->bn3_bias, L->bn3_running_mean,
                                       L->bn3_running_var, L->momentum, L->eps, L->training, bn3);
     const size_t smem4 = (size_t)(CS * (CS + 1) + 2 * CS) * sizeof(float);

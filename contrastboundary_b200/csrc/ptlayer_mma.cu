@@ -1,0 +1,214 @@
+// ptlayer_mma.cu — the dense contraction of the PointTransformer local aggregation on the tensor cores.
+// Reference: linear_w[2] of PointTransformerLayer (pytorch/model/blocks.py:24-28,40): for every (point, neighbour)
+// row, w2 = W3 relu(bn2(w0)) + b3 — the only genuine (n*k) x c x c/8 dense contraction of the layer.
+//
+// One warp owns a tile of 16 consecutive rows of the (n*k) row space (one neighbourhood for k = 16) = one m16 MMA
+// tile.  The A operand u = relu(bn2(x_k[idx] - x_q + pr)) never exists in memory: every lane gathers and computes
+// exactly the elements of its A fragment.  The contraction index (channel) is PERMUTED inside each group of 8
+// channels — virtual column t <-> channel 2t, t+4 <-> channel 2t+1 — so that a lane's fragment elements are two
+// adjacent channels of rows g and g+8: one 8-byte gather per row and k-step, and 32 contiguous bytes per row
+// across the four lanes of a quad.  B = W3 is staged once per CTA in shared memory (split into TF32 hi / lo)
+// with the same permutation folded into its indexing.  3xTF32 (tf32.cuh) keeps FP32-level accuracy.
+#include "ptlayer.cuh"
+#include "tf32.cuh"
+
+#define PM_THREADS 256
+#define PM_WARPS (PM_THREADS / 32)
+
+static int g_pt_mma = 1;
+extern "C" int cb_pt_set_tensor_cores(int on) { g_pt_mma = on ? 1 : 0; return g_pt_mma; }
+int cb_pt_mma_enabled() { return g_pt_mma; }
+
+struct PmSmall { float w1[9], b1[3], sc1[3], sh1[3]; };
+__device__ __forceinline__ PmSmall pm_small_load(const float *__restrict__ d)
+{
+    PmSmall s;
+#pragma unroll
+    for (int i = 0; i < 9; i++) s.w1[i] = __ldg(d + i);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { s.b1[i] = __ldg(d + 9 + i); s.sc1[i] = __ldg(d + 12 + i); s.sh1[i] = __ldg(d + 15 + i); }
+    return s;
+}
+__device__ __forceinline__ void pm_g1(const PmSmall &sp, float rx, float ry, float rz, float (&g)[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float h = sp.w1[3 * a] * rx + sp.w1[3 * a + 1] * ry + sp.w1[3 * a + 2] * rz + sp.b1[a];
+        g[a] = fmaxf(h * sp.sc1[a] + sp.sh1[a], 0.f);
+    }
+}
+
+// shared-memory size of k_pt_w2_mma<C>
+template <int C> struct PmW2 {
+    static constexpr int CS = C / 8;
+    static constexpr int NT = (CS + 7) / 8;          // n-tiles of 8 output columns
+    static constexpr int CSP = NT * 8;               // padded output columns (rows of W3 beyond CS are zero)
+    static constexpr int LDW = C + 8;                // row stride of the staged W3: (LDW / 2) mod 16 == 4 -> conflict-free LDS.64
+    static constexpr bool PRESPLIT = C <= 256;       // hi and lo copies fit in shared memory
+    static constexpr size_t smem = (size_t)(PRESPLIT ? 2 : 1) * CSP * LDW * 4 + (size_t)C * 8 * 4 + 2 * CS * 4;
+};
+
+template <int C>
+__global__ void __launch_bounds__(PM_THREADS) k_pt_w2_mma(int n, int k, int ld, const float *__restrict__ rel,
+                                                          const int *__restrict__ idx, const float *__restrict__ xq,
+                                                          const float *__restrict__ xk, const float *__restrict__ w2p,
+                                                          const float *__restrict__ b2p, const float *__restrict__ smalld,
+                                                          const float *__restrict__ bn2 /* [4][C] */,
+                                                          const float *__restrict__ w3 /* [CS][C] */,
+                                                          const float *__restrict__ b3, float *__restrict__ w2out,
+                                                          double *__restrict__ stats /* [2][CS] */)
+{
+    using T = PmW2<C>;
+    constexpr int CS = T::CS, NT = T::NT, CSP = T::CSP, LDW = T::LDW;
+    extern __shared__ __align__(16) unsigned char pm_sm[];
+    unsigned *Wh = reinterpret_cast<unsigned *>(pm_sm);                       // [CSP][LDW]  tf32 hi (or raw fp32 when !PRESPLIT)
+    unsigned *Wl = Wh + (T::PRESPLIT ? CSP * LDW : 0);                        // [CSP][LDW]  tf32 lo
+    float *P = reinterpret_cast<float *>(Wh + (T::PRESPLIT ? 2 : 1) * CSP * LDW);   // [C][8]: w2a w2b w2c b2 sc2 sh2 - -
+    float *comb = P + C * 8;                                                  // [2][CS]
+    const PmSmall sp = pm_small_load(smalld);
+    for (int e = threadIdx.x; e < CSP * C; e += PM_THREADS) {
+        const int i = e / C, c = e % C;
+        const float v = i < CS ? __ldg(w3 + (size_t)i * C + c) : 0.f;
+        if (T::PRESPLIT) {
+            unsigned hi, lo;
+            tg_split(v, hi, lo);
+            Wh[i * LDW + c] = hi; Wl[i * LDW + c] = lo;
+        } else {
+            Wh[i * LDW + c] = __float_as_uint(v);
+        }
+    }
+    for (int c = threadIdx.x; c < C; c += PM_THREADS) {
+        float *p = P + c * 8;
+        p[0] = __ldg(w2p + 3 * c); p[1] = __ldg(w2p + 3 * c + 1); p[2] = __ldg(w2p + 3 * c + 2); p[3] = __ldg(b2p + c);
+        p[4] = __ldg(bn2 + c); p[5] = __ldg(bn2 + C + c); p[6] = 0.f; p[7] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 2 * CS; i += PM_THREADS) comb[i] = 0.f;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long rows = (long long)n * k;
+    const long long tiles = (rows + 15) >> 4;
+    float t1[NT][2], t2[NT][2], bias3[NT][2];
+#pragma unroll
+    for (int jn = 0; jn < NT; jn++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            t1[jn][e] = 0.f; t2[jn][e] = 0.f;
+            const int col = jn * 8 + 2 * t + e;
+            bias3[jn][e] = col < CS ? __ldg(b3 + col) : 0.f;
+        }
+    for (long long tile = (long long)blockIdx.x * PM_WARPS + wib; tile < tiles; tile += (long long)gridDim.x * PM_WARPS) {
+        const long long rA = tile * 16 + g, rB = rA + 8;
+        const bool vA = rA < rows, vB = rB < rows;
+        const long long ra = vA ? rA : 0, rb = vB ? rB : 0;
+        const float *xkA = xk + (size_t)__ldg(idx + ra) * ld, *xkB = xk + (size_t)__ldg(idx + rb) * ld;
+        const float *xqA = xq + (size_t)(ra / k) * ld, *xqB = xq + (size_t)(rb / k) * ld;
+        float gA[3], gB[3];
+        pm_g1(sp, __ldg(rel + 3 * ra), __ldg(rel + 3 * ra + 1), __ldg(rel + 3 * ra + 2), gA);
+        pm_g1(sp, __ldg(rel + 3 * rb), __ldg(rel + 3 * rb + 1), __ldg(rel + 3 * rb + 2), gB);
+        float acc[NT][4];
+#pragma unroll
+        for (int jn = 0; jn < NT; jn++) acc[jn][0] = acc[jn][1] = acc[jn][2] = acc[jn][3] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < C / 8; j++) {
+            const int ch = 8 * j + 2 * t;
+            const float2 xa = __ldg(reinterpret_cast<const float2 *>(xkA + ch)), xb = __ldg(reinterpret_cast<const float2 *>(xkB + ch));
+            const float2 qa = __ldg(reinterpret_cast<const float2 *>(xqA + ch)), qb = __ldg(reinterpret_cast<const float2 *>(xqB + ch));
+            const float4 p0 = *reinterpret_cast<const float4 *>(P + ch * 8), p0b = *reinterpret_cast<const float4 *>(P + ch * 8 + 4);
+            const float4 p1 = *reinterpret_cast<const float4 *>(P + ch * 8 + 8), p1b = *reinterpret_cast<const float4 *>(P + ch * 8 + 12);
+            // u = relu(bn2(x_k - x_q + W2 g1 + b2)), same operation order as the SIMT kernels
+            const float prA0 = p0.x * gA[0] + p0.y * gA[1] + p0.z * gA[2] + p0.w, prA1 = p1.x * gA[0] + p1.y * gA[1] + p1.z * gA[2] + p1.w;
+            const float prB0 = p0.x * gB[0] + p0.y * gB[1] + p0.z * gB[2] + p0.w, prB1 = p1.x * gB[0] + p1.y * gB[1] + p1.z * gB[2] + p1.w;
+            float uA0 = fmaxf((xa.x - qa.x + prA0) * p0b.x + p0b.y, 0.f), uA1 = fmaxf((xa.y - qa.y + prA1) * p1b.x + p1b.y, 0.f);
+            float uB0 = fmaxf((xb.x - qb.x + prB0) * p0b.x + p0b.y, 0.f), uB1 = fmaxf((xb.y - qb.y + prB1) * p1b.x + p1b.y, 0.f);
+            if (!vA) { uA0 = 0.f; uA1 = 0.f; }
+            if (!vB) { uB0 = 0.f; uB1 = 0.f; }
+            unsigned ah[4], al[4];
+            tg_split(uA0, ah[0], al[0]);      // (row g,   virtual k t)   = channel 8j + 2t
+            tg_split(uB0, ah[1], al[1]);      // (row g+8, virtual k t)
+            tg_split(uA1, ah[2], al[2]);      // (row g,   virtual k t+4) = channel 8j + 2t + 1
+            tg_split(uB1, ah[3], al[3]);      // (row g+8, virtual k t+4)
+#pragma unroll
+            for (int jn = 0; jn < NT; jn++) {
+                const int off = (jn * 8 + g) * LDW + ch;      // B(k, n = g): W3[8 jn + g][channel]
+                unsigned bh0, bh1, bl0, bl1;
+                if (T::PRESPLIT) {
+                    const uint2 h = *reinterpret_cast<const uint2 *>(Wh + off), l = *reinterpret_cast<const uint2 *>(Wl + off);
+                    bh0 = h.x; bh1 = h.y; bl0 = l.x; bl1 = l.y;
+                } else {
+                    const uint2 w = *reinterpret_cast<const uint2 *>(Wh + off);
+                    tg_split(__uint_as_float(w.x), bh0, bl0);
+                    tg_split(__uint_as_float(w.y), bh1, bl1);
+                }
+                tg_mma(acc[jn], al, bh0, bh1);
+                tg_mma(acc[jn], ah, bl0, bl1);
+                tg_mma(acc[jn], ah, bh0, bh1);
+            }
+        }
+#pragma unroll
+        for (int jn = 0; jn < NT; jn++) {
+            const int col = jn * 8 + 2 * t;
+            if (col < CS) {
+                const float oA0 = acc[jn][0] + bias3[jn][0], oA1 = acc[jn][1] + bias3[jn][1];
+                const float oB0 = acc[jn][2] + bias3[jn][0], oB1 = acc[jn][3] + bias3[jn][1];
+                if (vA) {
+                    *reinterpret_cast<float2 *>(w2out + rA * CS + col) = make_float2(oA0, oA1);
+                    t1[jn][0] += oA0; t2[jn][0] += oA0 * oA0; t1[jn][1] += oA1; t2[jn][1] += oA1 * oA1;
+                }
+                if (vB) {
+                    *reinterpret_cast<float2 *>(w2out + rB * CS + col) = make_float2(oB0, oB1);
+                    t1[jn][0] += oB0; t2[jn][0] += oB0 * oB0; t1[jn][1] += oB1; t2[jn][1] += oB1 * oB1;
+                }
+            }
+        }
+    }
+    // BatchNorm statistics of w2: reduce over the 8 row-lanes (g), then block, then global (double)
+#pragma unroll
+    for (int jn = 0; jn < NT; jn++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            float a = t1[jn][e], b = t2[jn][e];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                a += __shfl_xor_sync(CB_FULL_MASK, a, o);
+                b += __shfl_xor_sync(CB_FULL_MASK, b, o);
+            }
+            const int col = jn * 8 + 2 * t + e;
+            if (g == 0 && col < CS) { atomicAdd(&comb[col], a); atomicAdd(&comb[CS + col], b); }
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CS; i += PM_THREADS) atomicAdd(stats + i, (double)comb[i]);
+}
+
+template <int C>
+static void pm_w2_launch(int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
+                         const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3,
+                         const float *b3, float *w2out, double *stats, cudaStream_t st)
+{
+    const size_t smem = PmW2<C>::smem;
+    cudaFuncSetAttribute(k_pt_w2_mma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long tiles = ((long long)n * k + 15) / 16;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (tiles + PM_WARPS - 1) / PM_WARPS;
+    if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
+    if (blocks < 1) blocks = 1;
+    k_pt_w2_mma<C><<<(int)blocks, PM_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats);
+}
+
+// dispatch used by ptlayer_fwd.cu
+void cb_pt_w2_mma(int c, int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
+                  const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3, const float *b3,
+                  float *w2out, double *stats, cudaStream_t st)
+{
+    switch (c) {
+    case 32: pm_w2_launch<32>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
+    case 64: pm_w2_launch<64>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
+    case 128: pm_w2_launch<128>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
+    case 256: pm_w2_launch<256>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
+    case 512: pm_w2_launch<512>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
+    default: break;
+    }
+}

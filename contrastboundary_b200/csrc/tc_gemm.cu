@@ -14,29 +14,12 @@
 // Instruction: mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 (operands staged in shared memory by the
 // block; no tcgen05/TMEM here on purpose: tiles are 128 x {32,64} x 32 and the kernels are bandwidth-bound).
 #include "common.cuh"
+#include "tf32.cuh"
 
 #define TG_BM 128
 #define TG_BK 32
 #define TG_LDS 36          // padded k-stride of the staged tiles: bank = (4*row + k) mod 32 -> conflict-free fragments
 #define TG_THREADS 256
-
-__device__ __forceinline__ unsigned tg_tf32(float x)
-{
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void tg_split(float x, unsigned &hi, unsigned &lo)
-{
-    hi = tg_tf32(x);
-    lo = tg_tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void tg_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 // C[n x N] = A[n x K] * B (+ bias).  TRANS_B: B[k][j] = W[j*ldw + k] (forward), else W[k*ldw + j] (dgrad).
 // Block: 128 rows x BN columns (BN = 32 | 64), 8 warps x 16 rows; blockIdx.y tiles N.  Persistent over row tiles:

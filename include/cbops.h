@@ -287,6 +287,9 @@ int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const 
                          const float *xq, const float *xk, const float *xv, const float *w2buf,
                          const float *abuf, const float *bnbuf, const float *grad_out, float *grad_xq,
                          float *grad_xk, float *grad_xv, float *grad_params, float *scratch, void *stream);
+/* 1 (default): the (n*k) x c x c/8 contraction of the layer (linear_w[2], blocks.py:40) runs on the tensor cores
+ * (mma.sync m16n8k8 TF32 with 3xTF32 error compensation, ptlayer_mma.cu); 0: FP32 SIMT kernels.  Returns the setting. */
+int cb_pt_set_tensor_cores(int on);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,19 @@ def outlier_fraction(a, b, tol):
 @pytest.mark.parametrize("c,k,n_list", [(32, 8, [3000, 2000]), (64, 16, [1500, 900]), (128, 16, [700, 500]),
                                         (256, 16, [300, 200]), (512, 16, [90, 70]), (32, 16, [12, 700])])
 @pytest.mark.parametrize("training", [True, False])
-def test_fused_layer_matches_unfused(c, k, n_list, training):
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_fused_layer_matches_unfused(c, k, n_list, training, tensor_cores):
+    """tensor_cores: the (n*k) x c x c/8 contraction on mma.sync with 3xTF32 (ptlayer_mma.cu) or FP32 SIMT"""
+    import ctypes as C
+    from contrastboundary_b200 import _lib as L
+    L.lib().cb_pt_set_tensor_cores(C.c_int(1 if tensor_cores else 0))
+    try:
+        _fused_layer_case(c, k, n_list, training)
+    finally:
+        L.lib().cb_pt_set_tensor_cores(C.c_int(1))
+
+
+def _fused_layer_case(c, k, n_list, training):
     from contrastboundary_b200 import model
     lv = make_level(n_list, k, 100 + c)
     torch.manual_seed(c + k)
