@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(LG_THREADS) k_skinny_wgrad4(int n, int ci, int
 int cb_tc_enabled();
 void cb_tc_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, cudaStream_t st);
 void cb_tc_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, cudaStream_t st);
-void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, cudaStream_t st);
+void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, const float *xsc,
+                        const float *xsh, cudaStream_t st);
 
 extern "C" int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream)
 {
@@ -262,7 +263,7 @@ extern "C" int cb_linear_wgrad(int n, int ci, int co, const float *X, const floa
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)co, st);
     if (n == 0) return CB_OK;
     if (cb_tc_enabled()) {
-        cb_tc_linear_wgrad(n, ci, co, X, G, dW, db, st);
+        cb_tc_linear_wgrad(n, ci, co, X, G, dW, db, nullptr, nullptr, st);
         CB_COUNT(3);
         CB_CUDA_CHECK("cb_linear_wgrad");
         return CB_OK;

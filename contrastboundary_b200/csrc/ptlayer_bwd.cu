@@ -215,6 +215,32 @@ __device__ __forceinline__ float pt_dw2(float dy3, float w2v, float mean3, float
 }
 
 // ---------------------------------------------------------------------------------------------
+// B4 (tensor-core path): dw2 = BN3'(dy3) materialised as a (rows, CS) matrix — the narrow operand of the two
+// tensor-core GEMMs dW3 = dw2^T relu(bn2(w0)) and dy2 = (dw2 W3) [y2 > 0] (tc_gemm.cu) — and db3 = sum_rows dw2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_THREADS) k_pt_dw2(long long rows, int CS, const float *__restrict__ D,
+                                                       const float *__restrict__ w2buf, const float *__restrict__ bn3,
+                                                       const float *__restrict__ coef3, float *__restrict__ dw2,
+                                                       float *__restrict__ gb3)
+{
+    // thread -> column i = tid % CS (CS divides 256), rows strided
+    const int i = threadIdx.x % CS, rsub = threadIdx.x / CS, RPB = PT_THREADS / CS;
+    const float m3 = bn3[2 * CS + i], i3 = bn3[3 * CS + i], k3 = coef3[i], a3 = coef3[CS + i], b3 = coef3[2 * CS + i];
+    float acc = 0.f;
+    for (long long r = (long long)blockIdx.x * RPB + rsub; r < rows; r += (long long)gridDim.x * RPB) {
+        const float v = pt_dw2(__ldg(D + r * CS + i), __ldg(w2buf + r * CS + i), m3, i3, k3, a3, b3);
+        dw2[r * CS + i] = v;
+        acc += v;
+    }
+    __shared__ float comb[64];
+    if (threadIdx.x < 64) comb[threadIdx.x] = 0.f;
+    __syncthreads();
+    atomicAdd(&comb[i], acc);
+    __syncthreads();
+    if (threadIdx.x < CS) atomicAdd(gb3 + threadIdx.x, comb[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // B4: dW3[i][c] += sum_rows dw2[row,i] * u[row,c] ; sums of dy2 = (W3^T dw2) [y2>0] and dy2*xhat2.
 // Thread (row-in-group, channel): CT = min(C,256) channels per block column, RG = 256/CT rows at once.
 // ---------------------------------------------------------------------------------------------
@@ -346,7 +372,10 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_dw3(int n, int k, int ld,
 // ---------------------------------------------------------------------------------------------
 // B5: main c-space backward (warp per point)
 // ---------------------------------------------------------------------------------------------
-template <int C>
+// STORED: the pre-BatchNorm activation w0 (n,k,C) was kept by the forward pass and dy2 = (W3^T dw2) [y2 > 0] (n,k,C) was
+// produced by the tensor-core GEMM (tc_gemm.cu, fused relu-bn epilogue): the kernel streams both instead of gathering
+// x_k and re-doing the c x c/8 contraction (w0s = w0, dy2s = dy2; w3 / w2buf / D / coef3 / bn3 are then unused).
+template <int C, bool STORED>
 __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld, const float *__restrict__ rel,
                                                             const int *__restrict__ idx, const float *__restrict__ xq,
                                                             const float *__restrict__ xk, const float *__restrict__ w2p,
@@ -359,14 +388,16 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
                                                             const float *__restrict__ G, float *__restrict__ gxq,
                                                             float *__restrict__ gxk, float *__restrict__ gxv,
                                                             float *__restrict__ gW2, float *__restrict__ gb2,
-                                                            float *__restrict__ dy1, double *__restrict__ sums1)
+                                                            float *__restrict__ dy1, double *__restrict__ sums1,
+                                                            const float *__restrict__ w0s, const float *__restrict__ dy2s)
 {
     const PtSmall sp = pt_small_load(smalld);
     using M = PtMap<C>;
     constexpr int VW = M::VW, NS = M::NS, CS = M::CS;
     constexpr int JPL = CS > 32 ? CS / 32 : 1;          // dw2 entries per lane
     extern __shared__ __align__(16) float sm_w3[];     // [CS][C]
-    for (int i = threadIdx.x; i < CS * C; i += PT_THREADS) sm_w3[i] = w3[i];
+    if (!STORED)
+        for (int i = threadIdx.x; i < CS * C; i += PT_THREADS) sm_w3[i] = w3[i];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float wa[NS][VW], wb[NS][VW], wc[NS][VW], bb[NS][VW], sc[NS][VW], sh[NS][VW], mu[NS][VW], iv[NS][VW];
     float k2[NS][VW], ma2[NS][VW], mb2[NS][VW];
@@ -386,7 +417,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
 #pragma unroll
     for (int t = 0; t < JPL; t++) {
         const int i = (lane + 32 * t) % CS;
-        m3[t] = bn3[2 * CS + i]; i3[t] = bn3[3 * CS + i]; k3[t] = coef3[i]; a3[t] = coef3[CS + i]; b3c[t] = coef3[2 * CS + i];
+        m3[t] = 0.f; i3[t] = 0.f; k3[t] = 0.f; a3[t] = 0.f; b3c[t] = 0.f;
+        if (!STORED) { m3[t] = bn3[2 * CS + i]; i3[t] = bn3[3 * CS + i]; k3[t] = coef3[i]; a3[t] = coef3[CS + i]; b3c[t] = coef3[2 * CS + i]; }
     }
     const float mean1[3] = {bn1ms[0], bn1ms[1], bn1ms[2]}, inv1[3] = {bn1ms[3], bn1ms[4], bn1ms[5]};
     float s1a[3] = {0, 0, 0}, s1b[3] = {0, 0, 0};
@@ -396,7 +428,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
         float q[NS][VW], g[NS][VW], dq[NS][VW];
 #pragma unroll
         for (int s = 0; s < NS; s++) {
-            pt_load<VW>(xq + (size_t)pt * ld + M::ch(lane, s, 0), q[s]);
+            if (!STORED) pt_load<VW>(xq + (size_t)pt * ld + M::ch(lane, s, 0), q[s]);
             pt_load<VW>(G + (size_t)pt * C + M::ch(lane, s, 0), g[s]);
 #pragma unroll
             for (int v = 0; v < VW; v++) dq[s][v] = 0.f;
@@ -411,22 +443,28 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
 #pragma unroll
             for (int t = 0; t < JPL; t++) {
                 const int i = (lane + 32 * t) % CS;
-                dw2o[t] = pt_dw2(__ldg(D + row * CS + i), __ldg(w2buf + row * CS + i), m3[t], i3[t], k3[t], a3[t], b3c[t]);
+                dw2o[t] = 0.f;
+                if (!STORED) dw2o[t] = pt_dw2(__ldg(D + row * CS + i), __ldg(w2buf + row * CS + i), m3[t], i3[t], k3[t], a3[t], b3c[t]);
             }
             float dg[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 float x[VW], aw[VW], w0[VW], du[VW];
-                pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
                 pt_load<VW>(abuf + row * CS + (M::ch(lane, s, 0) % CS), aw);
+                if (STORED) {
+                    pt_load<VW>(w0s + row * C + M::ch(lane, s, 0), w0);
+                    pt_load<VW>(dy2s + row * C + M::ch(lane, s, 0), du);      // already masked by [y2 > 0]
+                } else {
+                    pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
 #pragma unroll
-                for (int v = 0; v < VW; v++) {
-                    const float pr = wa[s][v] * g1[0] + wb[s][v] * g1[1] + wc[s][v] * g1[2] + bb[s][v];
-                    w0[v] = x[v] - q[s][v] + pr;
-                    du[v] = 0.f;
+                    for (int v = 0; v < VW; v++) {
+                        const float pr = wa[s][v] * g1[0] + wb[s][v] * g1[1] + wc[s][v] * g1[2] + bb[s][v];
+                        w0[v] = x[v] - q[s][v] + pr;
+                        du[v] = 0.f;
+                    }
                 }
 #pragma unroll
-                for (int i = 0; i < CS; i++) {
+                for (int i = 0; i < (STORED ? 0 : CS); i++) {
                     const float d = __shfl_sync(CB_FULL_MASK, dw2o[i / 32], i % 32);
                     const float *wp = sm_w3 + i * C + M::ch(lane, s, 0);
                     float wv[VW];
@@ -440,7 +478,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
                     const float y2 = w0[v] * sc[s][v] + sh[s][v];
-                    const float dy2 = y2 > 0.f ? du[v] : 0.f;
+                    const float dy2 = (STORED || y2 > 0.f) ? du[v] : 0.f;
                     dw0[v] = k2[s][v] * (dy2 - ma2[s][v] - (w0[v] - mu[s][v]) * iv[s][v] * mb2[s][v]);
                     dval[v] = g[s][v] * aw[v];
                     dq[s][v] -= dw0[v];
@@ -546,13 +584,21 @@ extern "C" size_t cb_pt_bwd_scratch_floats(int n, int k, int c)
     const size_t cs = (size_t)c / 8;
     const size_t dbl = 2 * (2 * cs + 2 * (size_t)c + 6 + 8);          // double region, in floats
     const size_t coef = 3 * cs + 3 * (size_t)c + 9 + 16;
-    return dbl + coef + (size_t)n * k * cs + (size_t)n * k * 3 + 64;
+    // + dw2 (n,k,cs) and dy2 (n,k,c) of the tensor-core path
+    return dbl + coef + (size_t)n * k * cs + (size_t)n * k * 3 + 64 + (size_t)n * k * cs + (size_t)n * k * c + 64;
 }
+
+int cb_pt_mma_enabled();
+void cb_tc_linear_dgrad_relu_bn(int n, int ci, int co, const float *G, const float *W, float *dX, const float *z,
+                                const float *bnp, double *sums, cudaStream_t st);
+void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, const float *xsc,
+                        const float *xsh, cudaStream_t st);
 
 template <int C>
 static int pt_backward_c(int n, int k, int ld, const CbPtLayer *L, const float *rel, const int *idx, const float *xq,
                          const float *xk, const float *xv, const float *w2buf, const float *abuf, const float *bnbuf,
-                         const float *G, float *gxq, float *gxk, float *gxv, float *gbuf, float *scratch, cudaStream_t st)
+                         const float *G, float *gxq, float *gxk, float *gxv, float *gbuf, float *scratch, const float *w0buf,
+                         cudaStream_t st)
 {
     constexpr int CS = C / 8;
     const float *small = bnbuf, *bn1ms = bnbuf + 18, *bn2 = bnbuf + 24, *bn3 = bnbuf + 24 + 4 * C;
@@ -582,7 +628,19 @@ static int pt_backward_c(int n, int k, int ld, const CbPtLayer *L, const float *
         k_pt_bwd_softmax<<<g2, PT_THREADS, smem, st>>>(n, k, CS, w2buf, abuf, bn3, L->w4, D, gW4, gb4, sums3);
     }
     k_pt_bn_coef<<<1, 128, 0, st>>>(sums3, rows, CS, L->bn3_weight, bn3 + 3 * CS, L->training, coef3, gg3, gbe3);
-    {
+    const long long nrows = (long long)n * k;
+    const bool stored = w0buf != nullptr && cb_pt_mma_enabled() && nrows < (1LL << 31);
+    float *DW2 = dy1 + (((size_t)n * k * 3 + 3) & ~(size_t)3) + 16;   // (n,k,CS)   tensor-core path only (16-byte aligned)
+    float *DY2 = DW2 + (size_t)n * k * CS + 16;                      // (n,k,C)
+    if (stored) {
+        // tensor cores (3xTF32): dw2 -> dW3 = dw2^T relu(bn2(w0)) ; dy2 = (dw2 W3) [y2 > 0] with the bn2-backward sums
+        int gd = (int)((nrows * CS + PT_THREADS - 1) / PT_THREADS);
+        if (gd > 148 * 8) gd = 148 * 8;
+        if (gd < 1) gd = 1;
+        k_pt_dw2<<<gd, PT_THREADS, 0, st>>>(nrows, CS, D, w2buf, bn3, coef3, DW2, gb3);
+        cb_tc_linear_wgrad((int)nrows, C, CS, w0buf, DW2, gW3, nullptr, bn2, bn2 + C, st);
+        cb_tc_linear_dgrad_relu_bn((int)nrows, C, CS, DW2, L->w3, DY2, w0buf, bn2, sums2, st);
+    } else {
         constexpr int CT = C < 256 ? C : 256;
         const long long groups = ((long long)n * k + 63) / 64;
         int gx = (int)(groups < 148 * 4 ? (groups < 1 ? 1 : groups) : 148 * 4);
@@ -591,12 +649,16 @@ static int pt_backward_c(int n, int k, int ld, const CbPtLayer *L, const float *
                                                    gW3, gb3, sums2);
     }
     k_pt_bn_coef<<<(C + 127) / 128, 128, 0, st>>>(sums2, rows, C, L->bn2_weight, bn2 + 3 * C, L->training, coef2, gg2, gbe2);
-    {
+    if (stored) {
+        k_pt_bwd_main<C, true><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn1ms, bn2, bn3, coef2,
+                                                            coef3, L->w3, w2buf, abuf, D, G, gxq, gxk, gxv, gW2, gb2, dy1,
+                                                            sums1, w0buf, DY2);
+    } else {
         const size_t smem = (size_t)CS * C * sizeof(float);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_bwd_main<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_pt_bwd_main<C><<<grid, PT_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn1ms, bn2, bn3, coef2,
-                                                         coef3, L->w3, w2buf, abuf, D, G, gxq, gxk, gxv, gW2, gb2, dy1,
-                                                         sums1);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_bwd_main<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_pt_bwd_main<C, false><<<grid, PT_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn1ms, bn2, bn3, coef2,
+                                                                coef3, L->w3, w2buf, abuf, D, G, gxq, gxk, gxv, gW2, gb2, dy1,
+                                                                sums1, nullptr, nullptr);
     }
     k_pt_bn_coef<<<1, 32, 0, st>>>(sums1, rows, 3, L->bn1_weight, bn1ms + 3, L->training, coef1, gg1, gbe1);
     {
@@ -614,7 +676,8 @@ static int pt_backward_c(int n, int k, int ld, const CbPtLayer *L, const float *
 extern "C" int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const int *idx,
                                     const float *xq, const float *xk, const float *xv, const float *w2buf,
                                     const float *abuf, const float *bnbuf, const float *grad_out, float *grad_xq,
-                                    float *grad_xk, float *grad_xv, float *grad_params, float *scratch, void *stream)
+                                    float *grad_xk, float *grad_xv, float *grad_params, float *scratch, const float *w0buf,
+                                    void *stream)
 {
     CB_REQUIRE(n >= 0 && k >= 1 && k <= PT_KMAX, CB_EINVAL, "cb_pt_layer_backward: n=%d k=%d", n, k);
     CB_REQUIRE(L && rel && idx && xq && xk && xv && w2buf && abuf && bnbuf && grad_out && grad_xq && grad_xk && grad_xv &&
@@ -623,7 +686,7 @@ extern "C" int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return CB_OK;
     switch (c) {
-#define PT_CASE(CC) case CC: return pt_backward_c<CC>(n, k, ld, L, rel, idx, xq, xk, xv, w2buf, abuf, bnbuf, grad_out, grad_xq, grad_xk, grad_xv, grad_params, scratch, st);
+#define PT_CASE(CC) case CC: return pt_backward_c<CC>(n, k, ld, L, rel, idx, xq, xk, xv, w2buf, abuf, bnbuf, grad_out, grad_xq, grad_xk, grad_xv, grad_params, scratch, w0buf, st);
         PT_CASE(32) PT_CASE(64) PT_CASE(128) PT_CASE(256) PT_CASE(512)
 #undef PT_CASE
     default:

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, int ld
                                                             const int *__restrict__ idx, const float *__restrict__ xq,
                                                             const float *__restrict__ xk, const float *__restrict__ w2p,
                                                             const float *__restrict__ b2p, const float *__restrict__ smalld,
-                                                            double *__restrict__ stats)
+                                                            double *__restrict__ stats, float *__restrict__ w0out)
 {
     const PtSmall sp = pt_small_load(smalld);
     using M = PtMap<C>;
@@ -165,14 +165,16 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_w0_stats(int n, int k, int ld
             pt_g1(sp, __ldg(rel + 3 * row), __ldg(rel + 3 * row + 1), __ldg(rel + 3 * row + 2), g);
 #pragma unroll
             for (int s = 0; s < NS; s++) {
-                float x[VW];
+                float x[VW], w0v[VW];
                 pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
 #pragma unroll
                 for (int v = 0; v < VW; v++) {
                     const float pr = wa[s][v] * g[0] + wb[s][v] * g[1] + wc[s][v] * g[2] + bb[s][v];
                     const float w0 = x[v] - q[s][v] + pr;
+                    w0v[v] = w0;
                     s1[s][v] += w0; s2[s][v] += w0 * w0;
                 }
+                if (w0out) pt_store<VW>(w0out + row * C + M::ch(lane, s, 0), w0v);   // kept for the backward pass
             }
         }
     }
@@ -445,7 +447,7 @@ void cb_pt_w2_mma(int c, int n, int k, int ld, const float *rel, const int *idx,
 template <int C>
 static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *rel, const double *moments, const int *idx,
                         const float *xq, const float *xk, const float *xv, float *out, float *w2buf, float *abuf,
-                        float *bnbuf, double *stats, cudaStream_t st)
+                        float *bnbuf, double *stats, float *w0buf, cudaStream_t st)
 {
     constexpr int CS = C / 8;
     float *small = bnbuf, *bn2 = bnbuf + 24, *bn3 = bnbuf + 24 + 4 * C;
@@ -457,10 +459,10 @@ static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *r
                                      L->bn1_running_var, L->momentum, L->eps, L->training, bnbuf + 12);
     const int grid = pt_grid(n);
     if (L->training)
-        k_pt_w0_stats<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, stats2);
+        k_pt_w0_stats<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, stats2, w0buf);
     k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(stats2, rows, C, L->bn2_weight, L->bn2_bias, L->bn2_running_mean,
                                                     L->bn2_running_var, L->momentum, L->eps, L->training, bn2);
-    if (cb_pt_mma_enabled() && ld % 2 == 0) {
+    if (cb_pt_mma_enabled() && ld % 4 == 0) {
         // tensor cores (3xTF32), ptlayer_mma.cu
         cb_pt_w2_mma(C, n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3, st);
     } else {
@@ -487,7 +489,7 @@ extern "C" size_t cb_pt_stats_doubles(int c) { return (size_t)(2 * c + 2 * (c / 
 
 extern "C" int cb_pt_layer_forward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const double *moments,
                                    const int *idx, const float *xq, const float *xk, const float *xv, float *out,
-                                   float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream)
+                                   float *w2buf, float *abuf, float *bnbuf, double *stats, float *w0buf, void *stream)
 {
     CB_REQUIRE(n >= 0 && k >= 1 && k <= PT_KMAX, CB_EINVAL, "cb_pt_layer_forward: n=%d k=%d (k <= %d)", n, k, PT_KMAX);
     CB_REQUIRE(ld >= c && ld % 4 == 0, CB_EINVAL, "cb_pt_layer_forward: ld=%d (row stride of x_q/x_k/x_v) must be >= c and a multiple of 4", ld);
@@ -496,11 +498,11 @@ extern "C" int cb_pt_layer_forward(int n, int k, int c, int ld, const CbPtLayer 
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return CB_OK;
     switch (c) {
-    case 32: return pt_forward_c<32>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 64: return pt_forward_c<64>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 128: return pt_forward_c<128>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 256: return pt_forward_c<256>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
-    case 512: return pt_forward_c<512>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, st);
+    case 32: return pt_forward_c<32>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, w0buf, st);
+    case 64: return pt_forward_c<64>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, w0buf, st);
+    case 128: return pt_forward_c<128>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, w0buf, st);
+    case 256: return pt_forward_c<256>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, w0buf, st);
+    case 512: return pt_forward_c<512>(n, k, ld, L, rel, moments, idx, xq, xk, xv, out, w2buf, abuf, bnbuf, stats, w0buf, st);
     default:
         cb_set_error("cb_pt_layer_forward: c=%d unsupported (32,64,128,256,512)", c);
         return CB_EUNSUPPORTED;

@@ -6,8 +6,8 @@
 // tile.  The A operand u = relu(bn2(x_k[idx] - x_q + pr)) never exists in memory: every lane gathers and computes
 // exactly the elements of its A fragment.  The contraction index (channel) is PERMUTED inside each group of 8
 // channels — virtual column t <-> channel 2t, t+4 <-> channel 2t+1 — so that a lane's fragment elements are two
-// adjacent channels of rows g and g+8: one 8-byte gather per row and k-step, and 32 contiguous bytes per row
-// across the four lanes of a quad.  B = W3 is staged once per CTA in shared memory (split into TF32 hi / lo)
+// adjacent channels of rows g and g+8; two k-steps are processed together, so a lane gathers 16 bytes per row and
+// the four lanes of a quad read 64 contiguous bytes of a feature row.  B = W3 is staged once per CTA in shared memory (split into TF32 hi / lo)
 // with the same permutation folded into its indexing.  3xTF32 (tf32.cuh) keeps FP32-level accuracy.
 #include "ptlayer.cuh"
 #include "tf32.cuh"
@@ -43,7 +43,7 @@ template <int C> struct PmW2 {
     static constexpr int CS = C / 8;
     static constexpr int NT = (CS + 7) / 8;          // n-tiles of 8 output columns
     static constexpr int CSP = NT * 8;               // padded output columns (rows of W3 beyond CS are zero)
-    static constexpr int LDW = C + 8;                // row stride of the staged W3: (LDW / 2) mod 16 == 4 -> conflict-free LDS.64
+    static constexpr int LDW = C + 16;               // row stride of the staged W3: (LDW / 4) mod 8 == 4 -> conflict-free LDS.128
     static constexpr bool PRESPLIT = C <= 256;       // hi and lo copies fit in shared memory
     static constexpr size_t smem = (size_t)(PRESPLIT ? 2 : 1) * CSP * LDW * 4 + (size_t)C * 8 * 4 + 2 * CS * 4;
 };
@@ -110,40 +110,52 @@ __global__ void __launch_bounds__(PM_THREADS) k_pt_w2_mma(int n, int k, int ld, 
         float acc[NT][4];
 #pragma unroll
         for (int jn = 0; jn < NT; jn++) acc[jn][0] = acc[jn][1] = acc[jn][2] = acc[jn][3] = 0.f;
-#pragma unroll 2
-        for (int j = 0; j < C / 8; j++) {
-            const int ch = 8 * j + 2 * t;
-            const float2 xa = __ldg(reinterpret_cast<const float2 *>(xkA + ch)), xb = __ldg(reinterpret_cast<const float2 *>(xkB + ch));
-            const float2 qa = __ldg(reinterpret_cast<const float2 *>(xqA + ch)), qb = __ldg(reinterpret_cast<const float2 *>(xqB + ch));
-            const float4 p0 = *reinterpret_cast<const float4 *>(P + ch * 8), p0b = *reinterpret_cast<const float4 *>(P + ch * 8 + 4);
-            const float4 p1 = *reinterpret_cast<const float4 *>(P + ch * 8 + 8), p1b = *reinterpret_cast<const float4 *>(P + ch * 8 + 12);
-            // u = relu(bn2(x_k - x_q + W2 g1 + b2)), same operation order as the SIMT kernels
-            const float prA0 = p0.x * gA[0] + p0.y * gA[1] + p0.z * gA[2] + p0.w, prA1 = p1.x * gA[0] + p1.y * gA[1] + p1.z * gA[2] + p1.w;
-            const float prB0 = p0.x * gB[0] + p0.y * gB[1] + p0.z * gB[2] + p0.w, prB1 = p1.x * gB[0] + p1.y * gB[1] + p1.z * gB[2] + p1.w;
-            float uA0 = fmaxf((xa.x - qa.x + prA0) * p0b.x + p0b.y, 0.f), uA1 = fmaxf((xa.y - qa.y + prA1) * p1b.x + p1b.y, 0.f);
-            float uB0 = fmaxf((xb.x - qb.x + prB0) * p0b.x + p0b.y, 0.f), uB1 = fmaxf((xb.y - qb.y + prB1) * p1b.x + p1b.y, 0.f);
-            if (!vA) { uA0 = 0.f; uA1 = 0.f; }
-            if (!vB) { uB0 = 0.f; uB1 = 0.f; }
-            unsigned ah[4], al[4];
-            tg_split(uA0, ah[0], al[0]);      // (row g,   virtual k t)   = channel 8j + 2t
-            tg_split(uB0, ah[1], al[1]);      // (row g+8, virtual k t)
-            tg_split(uA1, ah[2], al[2]);      // (row g,   virtual k t+4) = channel 8j + 2t + 1
-            tg_split(uB1, ah[3], al[3]);      // (row g+8, virtual k t+4)
+#pragma unroll 1
+        for (int j = 0; j < C / 16; j++) {
+            // 16 channels = two k-steps; this lane owns channels ch .. ch+3 of rows g and g+8
+            const int ch = 16 * j + 4 * t;
+            const float4 xa = __ldg(reinterpret_cast<const float4 *>(xkA + ch)), xb = __ldg(reinterpret_cast<const float4 *>(xkB + ch));
+            const float4 qa = __ldg(reinterpret_cast<const float4 *>(xqA + ch)), qb = __ldg(reinterpret_cast<const float4 *>(xqB + ch));
+            const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+            const float qav[4] = {qa.x, qa.y, qa.z, qa.w}, qbv[4] = {qb.x, qb.y, qb.z, qb.w};
+            float uA[4], uB[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float4 p = *reinterpret_cast<const float4 *>(P + (ch + e) * 8), pb = *reinterpret_cast<const float4 *>(P + (ch + e) * 8 + 4);
+                // u = relu(bn2(x_k - x_q + W2 g1 + b2)), same operation order as the SIMT kernels
+                const float prA = p.x * gA[0] + p.y * gA[1] + p.z * gA[2] + p.w;
+                const float prB = p.x * gB[0] + p.y * gB[1] + p.z * gB[2] + p.w;
+                uA[e] = vA ? fmaxf((xav[e] - qav[e] + prA) * pb.x + pb.y, 0.f) : 0.f;
+                uB[e] = vB ? fmaxf((xbv[e] - qbv[e] + prB) * pb.x + pb.y, 0.f) : 0.f;
+            }
+            unsigned ah[2][4], al[2][4];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                tg_split(uA[2 * s2], ah[s2][0], al[s2][0]);          // (row g,   virtual k t)   = channel ch + 2 s2
+                tg_split(uB[2 * s2], ah[s2][1], al[s2][1]);          // (row g+8, virtual k t)
+                tg_split(uA[2 * s2 + 1], ah[s2][2], al[s2][2]);      // (row g,   virtual k t+4) = channel ch + 2 s2 + 1
+                tg_split(uB[2 * s2 + 1], ah[s2][3], al[s2][3]);      // (row g+8, virtual k t+4)
+            }
 #pragma unroll
             for (int jn = 0; jn < NT; jn++) {
                 const int off = (jn * 8 + g) * LDW + ch;      // B(k, n = g): W3[8 jn + g][channel]
-                unsigned bh0, bh1, bl0, bl1;
+                unsigned bh[4], bl[4];
                 if (T::PRESPLIT) {
-                    const uint2 h = *reinterpret_cast<const uint2 *>(Wh + off), l = *reinterpret_cast<const uint2 *>(Wl + off);
-                    bh0 = h.x; bh1 = h.y; bl0 = l.x; bl1 = l.y;
+                    const uint4 h = *reinterpret_cast<const uint4 *>(Wh + off), l = *reinterpret_cast<const uint4 *>(Wl + off);
+                    bh[0] = h.x; bh[1] = h.y; bh[2] = h.z; bh[3] = h.w; bl[0] = l.x; bl[1] = l.y; bl[2] = l.z; bl[3] = l.w;
                 } else {
-                    const uint2 w = *reinterpret_cast<const uint2 *>(Wh + off);
-                    tg_split(__uint_as_float(w.x), bh0, bl0);
-                    tg_split(__uint_as_float(w.y), bh1, bl1);
+                    const uint4 w = *reinterpret_cast<const uint4 *>(Wh + off);
+                    tg_split(__uint_as_float(w.x), bh[0], bl[0]);
+                    tg_split(__uint_as_float(w.y), bh[1], bl[1]);
+                    tg_split(__uint_as_float(w.z), bh[2], bl[2]);
+                    tg_split(__uint_as_float(w.w), bh[3], bl[3]);
                 }
-                tg_mma(acc[jn], al, bh0, bh1);
-                tg_mma(acc[jn], ah, bl0, bl1);
-                tg_mma(acc[jn], ah, bh0, bh1);
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++) {
+                    tg_mma(acc[jn], al[s2], bh[2 * s2], bh[2 * s2 + 1]);
+                    tg_mma(acc[jn], ah[s2], bl[2 * s2], bl[2 * s2 + 1]);
+                    tg_mma(acc[jn], ah[s2], bh[2 * s2], bh[2 * s2 + 1]);
+                }
             }
         }
 #pragma unroll

@@ -25,10 +25,15 @@
 // Block: 128 rows x BN columns (BN = 32 | 64), 8 warps x 16 rows; blockIdx.y tiles N.  Persistent over row tiles:
 // the A chunk of the NEXT (tile, k-chunk) is prefetched into registers while the current one is multiplied, and
 // the (hi, lo)-split B tile stays resident in shared memory when K <= 32 (the common case: one k-chunk).
-template <int BN, bool TRANS_B>
+// EPI = 1 (backward of relu(bn(.)) fused into the epilogue, used by the PointTransformer layer): with z (n x N) the
+// pre-BatchNorm activation and bnp = [scale | shift | mean | invstd] (N each), C = acc * [z*scale + shift > 0] and the
+// per-column sums of C and of C * xhat (xhat = (z - mean) * invstd) are accumulated into sums[2][N] (double).
+template <int BN, bool TRANS_B, int EPI>
 __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, const float *__restrict__ A,
                                                            const float *__restrict__ W, int ldw,
-                                                           const float *__restrict__ bias, float *__restrict__ C)
+                                                           const float *__restrict__ bias, float *__restrict__ C,
+                                                           const float *__restrict__ z, const float *__restrict__ bnp,
+                                                           double *__restrict__ sums)
 {
     constexpr int NTILE = BN / 8;
     constexpr int APT = (TG_BM * TG_BK / 4) / TG_THREADS;     // float4 of the A chunk per thread (4)
@@ -67,6 +72,21 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
         }
     };
 
+    // EPI == 1: per-column BatchNorm constants and running column sums of this thread's output columns
+    float esc[EPI ? NTILE : 1][2], esh[EPI ? NTILE : 1][2], emu[EPI ? NTILE : 1][2], eiv[EPI ? NTILE : 1][2];
+    float sa[EPI ? NTILE : 1][2], sb[EPI ? NTILE : 1][2];
+    if (EPI == 1) {
+#pragma unroll
+        for (int j = 0; j < NTILE; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int col = col0 + j * 8 + 2 * t + e;
+                const bool ok = col < N;
+                esc[j][e] = ok ? __ldg(bnp + col) : 0.f; esh[j][e] = ok ? __ldg(bnp + N + col) : 0.f;
+                emu[j][e] = ok ? __ldg(bnp + 2 * N + col) : 0.f; eiv[j][e] = ok ? __ldg(bnp + 3 * N + col) : 0.f;
+                sa[j][e] = 0.f; sb[j][e] = 0.f;
+            }
+    }
     float4 pa[APT];
     long long tile = blockIdx.x;
     if (nchunks == 1) stageB(0);
@@ -99,6 +119,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
             }
 #pragma unroll
             for (int ks = 0; ks < TG_BK; ks += 8) {
+                if (chunk * TG_BK + ks >= K) break;          // zero padding beyond K (uniform)
                 unsigned ah[4], al[4];
                 tg_split(As[warp * 16 + g][ks + t], ah[0], al[0]);
                 tg_split(As[warp * 16 + g + 8][ks + t], ah[1], al[1]);
@@ -126,11 +147,46 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
                 const long long row = row0 + warp * 16 + g + 8 * h;
                 if (row >= n) continue;
                 float *dst = C + row * N + col;
-                const float v0 = acc[j][2 * h] + b0, v1 = acc[j][2 * h + 1] + b1;
+                float v0 = acc[j][2 * h] + b0, v1 = acc[j][2 * h + 1] + b1;
+                if (EPI == 1) {
+                    // N is even and col is even: (col, col+1) are both valid or both out of range
+                    if (col < N) {
+                        const float2 zz = __ldg(reinterpret_cast<const float2 *>(z + row * N + col));
+                        v0 = (zz.x * esc[j][0] + esh[j][0] > 0.f) ? v0 : 0.f;
+                        v1 = (zz.y * esc[j][1] + esh[j][1] > 0.f) ? v1 : 0.f;
+                        sa[j][0] += v0; sa[j][1] += v1;
+                        sb[j][0] += v0 * ((zz.x - emu[j][0]) * eiv[j][0]);
+                        sb[j][1] += v1 * ((zz.y - emu[j][1]) * eiv[j][1]);
+                    }
+                }
                 if (col + 1 < N && ((N & 1) == 0)) *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
                 else { if (col < N) dst[0] = v0; if (col + 1 < N) dst[1] = v1; }
             }
         }
+    }
+    if (EPI == 1) {
+        // column sums: reduce over the 8 row-lanes (g) and the 8 warps, then one double atomic per column and block
+        __shared__ float ecomb[2][BN];
+        for (int i = tid; i < 2 * BN; i += TG_THREADS) (&ecomb[0][0])[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NTILE; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                float a = sa[j][e], b = sb[j][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    a += __shfl_xor_sync(CB_FULL_MASK, a, o);
+                    b += __shfl_xor_sync(CB_FULL_MASK, b, o);
+                }
+                if (g == 0) { atomicAdd(&ecomb[0][j * 8 + 2 * t + e], a); atomicAdd(&ecomb[1][j * 8 + 2 * t + e], b); }
+            }
+        __syncthreads();
+        for (int i = tid; i < BN; i += TG_THREADS)
+            if (col0 + i < N) {
+                atomicAdd(sums + col0 + i, (double)ecomb[0][i]);
+                atomicAdd(sums + N + col0 + i, (double)ecomb[1][i]);
+            }
     }
 }
 
@@ -138,9 +194,12 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
 // Block tile 64 (co) x 64 (ci); warps 4 (co) x 2 (ci): each 16 x 32.  blockIdx.y / z tile co / ci, blockIdx.x = row chunk.
 #define TW_T 64
 #define TW_LDS 72          // (72 mod 32) = 8: bank = (8*k + m) mod 32 -> conflict-free fragments
+// xsc / xsh (optional, ci each): the X operand is relu(X * xsc + xsh) — the post-BatchNorm activation recomputed from the
+// stored pre-activation while staging (PointTransformer layer: dW3 = dw2^T relu(bn2(w0))).
 __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, const float *__restrict__ X,
                                                          const float *__restrict__ G, float *__restrict__ dW,
-                                                         float *__restrict__ db, int rows_per_block)
+                                                         float *__restrict__ db, int rows_per_block,
+                                                         const float *__restrict__ xsc, const float *__restrict__ xsh)
 {
     __shared__ __align__(16) float Gs[TG_BK][TW_LDS];
     __shared__ __align__(16) float Xs[TG_BK][TW_LDS];
@@ -168,7 +227,14 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
             px[i] = pg[i];
             if (row < r_end) {
                 if (m0 + q < co) pg[i] = __ldg(reinterpret_cast<const float4 *>(G + row * co + m0 + q));
-                if (n0 + q < ci) px[i] = __ldg(reinterpret_cast<const float4 *>(X + row * ci + n0 + q));
+                if (n0 + q < ci) {
+                    px[i] = __ldg(reinterpret_cast<const float4 *>(X + row * ci + n0 + q));
+                    if (xsc) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4 *>(xsc + n0 + q)), sh = __ldg(reinterpret_cast<const float4 *>(xsh + n0 + q));
+                        px[i].x = fmaxf(px[i].x * sc.x + sh.x, 0.f); px[i].y = fmaxf(px[i].y * sc.y + sh.y, 0.f);
+                        px[i].z = fmaxf(px[i].z * sc.z + sh.z, 0.f); px[i].w = fmaxf(px[i].w * sc.w + sh.w, 0.f);
+                    }
+                }
             }
         }
     };
@@ -187,7 +253,9 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
                 const int r = e >> 6, q = e & 63;
                 const long long row = r0 + r;
                 Gs[r][q] = (row < r_end && m0 + q < co) ? __ldg(G + row * co + m0 + q) : 0.f;
-                Xs[r][q] = (row < r_end && n0 + q < ci) ? __ldg(X + row * ci + n0 + q) : 0.f;
+                float xv = (row < r_end && n0 + q < ci) ? __ldg(X + row * ci + n0 + q) : 0.f;
+                if (xsc && row < r_end && n0 + q < ci) xv = fmaxf(xv * __ldg(xsc + n0 + q) + __ldg(xsh + n0 + q), 0.f);
+                Xs[r][q] = xv;
             }
         }
         __syncthreads();
@@ -234,31 +302,41 @@ static int g_tc_enabled = 1;
 extern "C" int cb_linear_set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; return g_tc_enabled; }
 int cb_tc_enabled() { return g_tc_enabled; }
 
-template <bool TRANS_B>
-static void tc_launch(int n, int K, int N, const float *A, const float *W, int ldw, const float *bias, float *C, cudaStream_t st)
+template <bool TRANS_B, int EPI>
+static void tc_launch(int n, int K, int N, const float *A, const float *W, int ldw, const float *bias, float *C, const float *z,
+                      const float *bnp, double *sums, cudaStream_t st)
 {
     const int ntiles = (n + TG_BM - 1) / TG_BM;
     // column tiles of 64 (or 32 when that wastes fewer padded columns); the A tile of further column tiles comes from L2
     const int w64 = (N + 63) / 64 * 64 - N, w32 = (N + 31) / 32 * 32 - N;
-    const bool use32 = N <= 32 || w32 < w64;
+    // (the fused-epilogue variant keeps per-column constants and sums in registers: 32-wide tiles only; its A operand is
+    //  the narrow (rows x c/8) matrix, so re-reading it per column tile is cheap)
+    const bool use32 = N <= 32 || w32 < w64 || EPI == 1;
     const int gy = use32 ? (N + 31) / 32 : (N + 63) / 64;
     int gx = (148 * 2 + gy - 1) / gy;                        // persistent: ~2 CTAs per SM in total
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
-    if (use32) k_tc_gemm<32, TRANS_B><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
-    else k_tc_gemm<64, TRANS_B><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C);
+    if (use32) k_tc_gemm<32, TRANS_B, EPI><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C, z, bnp, sums);
+    else k_tc_gemm<64, TRANS_B, EPI == 1 ? 0 : EPI><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C, z, bnp, sums);
 }
 
 void cb_tc_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, cudaStream_t st)
 {
-    tc_launch<true>(n, ci, co, X, W, ci, b, Y, st);
+    tc_launch<true, 0>(n, ci, co, X, W, ci, b, Y, nullptr, nullptr, nullptr, st);
 }
 void cb_tc_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, cudaStream_t st)
 {
-    tc_launch<false>(n, co, ci, G, W, ci, nullptr, dX, st);
+    tc_launch<false, 0>(n, co, ci, G, W, ci, nullptr, dX, nullptr, nullptr, nullptr, st);
 }
-// dW and db must be zero-filled by the caller
-void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, cudaStream_t st)
+// dX = (G W) * [z * scale + shift > 0] with the BatchNorm-backward column sums (see k_tc_gemm, EPI = 1); ci must be even
+void cb_tc_linear_dgrad_relu_bn(int n, int ci, int co, const float *G, const float *W, float *dX, const float *z,
+                                const float *bnp, double *sums, cudaStream_t st)
+{
+    tc_launch<false, 1>(n, co, ci, G, W, ci, nullptr, dX, z, bnp, sums, st);
+}
+// dW and db must be zero-filled by the caller; xsc / xsh: optional relu(bn(.)) prologue on X
+void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, const float *xsc,
+                        const float *xsh, cudaStream_t st)
 {
     const int ty = (co + TW_T - 1) / TW_T, tz = (ci + TW_T - 1) / TW_T;
     int blocks = (148 * 2) / (ty * tz);
@@ -266,5 +344,5 @@ void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, f
     int rpb = (n + blocks - 1) / blocks;
     rpb = (rpb + TG_BK - 1) / TG_BK * TG_BK;
     blocks = (n + rpb - 1) / rpb;
-    k_tc_wgrad<<<dim3(blocks, ty, tz), TG_THREADS, 0, st>>>(n, ci, co, X, G, dW, db, rpb);
+    k_tc_wgrad<<<dim3(blocks, ty, tz), TG_THREADS, 0, st>>>(n, ci, co, X, G, dW, db, rpb, xsc, xsh);
 }

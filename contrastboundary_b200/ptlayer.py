@@ -11,6 +11,15 @@ from . import _lib as L
 
 READY = True
 _FP = C.c_void_p
+TENSOR_CORES = True     # the (n*k) x c x c/8 contraction on the tensor cores (3xTF32), forward and backward
+
+
+def set_tensor_cores(flag):
+    """True (default): mma.sync 3xTF32 kernels; the forward keeps w0 (n,k,c) for the backward GEMMs.
+    False: FP32 SIMT kernels that recompute every (n,k,c) quantity from gathers."""
+    global TENSOR_CORES
+    TENSOR_CORES = bool(flag)
+    L.lib().cb_pt_set_tensor_cores(C.c_int(1 if flag else 0))
 
 
 class CbPtLayer(C.Structure):
@@ -55,11 +64,15 @@ class PtAttentionFn(Function):
         bnbuf = torch.empty(lib.cb_pt_bnbuf_floats(C.c_int(c)), dtype=torch.float32, device=dev)
         stats = torch.empty(lib.cb_pt_stats_doubles(C.c_int(c)), dtype=torch.float64, device=dev)
         ps = _param_struct(params, buffers, momentum, eps, training)
+        # tensor-core backward: keep the pre-BatchNorm activation w0 (n,k,c) instead of re-gathering it three times
+        keep_w0 = bool(training) and TENSOR_CORES and any(ctx.needs_input_grad)
+        w0buf = torch.empty((n, k, c), dtype=torch.float32, device=dev) if keep_w0 else None
         rc = lib.cb_pt_layer_forward(C.c_int(n), C.c_int(k), C.c_int(c), C.c_int(ld), C.byref(ps), L.ptr(rel), L.ptr(moments), L.ptr(idx),
                                      L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(out), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf),
-                                     L.ptr(stats), L.stream())
+                                     L.ptr(stats), L.ptr(w0buf), L.stream())
         L.check(rc, "cb_pt_layer_forward")
         ctx.save_for_backward(rel, idx, qkv, w2buf, abuf, bnbuf, *params)
+        ctx.w0buf = w0buf
         ctx.training = training
         return out
 
@@ -85,8 +98,9 @@ class PtAttentionFn(Function):
         ps = _param_struct(params, (params[0],) * 6, 0.0, 0.0, ctx.training)   # running stats unused in backward
         rc = lib.cb_pt_layer_backward(C.c_int(n), C.c_int(k), C.c_int(c), C.c_int(ld), C.byref(ps), L.ptr(rel), L.ptr(idx), L.ptr(xq),
                                       L.ptr(xk), L.ptr(xv), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf), L.ptr(gout),
-                                      L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.stream())
+                                      L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.ptr(ctx.w0buf), L.stream())
         L.check(rc, "cb_pt_layer_backward")
+        ctx.w0buf = None
         PtAttentionFn.debug_last = (scratch, gbuf, bnbuf)
         grads, o = [], 0
         for sz, p in zip(sizes, params):

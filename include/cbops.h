@@ -169,7 +169,9 @@ size_t cb_pt_stats_doubles(int c);
 int cb_pt_rel(int n, int k, const float *p, const int *idx, float *rel, double *moments, void *stream);
 int cb_pt_layer_forward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const double *moments,
                         const int *idx, const float *xq, const float *xk, const float *xv, float *out,
-                        float *w2buf, float *abuf, float *bnbuf, double *stats, void *stream);
+                        float *w2buf, float *abuf, float *bnbuf, double *stats, float *w0buf, void *stream);
+/* w0buf: optional (n,k,c) output (training only): the pre-BatchNorm activation w0 = x_k[idx] - x_q + pr, kept so that
+ * cb_pt_layer_backward can run its two dense contractions as tensor-core GEMMs over streamed operands; NULL = not kept. */
 
 /* ------------------------------------------------------------------------------------------------
  * a12  radius neighbours        replaces batch_nanoflann_neighbors / op BatchOrderedNeighbors
@@ -286,7 +288,9 @@ size_t cb_pt_bwd_scratch_floats(int n, int k, int c);
 int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const float *rel, const int *idx,
                          const float *xq, const float *xk, const float *xv, const float *w2buf,
                          const float *abuf, const float *bnbuf, const float *grad_out, float *grad_xq,
-                         float *grad_xk, float *grad_xv, float *grad_params, float *scratch, void *stream);
+                         float *grad_xk, float *grad_xv, float *grad_params, float *scratch, const float *w0buf,
+                         void *stream);
+/* w0buf: the buffer cb_pt_layer_forward filled, or NULL (FP32 SIMT kernels that re-gather and recompute). */
 /* 1 (default): the (n*k) x c x c/8 contraction of the layer (linear_w[2], blocks.py:40) runs on the tensor cores
  * (mma.sync m16n8k8 TF32 with 3xTF32 error compensation, ptlayer_mma.cu); 0: FP32 SIMT kernels.  Returns the setting. */
 int cb_pt_set_tensor_cores(int on);

@@ -47,13 +47,12 @@ def outlier_fraction(a, b, tol):
 @pytest.mark.parametrize("tensor_cores", [True, False])
 def test_fused_layer_matches_unfused(c, k, n_list, training, tensor_cores):
     """tensor_cores: the (n*k) x c x c/8 contraction on mma.sync with 3xTF32 (ptlayer_mma.cu) or FP32 SIMT"""
-    import ctypes as C
-    from contrastboundary_b200 import _lib as L
-    L.lib().cb_pt_set_tensor_cores(C.c_int(1 if tensor_cores else 0))
+    from contrastboundary_b200 import ptlayer
+    ptlayer.set_tensor_cores(tensor_cores)
     try:
         _fused_layer_case(c, k, n_list, training)
     finally:
-        L.lib().cb_pt_set_tensor_cores(C.c_int(1))
+        ptlayer.set_tensor_cores(True)
 
 
 def _fused_layer_case(c, k, n_list, training):
