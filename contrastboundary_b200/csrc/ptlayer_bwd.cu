@@ -433,11 +433,32 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
 #pragma unroll
             for (int v = 0; v < VW; v++) dq[s][v] = 0.f;
         }
+        // STORED: the streamed operands of row kk+1 are fetched (HBM latency) while row kk is processed
+        float w0n[STORED ? NS : 1][VW], dun[STORED ? NS : 1][VW];
+        if (STORED) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                pt_load<VW>(w0s + (size_t)pt * k * C + M::ch(lane, s, 0), w0n[s]);
+                pt_load<VW>(dy2s + (size_t)pt * k * C + M::ch(lane, s, 0), dun[s]);
+            }
+        }
         for (int kk = 0; kk < k; kk++) {
             const size_t row = (size_t)pt * k + kk;
             const int j = __ldg(idx + row);
             float g1[3], h1[3];
             pt_g1h(sp, __ldg(rel + 3 * row), __ldg(rel + 3 * row + 1), __ldg(rel + 3 * row + 2), g1, h1);
+            float w0c[STORED ? NS : 1][VW], duc[STORED ? NS : 1][VW];
+            if (STORED) {
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+#pragma unroll
+                    for (int v = 0; v < VW; v++) { w0c[s][v] = w0n[s][v]; duc[s][v] = dun[s][v]; }
+                    if (kk + 1 < k) {
+                        pt_load<VW>(w0s + (row + 1) * C + M::ch(lane, s, 0), w0n[s]);
+                        pt_load<VW>(dy2s + (row + 1) * C + M::ch(lane, s, 0), dun[s]);
+                    }
+                }
+            }
             // dw2 entries owned by this lane
             float dw2o[JPL];
 #pragma unroll
@@ -452,8 +473,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt_bwd_main(int n, int k, int ld
                 float x[VW], aw[VW], w0[VW], du[VW];
                 pt_load<VW>(abuf + row * CS + (M::ch(lane, s, 0) % CS), aw);
                 if (STORED) {
-                    pt_load<VW>(w0s + row * C + M::ch(lane, s, 0), w0);
-                    pt_load<VW>(dy2s + row * C + M::ch(lane, s, 0), du);      // already masked by [y2 > 0]
+#pragma unroll
+                    for (int v = 0; v < VW; v++) { w0[v] = w0c[s][v]; du[v] = duc[s][v]; }   // du already masked by [y2 > 0]
                 } else {
                     pt_load<VW>(xk + (size_t)j * ld + M::ch(lane, s, 0), x);
 #pragma unroll

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(PM_THREADS) k_pt_w2_mma(int n, int k, int ld, 
         float acc[NT][4];
 #pragma unroll
         for (int jn = 0; jn < NT; jn++) acc[jn][0] = acc[jn][1] = acc[jn][2] = acc[jn][3] = 0.f;
-#pragma unroll 1
+#pragma unroll 2
         for (int j = 0; j < C / 16; j++) {
             // 16 channels = two k-steps; this lane owns channels ch .. ch+3 of rows g and g+8
             const int ch = 16 * j + 4 * t;

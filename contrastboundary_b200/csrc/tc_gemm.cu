@@ -201,12 +201,15 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
                                                          float *__restrict__ db, int rows_per_block,
                                                          const float *__restrict__ xsc, const float *__restrict__ xsh)
 {
-    __shared__ __align__(16) float Gs[TG_BK][TW_LDS];
-    __shared__ __align__(16) float Xs[TG_BK][TW_LDS];
+    // staged operands, split into TF32 hi / lo once by the staging thread
+    __shared__ __align__(16) unsigned Gh[TG_BK][TW_LDS], Gl[TG_BK][TW_LDS];
+    __shared__ __align__(16) unsigned Xh[TG_BK][TW_LDS], Xl[TG_BK][TW_LDS];
+    __shared__ float dbs[TW_T];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     const int m0 = blockIdx.y * TW_T, n0 = blockIdx.z * TW_T;
+    const bool active = (m0 + wm * 16 < co) && (n0 + wn * 32 < ci);     // warps whose 16 x 32 patch is pure padding idle
     float acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
@@ -214,9 +217,14 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
     const long long r_begin = (long long)blockIdx.x * rows_per_block;
     long long r_end = r_begin + rows_per_block;
     if (r_end > n) r_end = n;
-    const bool vec = (ci % 4 == 0) && (co % 4 == 0) && ((((uintptr_t)X | (uintptr_t)G) & 15) == 0);
+    const bool vec = (ci % 4 == 0) && (co % 4 == 0) && ((((uintptr_t)X | (uintptr_t)G) & 15) == 0) &&
+                     (!xsc || ((((uintptr_t)xsc | (uintptr_t)xsh) & 15) == 0));
     constexpr int WPT = (TG_BK * (TW_T / 4)) / TG_THREADS;       // float4 per thread and matrix (2)
-    float4 pg[WPT], px[WPT];
+    float4 pg[WPT], px[WPT], gsum[WPT];
+#pragma unroll
+    for (int i = 0; i < WPT; i++) gsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < TW_T) dbs[tid] = 0.f;
+    __syncthreads();
     auto prefetch = [&](long long r0) {
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
@@ -238,6 +246,12 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
             }
         }
     };
+    auto put4 = [&](unsigned (*H)[TW_LDS], unsigned (*Lo)[TW_LDS], int r, int q, const float4 &v) {
+        uint4 h, l;
+        tg_split(v.x, h.x, l.x); tg_split(v.y, h.y, l.y); tg_split(v.z, h.z, l.z); tg_split(v.w, h.w, l.w);
+        *reinterpret_cast<uint4 *>(&H[r][q]) = h;
+        *reinterpret_cast<uint4 *>(&Lo[r][q]) = l;
+    };
     if (vec && r_begin < r_end) prefetch(r_begin);
     for (long long r0 = r_begin; r0 < r_end; r0 += TG_BK) {
         // stage 32 rows x 64 columns of G and of X (zero beyond the edges)
@@ -245,57 +259,69 @@ __global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, 
 #pragma unroll
             for (int i = 0; i < WPT; i++) {
                 const int e = tid + i * TG_THREADS;
-                *reinterpret_cast<float4 *>(&Gs[e >> 4][(e & 15) * 4]) = pg[i];
-                *reinterpret_cast<float4 *>(&Xs[e >> 4][(e & 15) * 4]) = px[i];
+                put4(Gh, Gl, e >> 4, (e & 15) * 4, pg[i]);
+                put4(Xh, Xl, e >> 4, (e & 15) * 4, px[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < WPT; i++) {                // column sums of G (a thread's columns are the same in every chunk)
+                gsum[i].x += pg[i].x; gsum[i].y += pg[i].y; gsum[i].z += pg[i].z; gsum[i].w += pg[i].w;
             }
         } else {
             for (int e = tid; e < TG_BK * TW_T; e += TG_THREADS) {
                 const int r = e >> 6, q = e & 63;
                 const long long row = r0 + r;
-                Gs[r][q] = (row < r_end && m0 + q < co) ? __ldg(G + row * co + m0 + q) : 0.f;
+                const float gv = (row < r_end && m0 + q < co) ? __ldg(G + row * co + m0 + q) : 0.f;
                 float xv = (row < r_end && n0 + q < ci) ? __ldg(X + row * ci + n0 + q) : 0.f;
                 if (xsc && row < r_end && n0 + q < ci) xv = fmaxf(xv * __ldg(xsc + n0 + q) + __ldg(xsh + n0 + q), 0.f);
-                Xs[r][q] = xv;
+                tg_split(gv, Gh[r][q], Gl[r][q]);
+                tg_split(xv, Xh[r][q], Xl[r][q]);
+                if (db && blockIdx.z == 0) atomicAdd(&dbs[q], gv);
             }
         }
         __syncthreads();
         if (vec && r0 + TG_BK < r_end) prefetch(r0 + TG_BK);
+        if (active) {
 #pragma unroll
-        for (int ks = 0; ks < TG_BK; ks += 8) {
-            unsigned ah[4], al[4];
-            tg_split(Gs[ks + t][wm * 16 + g], ah[0], al[0]);
-            tg_split(Gs[ks + t][wm * 16 + g + 8], ah[1], al[1]);
-            tg_split(Gs[ks + t + 4][wm * 16 + g], ah[2], al[2]);
-            tg_split(Gs[ks + t + 4][wm * 16 + g + 8], ah[3], al[3]);
+            for (int ks = 0; ks < TG_BK; ks += 8) {
+                const unsigned ah[4] = {Gh[ks + t][wm * 16 + g], Gh[ks + t][wm * 16 + g + 8], Gh[ks + t + 4][wm * 16 + g], Gh[ks + t + 4][wm * 16 + g + 8]};
+                const unsigned al[4] = {Gl[ks + t][wm * 16 + g], Gl[ks + t][wm * 16 + g + 8], Gl[ks + t + 4][wm * 16 + g], Gl[ks + t + 4][wm * 16 + g + 8]};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                unsigned bh0, bl0, bh1, bl1;
-                tg_split(Xs[ks + t][wn * 32 + j * 8 + g], bh0, bl0);
-                tg_split(Xs[ks + t + 4][wn * 32 + j * 8 + g], bh1, bl1);
-                tg_mma(acc[j], al, bh0, bh1);
-                tg_mma(acc[j], ah, bl0, bl1);
-                tg_mma(acc[j], ah, bh0, bh1);
+                for (int j = 0; j < 4; j++) {
+                    const int c = wn * 32 + j * 8 + g;
+                    const unsigned bh0 = Xh[ks + t][c], bh1 = Xh[ks + t + 4][c], bl0 = Xl[ks + t][c], bl1 = Xl[ks + t + 4][c];
+                    tg_mma(acc[j], al, bh0, bh1);
+                    tg_mma(acc[j], ah, bl0, bl1);
+                    tg_mma(acc[j], ah, bh0, bh1);
+                }
             }
-        }
-        if (db && blockIdx.z == 0 && tid < TW_T) {
-            float s = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < TG_BK; r++) s += Gs[r][tid];
-            accb += s;
         }
         __syncthreads();
     }
+    (void)accb;
+    if (db && blockIdx.z == 0) {
+        if (vec) {
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int m = m0 + wm * 16 + g + 8 * h, c = n0 + wn * 32 + j * 8 + 2 * t;
-            if (m < co) {
-                if (c < ci) atomicAdd(dW + (size_t)m * ci + c, acc[j][2 * h]);
-                if (c + 1 < ci) atomicAdd(dW + (size_t)m * ci + c + 1, acc[j][2 * h + 1]);
+            for (int i = 0; i < WPT; i++) {
+                const int q = ((tid + i * TG_THREADS) & 15) * 4;
+                atomicAdd(&dbs[q], gsum[i].x); atomicAdd(&dbs[q + 1], gsum[i].y);
+                atomicAdd(&dbs[q + 2], gsum[i].z); atomicAdd(&dbs[q + 3], gsum[i].w);
             }
         }
-    if (db && blockIdx.z == 0 && tid < TW_T && m0 + tid < co) atomicAdd(db + m0 + tid, accb);
+        __syncthreads();
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int m = m0 + wm * 16 + g + 8 * h, c = n0 + wn * 32 + j * 8 + 2 * t;
+                if (m < co) {
+                    if (c < ci) atomicAdd(dW + (size_t)m * ci + c, acc[j][2 * h]);
+                    if (c + 1 < ci) atomicAdd(dW + (size_t)m * ci + c + 1, acc[j][2 * h + 1]);
+                }
+            }
+    }
+    if (db && blockIdx.z == 0 && tid < TW_T && m0 + tid < co) atomicAdd(db + m0 + tid, dbs[tid]);
 }
 
 static int g_tc_enabled = 1;
