@@ -96,6 +96,19 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
         float acc[NTILE][4];
 #pragma unroll
         for (int j = 0; j < NTILE; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        // EPI == 1: the pre-activation of this thread's outputs, fetched now so that its HBM latency hides under the MMAs
+        float2 zz[EPI ? NTILE : 1][2];
+        if (EPI == 1) {
+#pragma unroll
+            for (int j = 0; j < NTILE; j++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const long long row = row0 + warp * 16 + g + 8 * h;
+                    const int col = col0 + j * 8 + 2 * t;
+                    zz[j][h] = make_float2(0.f, 0.f);
+                    if (row < n && col < N) zz[j][h] = __ldg(reinterpret_cast<const float2 *>(z + row * N + col));
+                }
+        }
         for (int chunk = 0; chunk < nchunks; chunk++) {
             if (vecA) {
 #pragma unroll
@@ -151,12 +164,12 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
                 if (EPI == 1) {
                     // N is even and col is even: (col, col+1) are both valid or both out of range
                     if (col < N) {
-                        const float2 zz = __ldg(reinterpret_cast<const float2 *>(z + row * N + col));
-                        v0 = (zz.x * esc[j][0] + esh[j][0] > 0.f) ? v0 : 0.f;
-                        v1 = (zz.y * esc[j][1] + esh[j][1] > 0.f) ? v1 : 0.f;
+                        const float2 zv = zz[j][h];
+                        v0 = (zv.x * esc[j][0] + esh[j][0] > 0.f) ? v0 : 0.f;
+                        v1 = (zv.y * esc[j][1] + esh[j][1] > 0.f) ? v1 : 0.f;
                         sa[j][0] += v0; sa[j][1] += v1;
-                        sb[j][0] += v0 * ((zz.x - emu[j][0]) * eiv[j][0]);
-                        sb[j][1] += v1 * ((zz.y - emu[j][1]) * eiv[j][1]);
+                        sb[j][0] += v0 * ((zv.x - emu[j][0]) * eiv[j][0]);
+                        sb[j][1] += v1 * ((zv.y - emu[j][1]) * eiv[j][1]);
                     }
                 }
                 if (col + 1 < N && ((N & 1) == 0)) *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
 #define TW_LDS 72          // (72 mod 32) = 8: bank = (8*k + m) mod 32 -> conflict-free fragments
 // xsc / xsh (optional, ci each): the X operand is relu(X * xsc + xsh) — the post-BatchNorm activation recomputed from the
 // stored pre-activation while staging (PointTransformer layer: dW3 = dw2^T relu(bn2(w0))).
-__global__ void __launch_bounds__(TG_THREADS) k_tc_wgrad(int n, int ci, int co, const float *__restrict__ X,
+__global__ void __launch_bounds__(TG_THREADS, 3) k_tc_wgrad(int n, int ci, int co, const float *__restrict__ X,
                                                          const float *__restrict__ G, float *__restrict__ dW,
                                                          float *__restrict__ db, int rows_per_block,
                                                          const float *__restrict__ xsc, const float *__restrict__ xsh)
@@ -365,7 +378,7 @@ void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, f
                         const float *xsh, cudaStream_t st)
 {
     const int ty = (co + TW_T - 1) / TW_T, tz = (ci + TW_T - 1) / TW_T;
-    int blocks = (148 * 2) / (ty * tz);
+    int blocks = (148 * 3) / (ty * tz);                       // 3 CTAs per SM: enough loads in flight for the narrow operands
     if (blocks < 8) blocks = 8;
     int rpb = (n + blocks - 1) / blocks;
     rpb = (rpb + TG_BK - 1) / TG_BK * TG_BK;
