@@ -28,33 +28,59 @@
 // EPI = 1 (backward of relu(bn(.)) fused into the epilogue, used by the PointTransformer layer): with z (n x N) the
 // pre-BatchNorm activation and bnp = [scale | shift | mean | invstd] (N each), C = acc * [z*scale + shift > 0] and the
 // per-column sums of C and of C * xhat (xhat = (z - mean) * invstd) are accumulated into sums[2][N] (double).
+#define TG_STAGES 3
+__device__ __forceinline__ void tg_cp_async16(void *smem, const void *gmem, bool valid)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;                   // 0 source bytes -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+template <int BN> struct TgSmem {
+    static constexpr size_t bytes = (size_t)TG_STAGES * TG_BM * TG_LDS * 4 + (size_t)2 * BN * TG_LDS * 4;
+};
+
 template <int BN, bool TRANS_B, int EPI>
-__global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, const float *__restrict__ A,
+__global__ void __launch_bounds__(TG_THREADS, 3) k_tc_gemm(int n, int K, int N, const float *__restrict__ A,
                                                            const float *__restrict__ W, int ldw,
                                                            const float *__restrict__ bias, float *__restrict__ C,
                                                            const float *__restrict__ z, const float *__restrict__ bnp,
                                                            double *__restrict__ sums)
 {
     constexpr int NTILE = BN / 8;
-    constexpr int APT = (TG_BM * TG_BK / 4) / TG_THREADS;     // float4 of the A chunk per thread (4)
-    __shared__ __align__(16) float As[TG_BM][TG_LDS];
-    __shared__ __align__(16) unsigned Bh[BN][TG_LDS];
-    __shared__ __align__(16) unsigned Bl[BN][TG_LDS];
+    constexpr int APT = (TG_BM * TG_BK / 4) / TG_THREADS;     // 16-byte pieces of an A chunk per thread (4)
+    extern __shared__ __align__(16) unsigned char tg_sm[];
+    float (*As)[TG_BM][TG_LDS] = reinterpret_cast<float (*)[TG_BM][TG_LDS]>(tg_sm);                               // [STAGES]
+    unsigned (*Bh)[TG_LDS] = reinterpret_cast<unsigned (*)[TG_LDS]>(tg_sm + (size_t)TG_STAGES * TG_BM * TG_LDS * 4);   // [BN]
+    unsigned (*Bl)[TG_LDS] = Bh + BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int col0 = blockIdx.y * BN;
     const bool vecA = (K % 4 == 0) && (((uintptr_t)A & 15) == 0);
     const int nchunks = (K + TG_BK - 1) / TG_BK;
     const long long ntiles = ((long long)n + TG_BM - 1) / TG_BM;
+    const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_it = my_tiles * nchunks;
 
-    auto loadA = [&](long long tile, int chunk, float4 (&pa)[APT]) {
+    // stage the A chunk of iteration `it` (row tile it / nchunks of this CTA, k-chunk it % nchunks) into slot it % STAGES
+    auto issueA = [&](long long it) {
+        const long long tile = blockIdx.x + (it / nchunks) * gridDim.x;
+        const int k0 = (int)(it % nchunks) * TG_BK;
+        const int slot = (int)(it % TG_STAGES);
+        if (vecA) {
 #pragma unroll
-        for (int i = 0; i < APT; i++) {
-            const int e = tid + i * TG_THREADS;
-            const int r = e >> 3, kq = (e & 7) * 4;
-            const long long row = tile * TG_BM + r;
-            pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < n && chunk * TG_BK + kq < K) pa[i] = __ldg(reinterpret_cast<const float4 *>(A + row * K + chunk * TG_BK + kq));
+            for (int i = 0; i < APT; i++) {
+                const int e = tid + i * TG_THREADS;
+                const int r = e >> 3, kq = (e & 7) * 4;
+                const long long row = tile * TG_BM + r;
+                const bool ok = row < n && k0 + kq < K;
+                tg_cp_async16(&As[slot][r][kq], ok ? (const void *)(A + row * K + k0 + kq) : (const void *)A, ok);
+            }
+        } else {
+            for (int e = tid; e < TG_BM * TG_BK; e += TG_THREADS) {
+                const int r = e >> 5, kk = e & 31;
+                const long long row = tile * TG_BM + r;
+                As[slot][r][kk] = (row < n && k0 + kk < K) ? __ldg(A + row * K + k0 + kk) : 0.f;
+            }
         }
     };
     auto stageB = [&](int chunk) {
@@ -87,68 +113,60 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
                 sa[j][e] = 0.f; sb[j][e] = 0.f;
             }
     }
-    float4 pa[APT];
-    long long tile = blockIdx.x;
-    if (nchunks == 1) stageB(0);
-    if (vecA && tile < ntiles) loadA(tile, 0, pa);
-    for (; tile < ntiles; tile += gridDim.x) {
+    if (nchunks == 1) stageB(0);                 // resident for the whole kernel (made visible by the first barrier below)
+    for (int c = 0; c < TG_STAGES - 1; c++) {
+        if (c < total_it) issueA(c);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    float acc[NTILE][4];
+    float2 zz[EPI ? NTILE : 1][2];
+    for (long long it = 0; it < total_it; it++) {
+        const long long tile = blockIdx.x + (it / nchunks) * gridDim.x;
+        const int chunk = (int)(it % nchunks);
         const long long row0 = tile * TG_BM;
-        float acc[NTILE][4];
+        if (chunk == 0) {
 #pragma unroll
-        for (int j = 0; j < NTILE; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        // EPI == 1: the pre-activation of this thread's outputs, fetched now so that its HBM latency hides under the MMAs
-        float2 zz[EPI ? NTILE : 1][2];
-        if (EPI == 1) {
+            for (int j = 0; j < NTILE; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+            // EPI == 1: the pre-activation of this thread's outputs, fetched now so that its HBM latency hides under the MMAs
+            if (EPI == 1) {
 #pragma unroll
-            for (int j = 0; j < NTILE; j++)
+                for (int j = 0; j < NTILE; j++)
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const long long row = row0 + warp * 16 + g + 8 * h;
-                    const int col = col0 + j * 8 + 2 * t;
-                    zz[j][h] = make_float2(0.f, 0.f);
-                    if (row < n && col < N) zz[j][h] = __ldg(reinterpret_cast<const float2 *>(z + row * N + col));
-                }
+                    for (int h = 0; h < 2; h++) {
+                        const long long row = row0 + warp * 16 + g + 8 * h;
+                        const int col = col0 + j * 8 + 2 * t;
+                        zz[j][h] = make_float2(0.f, 0.f);
+                        if (row < n && col < N) zz[j][h] = __ldg(reinterpret_cast<const float2 *>(z + row * N + col));
+                    }
+            }
         }
-        for (int chunk = 0; chunk < nchunks; chunk++) {
-            if (vecA) {
-#pragma unroll
-                for (int i = 0; i < APT; i++) {
-                    const int e = tid + i * TG_THREADS;
-                    *reinterpret_cast<float4 *>(&As[e >> 3][(e & 7) * 4]) = pa[i];
-                }
-            } else {
-                const int k0 = chunk * TG_BK;
-                for (int e = tid; e < TG_BM * TG_BK; e += TG_THREADS) {
-                    const int r = e >> 5, kk = e & 31;
-                    const long long row = row0 + r;
-                    As[r][kk] = (row < n && k0 + kk < K) ? __ldg(A + row * K + k0 + kk) : 0.f;
-                }
-            }
-            if (nchunks > 1) stageB(chunk);
-            __syncthreads();
-            if (vecA) {                                      // prefetch the next chunk (of this or of the next tile)
-                if (chunk + 1 < nchunks) loadA(tile, chunk + 1, pa);
-                else if (tile + gridDim.x < ntiles) loadA(tile + gridDim.x, 0, pa);
-            }
-#pragma unroll
-            for (int ks = 0; ks < TG_BK; ks += 8) {
-                if (chunk * TG_BK + ks >= K) break;          // zero padding beyond K (uniform)
-                unsigned ah[4], al[4];
-                tg_split(As[warp * 16 + g][ks + t], ah[0], al[0]);
-                tg_split(As[warp * 16 + g + 8][ks + t], ah[1], al[1]);
-                tg_split(As[warp * 16 + g][ks + t + 4], ah[2], al[2]);
-                tg_split(As[warp * 16 + g + 8][ks + t + 4], ah[3], al[3]);
-#pragma unroll
-                for (int j = 0; j < NTILE; j++) {
-                    const unsigned bh0 = Bh[j * 8 + g][ks + t], bh1 = Bh[j * 8 + g][ks + t + 4];
-                    const unsigned bl0 = Bl[j * 8 + g][ks + t], bl1 = Bl[j * 8 + g][ks + t + 4];
-                    tg_mma(acc[j], al, bh0, bh1);      // small terms first
-                    tg_mma(acc[j], ah, bl0, bl1);
-                    tg_mma(acc[j], ah, bh0, bh1);
-                }
-            }
+        asm volatile("cp.async.wait_group %0;" ::"n"(TG_STAGES - 2) : "memory");     // this iteration's A chunk has landed
+        __syncthreads();                      // ... for every thread; the slot of iteration it-1 (and the B tile) are free again
+        if (it + TG_STAGES - 1 < total_it) issueA(it + TG_STAGES - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (nchunks > 1) {
+            stageB(chunk);
             __syncthreads();
         }
+        const int slot = (int)(it % TG_STAGES);
+#pragma unroll
+        for (int ks = 0; ks < TG_BK; ks += 8) {
+            if (chunk * TG_BK + ks >= K) break;          // zero padding beyond K (uniform)
+            unsigned ah[4], al[4];
+            tg_split(As[slot][warp * 16 + g][ks + t], ah[0], al[0]);
+            tg_split(As[slot][warp * 16 + g + 8][ks + t], ah[1], al[1]);
+            tg_split(As[slot][warp * 16 + g][ks + t + 4], ah[2], al[2]);
+            tg_split(As[slot][warp * 16 + g + 8][ks + t + 4], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < NTILE; j++) {
+                const unsigned bh0 = Bh[j * 8 + g][ks + t], bh1 = Bh[j * 8 + g][ks + t + 4];
+                const unsigned bl0 = Bl[j * 8 + g][ks + t], bl1 = Bl[j * 8 + g][ks + t + 4];
+                tg_mma(acc[j], al, bh0, bh1);      // small terms first
+                tg_mma(acc[j], ah, bl0, bl1);
+                tg_mma(acc[j], ah, bh0, bh1);
+            }
+        }
+        if (chunk != nchunks - 1) continue;
         // ---- epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> row g+8
 #pragma unroll
         for (int j = 0; j < NTILE; j++) {
@@ -177,6 +195,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (EPI == 1) {
         // column sums: reduce over the 8 row-lanes (g) and the 8 warps, then one double atomic per column and block
         __shared__ float ecomb[2][BN];
@@ -208,16 +227,25 @@ __global__ void __launch_bounds__(TG_THREADS, 2) k_tc_gemm(int n, int K, int N, 
 #define TW_T 64
 #define TW_LDS 72          // (72 mod 32) = 8: bank = (8*k + m) mod 32 -> conflict-free fragments
 // xsc / xsh (optional, ci each): the X operand is relu(X * xsc + xsh) — the post-BatchNorm activation recomputed from the
-// stored pre-activation while staging (PointTransformer layer: dW3 = dw2^T relu(bn2(w0))).
-__global__ void __launch_bounds__(TG_THREADS, 3) k_tc_wgrad(int n, int ci, int co, const float *__restrict__ X,
-                                                         const float *__restrict__ G, float *__restrict__ dW,
-                                                         float *__restrict__ db, int rows_per_block,
-                                                         const float *__restrict__ xsc, const float *__restrict__ xsh)
+// stored pre-activation when the fragment is read (PointTransformer layer: dW3 = dw2^T relu(bn2(w0))).
+// The kernel is a pure stream over the rows (0.1-0.7 GFLOP, 40-340 MB): 32-row chunks of G and X are moved by a
+// TW_STAGES-deep cp.async pipeline (raw FP32; the TF32 hi / lo split happens in registers when a fragment is read), so
+// every CTA keeps TW_STAGES - 1 chunks of loads in flight and 3 CTAs per SM cover the HBM latency.
+#define TW_STAGES 4
+__device__ __forceinline__ void tw_cp_async16(void *smem, const void *gmem, bool valid)
 {
-    // staged operands, split into TF32 hi / lo once by the staging thread
-    __shared__ __align__(16) unsigned Gh[TG_BK][TW_LDS], Gl[TG_BK][TW_LDS];
-    __shared__ __align__(16) unsigned Xh[TG_BK][TW_LDS], Xl[TG_BK][TW_LDS];
-    __shared__ float dbs[TW_T];
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;                   // 0 source bytes -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(TG_THREADS, 3) k_tc_wgrad(int n, int ci, int co, const float *__restrict__ X,
+                                                            const float *__restrict__ G, float *__restrict__ dW,
+                                                            float *__restrict__ db, int rows_per_block,
+                                                            const float *__restrict__ xsc, const float *__restrict__ xsh)
+{
+    extern __shared__ __align__(16) float tw_sm[];
+    float (*Gs)[TG_BK][TW_LDS] = reinterpret_cast<float (*)[TG_BK][TW_LDS]>(tw_sm);                              // [STAGES]
+    float (*Xs)[TG_BK][TW_LDS] = reinterpret_cast<float (*)[TG_BK][TW_LDS]>(tw_sm + TW_STAGES * TG_BK * TW_LDS);   // [STAGES]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
@@ -230,98 +258,79 @@ __global__ void __launch_bounds__(TG_THREADS, 3) k_tc_wgrad(int n, int ci, int c
     const long long r_begin = (long long)blockIdx.x * rows_per_block;
     long long r_end = r_begin + rows_per_block;
     if (r_end > n) r_end = n;
-    const bool vec = (ci % 4 == 0) && (co % 4 == 0) && ((((uintptr_t)X | (uintptr_t)G) & 15) == 0) &&
-                     (!xsc || ((((uintptr_t)xsc | (uintptr_t)xsh) & 15) == 0));
-    constexpr int WPT = (TG_BK * (TW_T / 4)) / TG_THREADS;       // float4 per thread and matrix (2)
-    float4 pg[WPT], px[WPT], gsum[WPT];
+    const int nchunks = r_end > r_begin ? (int)((r_end - r_begin + TG_BK - 1) / TG_BK) : 0;
+    const bool vec = (ci % 4 == 0) && (co % 4 == 0) && ((((uintptr_t)X | (uintptr_t)G) & 15) == 0);
+    // relu(bn(.)) prologue constants of this thread's B-fragment columns
+    float psc[4], psh[4];
 #pragma unroll
-    for (int i = 0; i < WPT; i++) gsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < TW_T) dbs[tid] = 0.f;
-    __syncthreads();
-    auto prefetch = [&](long long r0) {
-#pragma unroll
-        for (int i = 0; i < WPT; i++) {
-            const int e = tid + i * TG_THREADS;
-            const int r = e >> 4, q = (e & 15) * 4;
-            const long long row = r0 + r;
-            pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            px[i] = pg[i];
-            if (row < r_end) {
-                if (m0 + q < co) pg[i] = __ldg(reinterpret_cast<const float4 *>(G + row * co + m0 + q));
-                if (n0 + q < ci) {
-                    px[i] = __ldg(reinterpret_cast<const float4 *>(X + row * ci + n0 + q));
-                    if (xsc) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4 *>(xsc + n0 + q)), sh = __ldg(reinterpret_cast<const float4 *>(xsh + n0 + q));
-                        px[i].x = fmaxf(px[i].x * sc.x + sh.x, 0.f); px[i].y = fmaxf(px[i].y * sc.y + sh.y, 0.f);
-                        px[i].z = fmaxf(px[i].z * sc.z + sh.z, 0.f); px[i].w = fmaxf(px[i].w * sc.w + sh.w, 0.f);
-                    }
-                }
-            }
-        }
-    };
-    auto put4 = [&](unsigned (*H)[TW_LDS], unsigned (*Lo)[TW_LDS], int r, int q, const float4 &v) {
-        uint4 h, l;
-        tg_split(v.x, h.x, l.x); tg_split(v.y, h.y, l.y); tg_split(v.z, h.z, l.z); tg_split(v.w, h.w, l.w);
-        *reinterpret_cast<uint4 *>(&H[r][q]) = h;
-        *reinterpret_cast<uint4 *>(&Lo[r][q]) = l;
-    };
-    if (vec && r_begin < r_end) prefetch(r_begin);
-    for (long long r0 = r_begin; r0 < r_end; r0 += TG_BK) {
-        // stage 32 rows x 64 columns of G and of X (zero beyond the edges)
+    for (int j = 0; j < 4; j++) {
+        const int c = n0 + wn * 32 + j * 8 + g;
+        psc[j] = (xsc && c < ci) ? __ldg(xsc + c) : 1.f;
+        psh[j] = (xsc && c < ci) ? __ldg(xsh + c) : 0.f;
+    }
+    auto issue = [&](int chunk) {                       // stage chunk -> slot chunk % TW_STAGES (zero beyond the edges)
+        const int slot = chunk % TW_STAGES;
+        const long long r0 = r_begin + (long long)chunk * TG_BK;
         if (vec) {
 #pragma unroll
-            for (int i = 0; i < WPT; i++) {
+            for (int i = 0; i < (TG_BK * (TW_T / 4)) / TG_THREADS; i++) {
                 const int e = tid + i * TG_THREADS;
-                put4(Gh, Gl, e >> 4, (e & 15) * 4, pg[i]);
-                put4(Xh, Xl, e >> 4, (e & 15) * 4, px[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < WPT; i++) {                // column sums of G (a thread's columns are the same in every chunk)
-                gsum[i].x += pg[i].x; gsum[i].y += pg[i].y; gsum[i].z += pg[i].z; gsum[i].w += pg[i].w;
+                const int r = e >> 4, q = (e & 15) * 4;
+                const long long row = r0 + r;
+                const bool okg = row < r_end && m0 + q < co, okx = row < r_end && n0 + q < ci;
+                tw_cp_async16(&Gs[slot][r][q], okg ? (const void *)(G + row * co + m0 + q) : (const void *)G, okg);
+                tw_cp_async16(&Xs[slot][r][q], okx ? (const void *)(X + row * ci + n0 + q) : (const void *)X, okx);
             }
         } else {
             for (int e = tid; e < TG_BK * TW_T; e += TG_THREADS) {
                 const int r = e >> 6, q = e & 63;
                 const long long row = r0 + r;
-                const float gv = (row < r_end && m0 + q < co) ? __ldg(G + row * co + m0 + q) : 0.f;
-                float xv = (row < r_end && n0 + q < ci) ? __ldg(X + row * ci + n0 + q) : 0.f;
-                if (xsc && row < r_end && n0 + q < ci) xv = fmaxf(xv * __ldg(xsc + n0 + q) + __ldg(xsh + n0 + q), 0.f);
-                tg_split(gv, Gh[r][q], Gl[r][q]);
-                tg_split(xv, Xh[r][q], Xl[r][q]);
-                if (db && blockIdx.z == 0) atomicAdd(&dbs[q], gv);
+                Gs[slot][r][q] = (row < r_end && m0 + q < co) ? __ldg(G + row * co + m0 + q) : 0.f;
+                Xs[slot][r][q] = (row < r_end && n0 + q < ci) ? __ldg(X + row * ci + n0 + q) : 0.f;
             }
         }
-        __syncthreads();
-        if (vec && r0 + TG_BK < r_end) prefetch(r0 + TG_BK);
+    };
+    // prologue: TW_STAGES - 1 chunks in flight (one commit group per chunk, empty groups keep the count uniform)
+    for (int c = 0; c < TW_STAGES - 1; c++) {
+        if (c < nchunks) issue(c);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(TW_STAGES - 2) : "memory");     // chunk's group has landed
+        __syncthreads();                                 // ... for every thread, and slot (chunk-1) % STAGES is free again
+        if (chunk + TW_STAGES - 1 < nchunks) issue(chunk + TW_STAGES - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int slot = chunk % TW_STAGES;
         if (active) {
 #pragma unroll
             for (int ks = 0; ks < TG_BK; ks += 8) {
-                const unsigned ah[4] = {Gh[ks + t][wm * 16 + g], Gh[ks + t][wm * 16 + g + 8], Gh[ks + t + 4][wm * 16 + g], Gh[ks + t + 4][wm * 16 + g + 8]};
-                const unsigned al[4] = {Gl[ks + t][wm * 16 + g], Gl[ks + t][wm * 16 + g + 8], Gl[ks + t + 4][wm * 16 + g], Gl[ks + t + 4][wm * 16 + g + 8]};
+                unsigned ah[4], al[4];
+                tg_split(Gs[slot][ks + t][wm * 16 + g], ah[0], al[0]);
+                tg_split(Gs[slot][ks + t][wm * 16 + g + 8], ah[1], al[1]);
+                tg_split(Gs[slot][ks + t + 4][wm * 16 + g], ah[2], al[2]);
+                tg_split(Gs[slot][ks + t + 4][wm * 16 + g + 8], ah[3], al[3]);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int c = wn * 32 + j * 8 + g;
-                    const unsigned bh0 = Xh[ks + t][c], bh1 = Xh[ks + t + 4][c], bl0 = Xl[ks + t][c], bl1 = Xl[ks + t + 4][c];
+                    float x0 = Xs[slot][ks + t][c], x1 = Xs[slot][ks + t + 4][c];
+                    if (xsc) { x0 = fmaxf(x0 * psc[j] + psh[j], 0.f); x1 = fmaxf(x1 * psc[j] + psh[j], 0.f); }
+                    unsigned bh0, bl0, bh1, bl1;
+                    tg_split(x0, bh0, bl0);
+                    tg_split(x1, bh1, bl1);
                     tg_mma(acc[j], al, bh0, bh1);
                     tg_mma(acc[j], ah, bl0, bl1);
                     tg_mma(acc[j], ah, bh0, bh1);
                 }
             }
         }
-        __syncthreads();
-    }
-    (void)accb;
-    if (db && blockIdx.z == 0) {
-        if (vec) {
-#pragma unroll
-            for (int i = 0; i < WPT; i++) {
-                const int q = ((tid + i * TG_THREADS) & 15) * 4;
-                atomicAdd(&dbs[q], gsum[i].x); atomicAdd(&dbs[q + 1], gsum[i].y);
-                atomicAdd(&dbs[q + 2], gsum[i].z); atomicAdd(&dbs[q + 3], gsum[i].w);
-            }
+        if (db && blockIdx.z == 0 && tid < TW_T) {
+            float s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < TG_BK; r++) s2 += Gs[slot][r][tid];
+            accb += s2;
         }
-        __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (active) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -334,7 +343,7 @@ __global__ void __launch_bounds__(TG_THREADS, 3) k_tc_wgrad(int n, int ci, int c
                 }
             }
     }
-    if (db && blockIdx.z == 0 && tid < TW_T && m0 + tid < co) atomicAdd(db + m0 + tid, dbs[tid]);
+    if (db && blockIdx.z == 0 && tid < TW_T && m0 + tid < co) atomicAdd(db + m0 + tid, accb);
 }
 
 static int g_tc_enabled = 1;
@@ -355,8 +364,18 @@ static void tc_launch(int n, int K, int N, const float *A, const float *W, int l
     int gx = (148 * 2 + gy - 1) / gy;                        // persistent: ~2 CTAs per SM in total
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
-    if (use32) k_tc_gemm<32, TRANS_B, EPI><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C, z, bnp, sums);
-    else k_tc_gemm<64, TRANS_B, EPI == 1 ? 0 : EPI><<<dim3(gx, gy), TG_THREADS, 0, st>>>(n, K, N, A, W, ldw, bias, C, z, bnp, sums);
+    int gx3 = (148 * 3 + gy - 1) / gy;                       // persistent: ~3 CTAs per SM in total
+    if (gx3 > ntiles) gx3 = ntiles;
+    if (gx3 < 1) gx3 = 1;
+    if (use32) {
+        static bool set32 = false;
+        if (!set32) { cudaFuncSetAttribute(k_tc_gemm<32, TRANS_B, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TgSmem<32>::bytes); set32 = true; }
+        k_tc_gemm<32, TRANS_B, EPI><<<dim3(gx3, gy), TG_THREADS, TgSmem<32>::bytes, st>>>(n, K, N, A, W, ldw, bias, C, z, bnp, sums);
+    } else {
+        static bool set64 = false;
+        if (!set64) { cudaFuncSetAttribute(k_tc_gemm<64, TRANS_B, EPI == 1 ? 0 : EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TgSmem<64>::bytes); set64 = true; }
+        k_tc_gemm<64, TRANS_B, EPI == 1 ? 0 : EPI><<<dim3(gx3, gy), TG_THREADS, TgSmem<64>::bytes, st>>>(n, K, N, A, W, ldw, bias, C, z, bnp, sums);
+    }
 }
 
 void cb_tc_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, cudaStream_t st)
@@ -383,5 +402,11 @@ void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, f
     int rpb = (n + blocks - 1) / blocks;
     rpb = (rpb + TG_BK - 1) / TG_BK * TG_BK;
     blocks = (n + rpb - 1) / rpb;
-    k_tc_wgrad<<<dim3(blocks, ty, tz), TG_THREADS, 0, st>>>(n, ci, co, X, G, dW, db, rpb, xsc, xsh);
+    const size_t smem = (size_t)2 * TW_STAGES * TG_BK * TW_LDS * sizeof(float);     // 73.7 KB: three CTAs per SM
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_tc_wgrad<<<dim3(blocks, ty, tz), TG_THREADS, smem, st>>>(n, ci, co, X, G, dW, db, rpb, xsc, xsh);
 }

@@ -8,7 +8,7 @@ from torch.autograd import Function
 
 from . import _lib as L
 
-MIN_ROWS = 512         # below this cuBLAS is fine (launch latency dominates anyway)
+MIN_ROWS = 8192        # below this cuBLAS is fine (and launch latency dominates anyway; measured: 512 is slower)
 MAX_CO = 512
 MAX_WGRAD = 16384      # ci*co handled by the SIMT wgrad kernel (the tensor-core kernel has no limit)
 TENSOR_CORES = True    # 3xTF32 tensor-core kernels (tc_gemm.cu); False = FP32 SIMT kernels (linear_ops.cu)
