@@ -67,3 +67,36 @@ def fast_linear(x, weight, bias=None):
 class Linear(nn.Linear):
     def forward(self, x):
         return fast_linear(x, self.weight, self.bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm1d with a deferred batch counter.  nn.BatchNorm1d increments `num_batches_tracked` with one tiny
+# kernel per layer and forward (123 of them per step of this network).  This subclass (same parameters, buffers
+# and state_dict) queues the counters instead; `flush_bn_counters()` bumps all of them with ONE multi-tensor op.
+# The counter only matters for momentum=None (cumulative average), which the reference never uses
+# (pytorch/model/blocks.py: nn.BatchNorm1d defaults, momentum 0.1).
+# ------------------------------------------------------------------------------------------------
+_bn_pending = []
+
+
+def bump_bn_counter(bn):
+    if bn.num_batches_tracked is not None:
+        _bn_pending.append(bn.num_batches_tracked)
+        if len(_bn_pending) >= 1024:          # stand-alone use of the layers (no network forward to flush them)
+            flush_bn_counters()
+
+
+def flush_bn_counters():
+    if _bn_pending:
+        torch._foreach_add_(list(_bn_pending), 1)
+        _bn_pending.clear()
+
+
+class BatchNorm1d(nn.BatchNorm1d):
+    def forward(self, x):
+        if self.momentum is None or not self.track_running_stats or not x.is_cuda:
+            return super().forward(x)
+        if self.training:
+            bump_bn_counter(self)
+        return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training,
+                            self.momentum, self.eps)

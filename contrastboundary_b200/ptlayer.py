@@ -8,6 +8,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib as L
+from .linear_ops import bump_bn_counter
 
 READY = True
 _FP = C.c_void_p
@@ -118,7 +119,7 @@ def pt_attention(layer, lv, qkv):
     training = layer.training
     if training:
         for bn in (lp[1], lw[0], lw[3]):
-            bn.num_batches_tracked += 1
+            bump_bn_counter(bn)
     return PtAttentionFn.apply(lv.rel, lv.rel_mom, lv.knn, qkv, buffers, lp[1].momentum, lp[1].eps,
                                training, *params)
 
@@ -175,7 +176,7 @@ def transition_down(td, x, prev_level, level):
     z = fast_linear(x, w[:, 3:].contiguous())
     bn = td.bn
     if td.training:
-        bn.num_batches_tracked += 1
+        bump_bn_counter(bn)
     return TransitionDownFn.apply(level.rel_down, level.down_idx, z, w[:, :3], bn.weight, bn.bias, bn.running_mean,
                                   bn.running_var, bn.momentum, bn.eps, td.training)
 
