@@ -100,3 +100,61 @@ class BatchNorm1d(nn.BatchNorm1d):
             bump_bn_counter(self)
         return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training,
                             self.momentum, self.eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused BatchNorm (+ residual) (+ ReLU): libcbops' cb_bn_act_forward / cb_bn_act_backward (bn_ops.cu)
+# ------------------------------------------------------------------------------------------------
+FUSED_BN = True
+
+
+class _BnActFn(Function):
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, momentum, eps, training, relu):
+        import ctypes as C
+        x = x.contiguous()
+        n, c = x.shape
+        y = torch.empty_like(x)
+        bnbuf = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        stats = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        res = residual.contiguous() if residual is not None else None
+        rc = L.lib().cb_bn_act_forward(C.c_longlong(n), C.c_int(c), L.ptr(x), L.ptr(res), L.ptr(gamma), L.ptr(beta),
+                                       L.ptr(running_mean), L.ptr(running_var), C.c_float(momentum), C.c_float(eps),
+                                       C.c_int(1 if training else 0), C.c_int(1 if relu else 0), L.ptr(y), L.ptr(bnbuf),
+                                       L.ptr(stats), L.stream())
+        L.check(rc, "cb_bn_act_forward")
+        ctx.save_for_backward(x, y, gamma, bnbuf)
+        ctx.cfg = (bool(training), bool(relu), residual is not None, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes as C
+        x, y, gamma, bnbuf = ctx.saved_tensors
+        training, relu, has_res, stats = ctx.cfg
+        n, c = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gres = torch.empty_like(x) if has_res else None
+        gg = torch.empty(c, dtype=torch.float32, device=x.device)
+        gb = torch.empty(c, dtype=torch.float32, device=x.device)
+        rc = L.lib().cb_bn_act_backward(C.c_longlong(n), C.c_int(c), L.ptr(x), L.ptr(y), L.ptr(gamma), L.ptr(bnbuf),
+                                        C.c_int(1 if training else 0), C.c_int(1 if relu else 0), L.ptr(gy), L.ptr(gx),
+                                        L.ptr(gres), L.ptr(gg), L.ptr(gb), L.ptr(stats), L.stream())
+        L.check(rc, "cb_bn_act_backward")
+        return gx, gres, gg, gb, None, None, None, None, None, None
+
+
+def bn_act(bn, x, residual=None, relu=True):
+    """act(bn(x) [+ residual]) for a BatchNorm1d module `bn` on an (n, c) tensor: the reference's
+    relu(bn(.)) / relu(bn3(.) + identity) patterns (blocks.py:76,127-133) in two kernels per direction."""
+    if (FUSED_BN and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
+            and bn.track_running_stats and bn.momentum is not None and bn.affine and x.shape[0] > 0):
+        if bn.training:
+            bump_bn_counter(bn)
+        return _BnActFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum),
+                              float(bn.eps), bn.training, relu)
+    y = bn(x)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointops
-from .linear_ops import BatchNorm1d, Linear, flush_bn_counters
+from .linear_ops import BatchNorm1d, Linear, bn_act, flush_bn_counters
 
 
 @dataclass
@@ -201,6 +201,14 @@ def _bn_rows(bn: nn.BatchNorm1d, x):
     return bn(x.reshape(-1, shp[-1])).view(shp)
 
 
+def _seq_bn_act(seq, x):
+    """forward of an nn.Sequential(Linear, BatchNorm1d, ReLU) (the module keeps the reference's structure and
+    state_dict names) through the fused BatchNorm+ReLU kernel"""
+    if len(seq) == 3 and isinstance(seq[1], nn.BatchNorm1d) and isinstance(seq[2], nn.ReLU):
+        return bn_act(seq[1], seq[0](x))
+    return seq(x)
+
+
 class PointTransformerLayer(nn.Module):
     """blocks.py:14-44"""
 
@@ -261,7 +269,7 @@ class TransitionDown(nn.Module):
 
     def forward(self, x, prev_level=None, level=None):
         if self.stride == 1:
-            return F.relu(self.bn(self.linear(x)))
+            return bn_act(self.bn, self.linear(x))
         if self.fused and level.rel_down is not None and self.linear.weight.shape[0] in (32, 64, 128, 256, 512):
             from . import ptlayer
             return ptlayer.transition_down(self, x, prev_level, level)
@@ -291,9 +299,9 @@ class TransitionUp(nn.Module):
             cnt = torch.cat([o[:1], o[1:] - o[:-1]]).to(x1.dtype).unsqueeze(1)       # device-side, no host sync
             mean = torch.zeros(b, x1.shape[1], dtype=x1.dtype, device=x1.device).index_add_(0, level1.scene_id, x1) / cnt
             g = self.linear2(mean)[level1.scene_id]
-            return self.linear1(torch.cat((x1, g), 1))
-        up = pointops._InterpolationFn.apply(self.linear2(x2), level1.up_idx, level1.up_w)
-        return self.linear1(x1) + up
+            return _seq_bn_act(self.linear1, torch.cat((x1, g), 1))
+        up = pointops._InterpolationFn.apply(_seq_bn_act(self.linear2, x2), level1.up_idx, level1.up_w)
+        return _seq_bn_act(self.linear1, x1) + up
 
 
 class PointTransformerBlock(nn.Module):
@@ -311,10 +319,9 @@ class PointTransformerBlock(nn.Module):
 
     def forward(self, lv, x):
         identity = x
-        x = F.relu(self.bn1(self.linear1(x)))
-        x = F.relu(self.bn2(self.transformer2(lv, x)))
-        x = self.bn3(self.linear3(x))
-        return F.relu(x + identity)
+        x = bn_act(self.bn1, self.linear1(x))
+        x = bn_act(self.bn2, self.transformer2(lv, x))
+        return bn_act(self.bn3, self.linear3(x), residual=identity)      # relu(bn3(linear3(x)) + identity)
 
 
 class _LatentMLP(nn.Module):
@@ -325,7 +332,7 @@ class _LatentMLP(nn.Module):
         self.infer = nn.Sequential(Linear(fdim, d_out), BatchNorm1d(d_out), nn.ReLU(inplace=True))
 
     def forward(self, x):
-        return self.infer(x)
+        return _seq_bn_act(self.infer, x)
 
 
 class MultiHead(nn.Module):

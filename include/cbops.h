@@ -275,6 +275,19 @@ int cb_td_backward(int m, int k, int c, const float *rel, const int *idx, const 
 int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream);
 int cb_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, void *stream);
 int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, void *stream);
+/* fused BatchNorm1d (+ residual) (+ ReLU) over an (n, c) matrix — relu(bn(linear(x))) and relu(bn3(.) + identity) of
+ * PointTransformerBlock / TransitionDown / TransitionUp / the head MLPs (pytorch/model/blocks.py:76,104-108,125-133).
+ * forward: y = act((x - mean) * invstd * gamma + beta [+ residual]); training: batch statistics (biased variance), running
+ * statistics updated with the unbiased one (nn.BatchNorm1d semantics); bnbuf (4c floats: scale, shift, mean, invstd) and
+ * stats (2c doubles, scratch) are caller-allocated; bnbuf is kept for the backward.
+ * backward: grad_x, grad_residual (optional, = grad_y masked by the ReLU), grad_gamma, grad_beta; sums: 2c doubles scratch. */
+int cb_bn_act_forward(long long n, int c, const float *x, const float *residual, const float *gamma, const float *beta,
+                      float *running_mean, float *running_var, float momentum, float eps, int training, int relu, float *y,
+                      float *bnbuf, double *stats, void *stream);
+int cb_bn_act_backward(long long n, int c, const float *x, const float *y, const float *gamma, const float *bnbuf, int training,
+                       int relu, const float *grad_y, float *grad_x, float *grad_residual, float *grad_gamma, float *grad_beta,
+                       double *sums, void *stream);
+
 /* 1 (default): the three calls above run on the tensor cores with 3xTF32 error compensation (hi/lo operand split,
  * FP32 accumulate; tc_gemm.cu) and are HBM-bound; 0: exact-FP32 SIMT kernels (and the ci*co <= 16384 limit of the SIMT
  * wgrad).  Returns the setting in force. */

@@ -167,3 +167,39 @@ def test_fused_transition_down(c_in, c_out, n_list, training):
     assert rel_err(a[2], r[2]) < 2e-2 and rel_err(a[3], r[3]) < 2e-2 and rel_err(a[4], r[4]) < 2e-2
     if training:
         assert rel_err(a[5], r[5]) < 1e-4 and rel_err(a[6], r[6]) < 1e-4
+
+
+@pytest.mark.parametrize("n,c", [(163840, 32), (40960, 64), (2560, 256), (640, 512), (7, 32)])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("residual,relu", [(False, True), (True, True), (False, False)])
+def test_fused_bn_act(n, c, training, residual, relu):
+    """fused BatchNorm (+ residual) (+ ReLU) kernels vs torch.nn.BatchNorm1d + add + relu (blocks.py:127-133)"""
+    from contrastboundary_b200 import linear_ops
+    torch.manual_seed(c + n % 13)
+    x0 = torch.randn(n, c, device="cuda") * 1.7 + 0.3
+    r0 = torch.randn(n, c, device="cuda") if residual else None
+    g = torch.randn(n, c, device="cuda")
+    res = {}
+    for fused in (False, True):
+        bn = linear_ops.BatchNorm1d(c).cuda()
+        with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, c)); bn.bias.copy_(torch.linspace(-0.2, 0.2, c))
+            bn.running_mean.fill_(0.1); bn.running_var.fill_(1.2)
+        bn.train(training)
+        x = x0.clone().requires_grad_(True)
+        r = r0.clone().requires_grad_(True) if residual else None
+        linear_ops.FUSED_BN = fused
+        try:
+            y = linear_ops.bn_act(bn, x, residual=r, relu=relu)
+            y.backward(g)
+        finally:
+            linear_ops.FUSED_BN = True
+        res[fused] = (y.detach(), x.grad.clone(), r.grad.clone() if residual else None, bn.weight.grad.clone(), bn.bias.grad.clone(),
+                      bn.running_mean.clone(), bn.running_var.clone())
+    a, b = res[False], res[True]
+    assert rel_err(b[0], a[0]) < 2e-5
+    assert rel_err(b[1], a[1]) < 2e-4
+    if residual:
+        assert torch.equal(b[2], a[2])
+    assert rel_err(b[3], a[3]) < 2e-4 and rel_err(b[4], a[4]) < 2e-4
+    assert rel_err(b[5], a[5]) < 1e-5 and rel_err(b[6], a[6]) < 1e-5
