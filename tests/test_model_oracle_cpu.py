@@ -43,6 +43,7 @@ def test_oracle_model_matches_real_reference(golden_dir):
             continue
         assert abs(float(params[name].grad.norm()) - ref) <= 1e-4 * max(ref, 1e-6) + 1e-7, name
     for name in cases.GOLDEN_GRADS:
-        assert np.allclose(params[name].grad.numpy(), g["grad/" + name], rtol=1e-4, atol=1e-6), name
+        # atol: torch-CPU reductions change their summation order with the thread count of the process (flaky at 1e-6)
+        assert np.allclose(params[name].grad.numpy(), g["grad/" + name], rtol=1e-4, atol=2e-5), name
     for i in range(5):
         assert np.allclose(up[i]["latent"].detach().numpy()[:64], g[f"latent/{i}"], rtol=1e-5, atol=1e-5)
