@@ -8,7 +8,9 @@ from torch.autograd import Function
 
 from . import _lib as L
 
-MIN_ROWS = 8192        # below this cuBLAS is fine (and launch latency dominates anyway; measured: 512 is slower)
+MIN_ROWS = 8192        # forward / dgrad: below this cuBLAS wins (measured: 2048 and 512 are slower; the deep levels have
+                       # K, N up to 512-768, where re-staging the split weight tile per k-chunk dominates the custom kernel)
+MIN_ROWS_WGRAD = 8192  # wgrad: with few rows the split-K atomics of the custom kernels cost more than cuBLAS' single pass
 MAX_CO = 512
 MAX_WGRAD = 16384      # ci*co handled by the SIMT wgrad kernel (the tensor-core kernel has no limit)
 TENSOR_CORES = True    # 3xTF32 tensor-core kernels (tc_gemm.cu); False = FP32 SIMT kernels (linear_ops.cu)
@@ -43,7 +45,7 @@ class _SkinnyLinearFn(Function):
             gx = torch.empty_like(x)
             L.call("cb_linear_dgrad", n, ci, co, g, weight, gx, L.stream())
         if ctx.needs_input_grad[1]:
-            if TENSOR_CORES or (ci * co <= MAX_WGRAD and co <= 256):
+            if n >= MIN_ROWS_WGRAD and (TENSOR_CORES or (ci * co <= MAX_WGRAD and co <= 256)):
                 gw = torch.empty_like(weight)
                 gb = torch.empty(co, dtype=torch.float32, device=x.device) if ctx.has_bias else None
                 L.call("cb_linear_wgrad", n, ci, co, x, g, gw, gb, L.stream())
