@@ -125,7 +125,7 @@ class GraphTrainStep(TrainStep):
     """TrainStep whose step() replays captured CUDA graphs.  Same numerics (the captured work IS TrainStep's
     work); falls back to TrainStep's stream mode for batch signatures it could not capture."""
 
-    def __init__(self, cfg: CBLConfig = None, device="cuda", ddp=False, eager_warmup=2, max_signatures=2, **kw):
+    def __init__(self, cfg: CBLConfig = None, device="cuda", ddp=False, eager_warmup=2, max_signatures=2, net_priority=False, **kw):
         # data parallel here = one all-reduce of the packed gradient after the graph; no DDP wrapper
         super().__init__(cfg, device, ddp=False, **kw)
         import torch.distributed as dist
@@ -143,6 +143,9 @@ class GraphTrainStep(TrainStep):
         self.launches_per_step = None
         self.graph_error = None
         self._packed = False       # True while every p.grad is a view of self.flat
+        # optional (measured: no effect on this workload): capture / replay the network graph on a HIGH-priority stream,
+        # so that the concurrently replaying geometry graph of the next batch only fills the SMs the network leaves idle
+        self.hp = torch.cuda.Stream(device=self.device, priority=-1) if net_priority else None
 
     # -- eager (stream-mode) step that also averages gradients across ranks -----------------------------
     def _set_packed(self, flag):
@@ -243,7 +246,7 @@ class GraphTrainStep(TrainStep):
                 for p in params:
                     p.grad = None
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self._net_pool):
+                with torch.cuda.graph(g, pool=self._net_pool, **({"stream": self.hp} if self.hp is not None else {})):
                     out, stages = self.model(sl.inputs, sl.levels)
                     loss = self.criterion(out, sl.inputs["point_labels"], stages)
                     loss.sum().backward()
@@ -312,7 +315,13 @@ class GraphTrainStep(TrainStep):
             self._launch_geo(other)
         main = torch.cuda.current_stream(self.device)
         main.wait_event(cur.ev_geo)
-        cur.net.replay()
+        if self.hp is not None:
+            self.hp.wait_stream(main)
+            with torch.cuda.stream(self.hp):
+                cur.net.replay()
+            main.wait_stream(self.hp)
+        else:
+            cur.net.replay()
         cur.holds = None
         if self.world > 1:
             import torch.distributed as dist
