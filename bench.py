@@ -168,6 +168,7 @@ def roofline_knn_gather(torch, dev):
     off = torch.tensor([n], dtype=torch.int32, device=dev)
     feat = torch.randn(n, c, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_r = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
     grid = fused.grid_build(xyz, off, k)
     out = fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off)
     st = torch.cuda.current_stream()
@@ -177,7 +178,9 @@ def roofline_knn_gather(torch, dev):
             fn()
         ts = []
         for _ in range(iters):
-            flush.zero_()                      # L2 flush between timed iterations
+            flush.zero_()                      # L2 flush between timed iterations: write 256 MiB (> 126 MB L2) ...
+            flush_r.sum()                      # ... then read 256 MiB, so that the L2 holds CLEAN foreign lines: the timed
+                                               # kernel is not charged for writing back the flush's dirty lines
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(st)
             fn()
@@ -207,7 +210,7 @@ def roofline_knn_gather(torch, dev):
             "whole_operator": {"what": "cb_knn_gather incl. grid build (11 small kernels)", "us": t_call * 1e6,
                                "achieved": alg / t_call / 1e9, "frac": alg / t_call / 1e9 / peak},
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)" if peaks else "fallback 6650 (B200_PROFILING.md)",
-            "l2": "256 MiB buffer zeroed between timed iterations"}
+            "l2": "between timed iterations a 256 MiB buffer is zeroed and another 256 MiB buffer is read (L2 left full of clean foreign lines)"}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -137,3 +137,49 @@ def test_tf_contrast_loss_matches_restatement():
             res.append((float(loss), f2.grad))
         assert abs(res[1][0] - res[0][0]) <= 1e-5 * abs(res[0][0])
         assert float((res[1][1] - res[0][1]).abs().max()) <= 1e-4 * float(res[0][1].abs().max())
+
+
+def test_segmentation_inputs_radius_pyramid():
+    """the whole 5-level input pyramid (datasets/base.py:767-842) built on the device vs the same
+    composition of the CPU oracle operators, level by level"""
+    from contrastboundary_b200 import tf_pyramid
+    p2 = cases.tf_config1()[0][:3000]
+    pts = np.concatenate([cases.tf_sphere()[0], p2], 0)
+    lens = np.array([15000, 3000], np.int32)
+    labels = (np.arange(len(pts)) % 13).astype(np.int64)
+    cfg = tf_pyramid.PyramidConfig()
+    out = tf_pyramid.segmentation_inputs_radius(pts, pts.copy(), labels, lens, cfg)
+    dl, r = cfg.first_subsampling_dl, cfg.first_subsampling_dl * cfg.density_parameter / 2
+    cp, cl = pts, lens
+    for lvl in range(cfg.num_layers):
+        lim = cfg.neighborhood_limits[lvl]
+        assert np.array_equal(out["points"][lvl].cpu().numpy(), cp), f"points lvl {lvl}"
+        assert np.array_equal(out["batches_len"][lvl].cpu().numpy(), cl)
+        nb = oracle.batch_neighbors(cp, cp, cl, cl, r)[:, :lim]
+        assert rows_equal_mod_ties(_pad_cols(out["neighbors"][lvl].cpu().numpy(), nb.shape[1]), nb, cp, cp), f"neighbors lvl {lvl}"
+        if lvl == cfg.num_layers - 1:
+            assert out["pools"][lvl].shape == (0, 1)
+            break
+        pp, pl = oracle.batch_grid_subsampling(cp, cl, 2 * dl)
+        pools = oracle.batch_neighbors(pp, cp, pl, cl, r)[:, :lim]
+        ups = oracle.batch_neighbors(cp, pp, cl, pl, 2 * r)[:, :lim]
+        assert rows_equal_mod_ties(_pad_cols(out["pools"][lvl].cpu().numpy(), pools.shape[1]), pools, pp, cp), f"pools lvl {lvl}"
+        assert rows_equal_mod_ties(_pad_cols(out["upsamples"][lvl + 1].cpu().numpy(), ups.shape[1]), ups, cp, pp), f"ups lvl {lvl}"
+        cp, cl, dl, r = pp, pl, dl * 2, r * 2
+    assert out["upsamples"][0].shape == (0, 1)
+    # batch weights and the stacked batch index matrices (base.py:776-779, 694-737)
+    w = out["batch_weights"].cpu().numpy()
+    assert np.allclose(w[:15000], 3000 / 15000) and np.allclose(w[15000:], 1.0)
+    ib = out["in_batches"].cpu().numpy()
+    assert ib.shape == (2, 15000) and ib[0, -1] == 14999 and ib[1, 2999] == 17999 and ib[1, 3000] == 18000
+    eq = tf_pyramid.stack_batch_inds(torch.tensor([3, 3], dtype=torch.int32, device="cuda")).cpu().numpy()
+    assert np.array_equal(eq, np.array([[0, 1, 2, 6], [3, 4, 5, 6]], np.int32))      # extra shadow column when no row is padded
+
+
+def _pad_cols(a, width):
+    """the fused crop returns exactly `limit` columns; the oracle's matrix is narrower when no row has that many
+    neighbours — the extra columns must then be pure shadow padding"""
+    if a.shape[1] <= width:
+        return a
+    assert (a[:, width:] == a.max()).all()
+    return a[:, :width]
