@@ -226,3 +226,44 @@ extern "C" int cb_cbl_backward_ex(int m, int K, int D, const float *feat, const 
     CB_CUDA_CHECK("cb_cbl_backward");
     return CB_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// SURVEY 8(f) row 3 — test-time boundary / plain masks (pytorch/model/basic_operators.py:69-97, used by
+// pytorch/tool/test.py:392-428 on full-resolution rooms with kr in {16, 32, 64}).
+//   valid neighbour = neighbour label >= 0;  bound_cnt = #{valid neighbours with a different label};
+//   bound = bound_cnt > 0;  plain = every neighbour is invalid or carries the centre's label;  both & valid_mask.
+// One thread per point; the reference materialises the (n, kr) gathered-label matrix three times.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_boundary_mask(long long n, int kr, const long long *__restrict__ labels, const int *__restrict__ idx,
+                                const unsigned char *__restrict__ valid, int *__restrict__ bound_cnt,
+                                unsigned char *__restrict__ bound, unsigned char *__restrict__ plain)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long li = labels[i];
+    int cnt = 0;
+    bool all_eq = true;
+    for (int t = 0; t < kr; t++) {
+        const long long lj = labels[__ldg(idx + i * kr + t)];
+        const bool vn = lj >= 0;
+        if (vn && lj != li) { cnt++; all_eq = false; }
+    }
+    const bool v = valid ? valid[i] != 0 : true;
+    if (bound_cnt) bound_cnt[i] = v ? cnt : 0;
+    if (bound) bound[i] = (v && cnt > 0) ? 1 : 0;
+    if (plain) plain[i] = (v && all_eq) ? 1 : 0;
+}
+
+extern "C" int cb_boundary_mask(long long n, int kr, const long long *labels, const int *neighbor_idx,
+                                const unsigned char *valid_mask, int *bound_cnt, unsigned char *bound, unsigned char *plain,
+                                void *stream)
+{
+    CB_REQUIRE(n >= 0 && kr >= 1 && labels && neighbor_idx, CB_EINVAL, "cb_boundary_mask: bad arguments");
+    if (n == 0) return CB_OK;
+    k_boundary_mask<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, kr, labels, neighbor_idx, valid_mask,
+                                                                                  bound_cnt, bound, plain);
+    CB_COUNT(1);
+    CB_CUDA_CHECK("cb_boundary_mask");
+    return CB_OK;
+}

@@ -222,6 +222,11 @@ int cb_grid_subsample_permute(int ncells, int fdim, const int *perm, const float
  *   idx (m,K) int32 with column 0 = the point itself (dropped as heads.py:196); d in {32,64,72}; K <= 65.
  * cb_cbl_backward: grad_feat (m,d), zero-filled by the caller, += scale[0] * d(sum loss_i)/d feat.
  * ---------------------------------------------------------------------------------------------- */
+/* test-time boundary / plain masks of get_boundary_mask (pytorch/model/basic_operators.py:69-97; tool/test.py:392-428):
+ * labels (n) int64 (negative = invalid), neighbor_idx (n,kr) int32, valid_mask (n) bytes or NULL; any output may be NULL.
+ * bound_cnt[i] = #valid neighbours with another label, bound = cnt > 0, plain = all neighbours invalid-or-equal (& valid). */
+int cb_boundary_mask(long long n, int kr, const long long *labels, const int *neighbor_idx, const unsigned char *valid_mask,
+                     int *bound_cnt, unsigned char *bound, unsigned char *plain, void *stream);
 int cb_cbl_classes(int m, int kr, int ncls, const int *label_idx, const long long *target, int *cls, void *stream);
 int cb_cbl_forward(int m, int K, int D, const float *feat, const int *idx, const int *cls, float temperature,
                    float *sums, void *stream);

@@ -173,3 +173,18 @@ def test_product_has_no_cpu_fallback():
     off = torch.tensor([10], dtype=torch.int32)
     with pytest.raises(_lib.CbopsError):
         pointops.knnquery(3, xyz, xyz, off, off)
+
+
+def test_boundary_mask_oracle_matches_real_reference(golden_dir):
+    """oracle/boundary.py vs goldens produced by the reference's own get_boundary_mask (basic_operators.py:69-97)"""
+    from oracle import boundary
+    g = np.load(os.path.join(golden_dir, "boundary_ref.npz"))
+    for case in range(3):
+        lab, idx = g[f"{case}/labels"], g[f"{case}/idx"]
+        valid = lab >= 0
+        b, p = boundary.get_boundary_mask(lab, idx, get_plain=True)
+        assert np.array_equal(b, g[f"{case}/bound"]) and np.array_equal(p, g[f"{case}/plain"])
+        bv, pv = boundary.get_boundary_mask(lab, idx, valid_mask=valid, get_plain=True)
+        assert np.array_equal(bv, g[f"{case}/bound_valid"]) and np.array_equal(pv, g[f"{case}/plain_valid"])
+        c = boundary.get_boundary_mask(lab, idx, valid_mask=valid, get_cnt=True)
+        assert np.array_equal(c, g[f"{case}/cnt"])
