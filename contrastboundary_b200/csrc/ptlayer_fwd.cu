@@ -442,7 +442,7 @@ extern "C" int cb_pt_rel(int n, int k, const float *p, const int *idx, float *re
 int cb_pt_mma_enabled();
 void cb_pt_w2_mma(int c, int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
                   const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3, const float *b3,
-                  float *w2out, double *stats, cudaStream_t st);
+                  float *w2out, double *stats, const float *w0, cudaStream_t st);
 
 template <int C>
 static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *rel, const double *moments, const int *idx,
@@ -464,7 +464,8 @@ static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *r
                                                     L->bn2_running_var, L->momentum, L->eps, L->training, bn2);
     if (cb_pt_mma_enabled() && ld % 4 == 0) {
         // tensor cores (3xTF32), ptlayer_mma.cu
-        cb_pt_w2_mma(C, n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3, st);
+        cb_pt_w2_mma(C, n, k, ld, rel, idx, xq, xk, L->w2, L->b2, small, bn2, L->w3, L->b3, w2buf, stats3,
+                     L->training ? w0buf : nullptr, st);
     } else {
         const size_t smem = (size_t)CS * C * sizeof(float);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pt_w2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(PM_THREADS) k_pt_w2_mma(int n, int k, int ld, 
                                                           const float *__restrict__ bn2 /* [4][C] */,
                                                           const float *__restrict__ w3 /* [CS][C] */,
                                                           const float *__restrict__ b3, float *__restrict__ w2out,
-                                                          double *__restrict__ stats /* [2][CS] */)
+                                                          double *__restrict__ stats /* [2][CS] */,
+                                                          const float *__restrict__ w0 /* (n,k,C) or NULL */)
 {
     using T = PmW2<C>;
     constexpr int CS = T::CS, NT = T::NT, CSP = T::CSP, LDW = T::LDW;
@@ -114,19 +115,31 @@ __global__ void __launch_bounds__(PM_THREADS) k_pt_w2_mma(int n, int k, int ld, 
         for (int j = 0; j < C / 16; j++) {
             // 16 channels = two k-steps; this lane owns channels ch .. ch+3 of rows g and g+8
             const int ch = 16 * j + 4 * t;
-            const float4 xa = __ldg(reinterpret_cast<const float4 *>(xkA + ch)), xb = __ldg(reinterpret_cast<const float4 *>(xkB + ch));
-            const float4 qa = __ldg(reinterpret_cast<const float4 *>(xqA + ch)), qb = __ldg(reinterpret_cast<const float4 *>(xqB + ch));
-            const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
-            const float qav[4] = {qa.x, qa.y, qa.z, qa.w}, qbv[4] = {qb.x, qb.y, qb.z, qb.w};
             float uA[4], uB[4];
+            if (w0) {
+                // training: w0 was materialised by the statistics pass (it is kept for the backward) — stream it
+                const float4 wa4 = __ldg(reinterpret_cast<const float4 *>(w0 + ra * C + ch)), wb4 = __ldg(reinterpret_cast<const float4 *>(w0 + rb * C + ch));
+                const float wav[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wbv[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float4 p = *reinterpret_cast<const float4 *>(P + (ch + e) * 8), pb = *reinterpret_cast<const float4 *>(P + (ch + e) * 8 + 4);
-                // u = relu(bn2(x_k - x_q + W2 g1 + b2)), same operation order as the SIMT kernels
-                const float prA = p.x * gA[0] + p.y * gA[1] + p.z * gA[2] + p.w;
-                const float prB = p.x * gB[0] + p.y * gB[1] + p.z * gB[2] + p.w;
-                uA[e] = vA ? fmaxf((xav[e] - qav[e] + prA) * pb.x + pb.y, 0.f) : 0.f;
-                uB[e] = vB ? fmaxf((xbv[e] - qbv[e] + prB) * pb.x + pb.y, 0.f) : 0.f;
+                for (int e = 0; e < 4; e++) {
+                    const float2 pb = *reinterpret_cast<const float2 *>(P + (ch + e) * 8 + 4);
+                    uA[e] = vA ? fmaxf(wav[e] * pb.x + pb.y, 0.f) : 0.f;
+                    uB[e] = vB ? fmaxf(wbv[e] * pb.x + pb.y, 0.f) : 0.f;
+                }
+            } else {
+                const float4 xa = __ldg(reinterpret_cast<const float4 *>(xkA + ch)), xb = __ldg(reinterpret_cast<const float4 *>(xkB + ch));
+                const float4 qa = __ldg(reinterpret_cast<const float4 *>(xqA + ch)), qb = __ldg(reinterpret_cast<const float4 *>(xqB + ch));
+                const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+                const float qav[4] = {qa.x, qa.y, qa.z, qa.w}, qbv[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float4 p = *reinterpret_cast<const float4 *>(P + (ch + e) * 8), pb = *reinterpret_cast<const float4 *>(P + (ch + e) * 8 + 4);
+                    // u = relu(bn2(x_k - x_q + W2 g1 + b2)), same operation order as the SIMT kernels
+                    const float prA = p.x * gA[0] + p.y * gA[1] + p.z * gA[2] + p.w;
+                    const float prB = p.x * gB[0] + p.y * gB[1] + p.z * gB[2] + p.w;
+                    uA[e] = vA ? fmaxf((xav[e] - qav[e] + prA) * pb.x + pb.y, 0.f) : 0.f;
+                    uB[e] = vB ? fmaxf((xbv[e] - qbv[e] + prB) * pb.x + pb.y, 0.f) : 0.f;
+                }
             }
             unsigned ah[2][4], al[2][4];
 #pragma unroll
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(PM_THREADS) k_pt_w2_mma(int n, int k, int ld, 
 template <int C>
 static void pm_w2_launch(int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
                          const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3,
-                         const float *b3, float *w2out, double *stats, cudaStream_t st)
+                         const float *b3, float *w2out, double *stats, const float *w0, cudaStream_t st)
 {
     const size_t smem = PmW2<C>::smem;
     cudaFuncSetAttribute(k_pt_w2_mma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -207,20 +220,20 @@ static void pm_w2_launch(int n, int k, int ld, const float *rel, const int *idx,
     long long blocks = (tiles + PM_WARPS - 1) / PM_WARPS;
     if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
     if (blocks < 1) blocks = 1;
-    k_pt_w2_mma<C><<<(int)blocks, PM_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats);
+    k_pt_w2_mma<C><<<(int)blocks, PM_THREADS, smem, st>>>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, w0);
 }
 
 // dispatch used by ptlayer_fwd.cu
 void cb_pt_w2_mma(int c, int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
                   const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3, const float *b3,
-                  float *w2out, double *stats, cudaStream_t st)
+                  float *w2out, double *stats, const float *w0, cudaStream_t st)
 {
     switch (c) {
-    case 32: pm_w2_launch<32>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
-    case 64: pm_w2_launch<64>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
-    case 128: pm_w2_launch<128>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
-    case 256: pm_w2_launch<256>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
-    case 512: pm_w2_launch<512>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, st); break;
+    case 32: pm_w2_launch<32>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, w0, st); break;
+    case 64: pm_w2_launch<64>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, w0, st); break;
+    case 128: pm_w2_launch<128>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, w0, st); break;
+    case 256: pm_w2_launch<256>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, w0, st); break;
+    case 512: pm_w2_launch<512>(n, k, ld, rel, idx, xq, xk, w2p, b2p, smalld, bn2, w3, b3, w2out, stats, w0, st); break;
     default: break;
     }
 }
