@@ -313,6 +313,172 @@ __global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-copy-warp variant (mode 5).  ncu on the variant above: 37 % of the executed instructions are the search warps
+// spinning on a FULL queue — the single copy warp, which alternates blocking waits for loads (mbarrier) and for
+// stores (bulk wait_group.read), is the bottleneck, not the search.  Here the copy role is split into a LOADER warp
+// (pops queue items, waits for a free slab on its `empty` mbarrier, issues the row loads) and a STORER warp (waits for
+// a slab's `full` mbarrier, issues the bulk store, releases the slab of the previous store once its shared-memory
+// read has finished), so loads are never held up behind a draining store; 6 warps search.
+// ---------------------------------------------------------------------------------------------
+#define KGW2_SEARCH 6
+
+__device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int KPL, int NS>
+__global__ void __launch_bounds__(256, 4) k_knn_gather_ws2(int m, int K, int c, int R, int slab_bytes,
+                                                        const float *__restrict__ new_xyz, const float *__restrict__ feat,
+                                                        const int *__restrict__ new_offset, int b, int self_query,
+                                                        const CbScene *__restrict__ scenes, const int *__restrict__ cells,
+                                                        const float4 *__restrict__ sorted, int *__restrict__ idx,
+                                                        float *__restrict__ dist2, float *__restrict__ grouped,
+                                                        CbGridHeader *hdr, int *flagged)
+{
+    extern __shared__ __align__(128) unsigned char kg_smem[];
+    __shared__ CbWarpScratch scratch[KGW2_SEARCH];
+    __shared__ __align__(8) unsigned long long full_bar[NS], empty_bar[NS];
+    __shared__ int q_entry[KGW_QN][1 + 32 * KPL];
+    __shared__ volatile int q_seq[KGW_QN];
+    __shared__ int q_tail;
+    __shared__ volatile int q_head;
+    __shared__ volatile int producers_done;
+    __shared__ volatile int total_chunks;          // -1 until the loader has issued its last chunk
+    __shared__ int ch_q[NS], ch_e0[NS], ch_rows[NS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x < KGW_QN) q_seq[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        q_tail = 0; q_head = 0; producers_done = 0; total_chunks = -1;
+        for (int s = 0; s < NS; s++) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned row_bytes = (unsigned)c * 4u;
+    const unsigned slab0 = smem_u32(kg_smem);
+    const int nchunks = (K + R - 1) / R;
+    if (wib < KGW2_SEARCH) {
+        // ------------------------------ search warps ------------------------------
+        const int stride = gridDim.x * KGW2_SEARCH;
+        for (int w = blockIdx.x * KGW2_SEARCH + wib; w < m; w += stride) {
+            int q = w;
+            float qx, qy, qz;
+            if (self_query) {
+                const float4 p = __ldg(sorted + w);
+                q = __float_as_int(p.w); qx = p.x; qy = p.y; qz = p.z;
+            } else {
+                qx = __ldg(new_xyz + 3 * q); qy = __ldg(new_xyz + 3 * q + 1); qz = __ldg(new_xyz + 3 * q + 2);
+            }
+            const int s = cb_scene_of(q, new_offset, b);
+            const CbScene sc = scenes[s];
+            typename CbTopKSel<KPL>::type tk;
+            tk.init(K, lane, sc.start);
+            bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+            if (ok && tk.has_tie()) ok = false;
+            if (!ok) {
+                if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const int e = j * 32 + lane;
+                if (e < K) {
+                    idx[(size_t)q * K + e] = tk.out_i(j);
+                    dist2[(size_t)q * K + e] = tk.out_d(j);
+                }
+            }
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(&q_tail, 1);
+                while (t - q_head >= KGW_QN) { }            // queue full: wait for the loader
+            }
+            t = __shfl_sync(CB_FULL_MASK, t, 0);
+            const int slot = t % KGW_QN;
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const int e = j * 32 + lane;
+                if (e < K) q_entry[slot][1 + e] = tk.out_i(j);
+            }
+            if (lane == 0) q_entry[slot][0] = q;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) q_seq[slot] = t + 1;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd((int *)&producers_done, 1); }
+    } else if (wib == KGW2_SEARCH) {
+        // ------------------------------ loader warp ------------------------------
+        int item = 0, g = 0;
+        for (;;) {
+            const int slot = item % KGW_QN;
+            if (q_seq[slot] != item + 1) {                   // nothing published yet
+                if (producers_done == KGW2_SEARCH) {
+                    __threadfence_block();
+                    if (item >= *((volatile int *)&q_tail) && q_seq[slot] != item + 1) break;
+                }
+                continue;
+            }
+            __threadfence_block();
+            for (int ci = 0; ci < nchunks; ci++, g++) {
+                const int sl = g % NS;
+                if (g >= NS) mbar_wait(smem_u32(&empty_bar[sl]), (unsigned)((g / NS - 1) & 1));   // slab released by the storer
+                const int e0 = ci * R;
+                const int rows = min(R, K - e0);
+                const unsigned bar = smem_u32(&full_bar[sl]);
+                if (lane == 0) {
+                    ch_q[sl] = q_entry[slot][0]; ch_e0[sl] = e0; ch_rows[sl] = rows;
+                    mbar_expect_tx(bar, (unsigned)rows * row_bytes);      // release: the storer sees ch_* after its wait
+                }
+                __syncwarp();
+                if (lane < rows)
+                    bulk_g2s(slab0 + (unsigned)sl * (unsigned)slab_bytes + (unsigned)lane * row_bytes,
+                             feat + (size_t)q_entry[slot][1 + e0 + lane] * c, row_bytes, bar);
+            }
+            __syncwarp();
+            item++;
+            if (lane == 0) q_head = item;                    // queue slot free again
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); total_chunks = g; }
+    } else {
+        // ------------------------------ storer warp ------------------------------
+        int g = 0;
+        for (;;) {
+            const int sl = g % NS;
+            const unsigned bar = smem_u32(&full_bar[sl]);
+            const unsigned parity = (unsigned)((g / NS) & 1);
+            bool ready = mbar_try(bar, parity);
+            if (!ready) {
+                const int tc = total_chunks;
+                if (tc >= 0 && g >= tc) break;               // the loader is done and every chunk has been stored
+                continue;
+            }
+            if (lane == 0) {
+                bulk_s2g(grouped + ((size_t)ch_q[sl] * K + ch_e0[sl]) * c, slab0 + (unsigned)sl * (unsigned)slab_bytes,
+                         (unsigned)ch_rows[sl] * row_bytes);
+                bulk_wait_read1();                           // every store but the newest has finished reading its slab
+                if (g >= 1) mbar_arrive(smem_u32(&empty_bar[(g - 1) % NS]));
+            }
+            __syncwarp();
+            g++;
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Direct variant: every warp searches and then copies its K rows itself with 16-byte register moves
 // (U rows = up to 16 independent LDG.128 per lane in flight, streaming STG.128 to the contiguous
 // grouped[q] block).  No shared-memory staging, so 32 warps per SM keep both the search issue slots and
@@ -439,6 +605,29 @@ static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const 
         CB_CUDA_CHECK("cb_knn_gather");
         return CB_OK;
     }
+    if (nsample <= 64 && g_kg_ws == 5) {
+        const int ns = 6;
+        const size_t smem_ws = (size_t)ns * slab;
+        int per = (int)(233472 / (smem_ws + 6800 + 1024));
+        if (per > 4) per = 4;
+        if (per < 1) per = 1;
+        int blocks_ws = 148 * per;
+        if (blocks_ws > (m + KGW2_SEARCH - 1) / KGW2_SEARCH) blocks_ws = (m + KGW2_SEARCH - 1) / KGW2_SEARCH;
+        if (nsample <= 32) {
+            cudaFuncSetAttribute(k_knn_gather_ws2<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+            k_knn_gather_ws2<1, 6><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, self_query,
+                                                                  v.scenes, v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged);
+        } else {
+            cudaFuncSetAttribute(k_knn_gather_ws2<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+            k_knn_gather_ws2<2, 6><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, self_query,
+                                                                  v.scenes, v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged);
+        }
+        cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
+        k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
+        CB_COUNT(4);
+        CB_CUDA_CHECK("cb_knn_gather");
+        return CB_OK;
+    }
     if (nsample <= 64 && g_kg_ws) {
         // warp-specialised kernel: ring of NS slabs, LA chunks in flight (mode 1: 8/4, mode 2: 12/8, mode 3: 6/4)
         const int ns = g_kg_ws == 2 ? 12 : (g_kg_ws == 3 ? 6 : 8);
@@ -491,7 +680,7 @@ static bool kg_tma_ok(int c, int nsample, const float *feat, const float *groupe
     return (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 && (size_t)c * 4 <= 16384;
 }
 
-extern "C" int cb_knn_gather_set_mode(int mode) { g_kg_ws = (mode >= 0 && mode <= 4) ? mode : 1; return g_kg_ws; }
+extern "C" int cb_knn_gather_set_mode(int mode) { g_kg_ws = (mode >= 0 && mode <= 5) ? mode : 3; return g_kg_ws; }
 
 extern "C" int cb_knn_gather_set_chunk_bytes(int bytes)
 {

@@ -81,9 +81,10 @@ int cb_knn_gather_grid(int m, int nsample, int c, const float *xyz, int n, const
                        const float *feat, const int *offset, const int *new_offset, int b, int *idx, float *dist2,
                        float *grouped, void *grid, size_t grid_bytes, void *stream);
 float cb_knn_set_occupancy(float factor);       /* tuning knob: target points per occupied grid cell = factor * K (default 0.45) */
-int cb_knn_gather_set_chunk_bytes(int bytes);
+int cb_knn_gather_set_chunk_bytes(int bytes);   /* tuning knob: bytes per TMA chunk (default 8192); returns the value in use */
 int cb_knn_gather_set_mode(int mode);   /* tuning knob: 3 (default) = 7 search warps + 1 TMA copy warp per CTA (6-slab ring);
-                                           0 = every warp searches and copies (TMA); 1,2 = other ring depths; 4 = register copy */   /* tuning knob: bytes per TMA chunk (default 2048); returns the value in use */
+                                           0 = every warp searches and copies (TMA); 1,2 = other ring depths; 4 = register copy;
+                                           5 = 6 search warps + a loader warp + a storer warp (same speed as 3) */
 
 /* ------------------------------------------------------------------------------------------------
  * a2  farthest point sampling             replaces furthestsampling_cuda_launcher

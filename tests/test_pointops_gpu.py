@@ -227,11 +227,11 @@ def test_queryandgroup_and_interpolation_api():
         assert np.allclose(out, ref, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 3, 4, 5])
 @pytest.mark.parametrize("k,c", [(16, 256), (16, 64), (8, 32), (36, 32), (64, 64), (3, 6)])
 def test_fused_knn_gather(k, c, mode):
     from contrastboundary_b200 import fused, _lib
-    _lib.lib().cb_knn_gather_set_mode(mode)          # 0 one-warp TMA, 1/3 warp-specialised TMA rings, 4 direct register copy
+    _lib.lib().cb_knn_gather_set_mode(mode)          # 0 one-warp TMA, 1/3 warp-specialised TMA rings, 4 direct register copy, 5 loader + storer warps
     xyz, off = cases.scene_multi()
     rng = np.random.default_rng(4)
     feat = rng.standard_normal((len(xyz), c)).astype(np.float32)

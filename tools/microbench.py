@@ -98,12 +98,15 @@ def main():
         grid = fused.grid_build(xyz, off, k)
         outb = fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off)
         from contrastboundary_b200 import _lib as L
-        for cb, ws in ((2048, 0), (8192, 3), (8192, 4)):
+        for cb, ws in ((8192, 3), (8192, 5), (4096, 5)):
             L.lib().cb_knn_gather_set_chunk_bytes(cb)
             L.lib().cb_knn_gather_set_mode(ws)
             medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb))
             print(f"      kernel only (grid prebuilt), ws={ws} chunk {cb:5d} B: {medk:8.1f} us (min {mnk:.1f}) -> {by / medk / 1e3:.0f} GB/s ({by / medk / 1e3 / 6569.6 * 100:.0f}%)")
         L.lib().cb_knn_gather_set_chunk_bytes(8192); L.lib().cb_knn_gather_set_mode(3)
+        xyz2 = xyz.clone()          # a distinct query tensor: queries are processed in ORIGINAL order (linear output addresses)
+        medq, mnq = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz2, feat, off, off, outb))
+        print(f"      kernel only, queries in original order (streamed output):  {medq:8.1f} us (min {mnq:.1f}) -> {by / medq / 1e3:.0f} GB/s ({by / medq / 1e3 / 6569.6 * 100:.0f}%)")
         med2, _ = timeit(lambda: pointops.knn_raw(k, xyz, xyz, off, off, False))
         idx, _ = pointops.knn_raw(k, xyz, xyz, off, off, False)
         med3, _ = timeit(lambda: pointops.grouping(feat, idx))
