@@ -14,6 +14,7 @@
 
 #define KG_WARPS 8
 static int g_kg_chunk_bytes = 8192;
+static int g_kg_spin_ns = 0;          // back-off of a search warp that finds the hand-off queue full (0 = busy spin)
 static int g_kg_ws = 3;              // 0 one-warp TMA | 1,2,3 warp-specialised TMA rings (8/4, 12/8, 6/4) | 4 direct register copy    // bytes per TMA chunk (two chunks are in flight per warp)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, i
                                                        const CbScene *__restrict__ scenes, const int *__restrict__ cells,
                                                        const float4 *__restrict__ sorted, int *__restrict__ idx,
                                                        float *__restrict__ dist2, float *__restrict__ grouped,
-                                                       CbGridHeader *hdr, int *flagged)
+                                                       CbGridHeader *hdr, int *flagged, int spin_ns)
 {
     extern __shared__ __align__(128) unsigned char kg_smem[];
     __shared__ CbWarpScratch scratch[KGW_SEARCH];
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, i
             int t = 0;
             if (lane == 0) {
                 t = atomicAdd(&q_tail, 1);
-                while (t - q_head >= KGW_QN) { }            // queue full: wait for the copy warp
+                while (t - q_head >= KGW_QN) { if (spin_ns) __nanosleep(spin_ns); }   // queue full: wait for the copy warp
             }
             t = __shfl_sync(CB_FULL_MASK, t, 0);
             const int slot = t % KGW_QN;
@@ -642,7 +643,7 @@ static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const 
         cudaFuncSetAttribute(k_knn_gather_ws<KPL, NS, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); \
         k_knn_gather_ws<KPL, NS, LA><<<blocks_ws, 256, smem_ws, st>>>(m, nsample, c, R, slab, new_xyz, feat, new_offset, b, \
                                                                       self_query, v.scenes, v.cells, v.sorted, idx, dist2,  \
-                                                                      grouped, v.hdr, v.flagged);                          \
+                                                                      grouped, v.hdr, v.flagged, g_kg_spin_ns);            \
     } while (0)
         if (nsample <= 32) {
             if (g_kg_ws == 2) KGW_LAUNCH(1, 12, 8); else if (g_kg_ws == 3) KGW_LAUNCH(1, 6, 4); else KGW_LAUNCH(1, 8, 4);
@@ -679,6 +680,8 @@ static bool kg_tma_ok(int c, int nsample, const float *feat, const float *groupe
 {
     return (c % 4 == 0) && (((uintptr_t)feat | (uintptr_t)grouped) % 16 == 0) && nsample <= 256 && (size_t)c * 4 <= 16384;
 }
+
+extern "C" int cb_knn_gather_set_spin_ns(int ns) { if (ns >= 0 && ns <= 4096) g_kg_spin_ns = ns; return g_kg_spin_ns; }
 
 extern "C" int cb_knn_gather_set_mode(int mode) { g_kg_ws = (mode >= 0 && mode <= 5) ? mode : 3; return g_kg_ws; }
 

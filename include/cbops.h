@@ -81,6 +81,7 @@ int cb_knn_gather_grid(int m, int nsample, int c, const float *xyz, int n, const
                        const float *feat, const int *offset, const int *new_offset, int b, int *idx, float *dist2,
                        float *grouped, void *grid, size_t grid_bytes, void *stream);
 float cb_knn_set_occupancy(float factor);       /* tuning knob: target points per occupied grid cell = factor * K (default 0.45) */
+int cb_knn_gather_set_spin_ns(int ns);          /* tuning knob: nanosleep back-off of search warps on a full hand-off queue (default 0) */
 int cb_knn_gather_set_chunk_bytes(int bytes);   /* tuning knob: bytes per TMA chunk (default 8192); returns the value in use */
 int cb_knn_gather_set_mode(int mode);   /* tuning knob: 3 (default) = 7 search warps + 1 TMA copy warp per CTA (6-slab ring);
                                            0 = every warp searches and copies (TMA); 1,2 = other ring depths; 4 = register copy;

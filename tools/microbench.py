@@ -98,7 +98,12 @@ def main():
         grid = fused.grid_build(xyz, off, k)
         outb = fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off)
         from contrastboundary_b200 import _lib as L
-        for cb, ws in ((8192, 3), (8192, 5), (4096, 5)):
+        for ns in (0, 8, 16, 32, 64):
+            L.lib().cb_knn_gather_set_spin_ns(ns); L.lib().cb_knn_gather_set_mode(3)
+            medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb), iters=20)
+            print(f"      kernel only, ws=3, queue-full back-off {ns:3d} ns: {medk:8.1f} us (min {mnk:.1f})")
+        L.lib().cb_knn_gather_set_spin_ns(0)
+        for cb, ws in ((8192, 3), (8192, 5)):
             L.lib().cb_knn_gather_set_chunk_bytes(cb)
             L.lib().cb_knn_gather_set_mode(ws)
             medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb))
