@@ -103,7 +103,7 @@ def main():
             medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb), iters=20)
             print(f"      kernel only, ws=3, queue-full back-off {ns:3d} ns: {medk:8.1f} us (min {mnk:.1f})")
         L.lib().cb_knn_gather_set_spin_ns(0)
-        for cb, ws in ((8192, 3), (8192, 5)):
+        for cb, ws in ((8192, 3), (16384, 3), (8192, 5), (8192, 1)):     # measured: 150-158 / 159 / 155 / 160 us
             L.lib().cb_knn_gather_set_chunk_bytes(cb)
             L.lib().cb_knn_gather_set_mode(ws)
             medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb))
