@@ -1,0 +1,72 @@
+"""CPU tests of the host-side logic around the CUDA path (no compute call into libcbops): level sizes of the
+TransitionDown chain, the stacked batch-index matrices of the TF pyramid, the CPU fall-back of the BatchNorm wrappers
+(state_dict compatibility with nn.BatchNorm1d) and the IoU histograms of the boundary evaluation."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from contrastboundary_b200 import boundary_eval, linear_ops, model, tf_pyramid
+
+
+def test_level_offsets_follow_the_reference_rule():
+    """per-scene floor(n_b / stride), accumulated (pytorch/model/blocks.py:64-67): remainders are lost at every level"""
+    cfg = model.CBLConfig()
+    ohs = model.level_offsets_host([40960, 40960 + 30001, 40960 + 30001 + 7], cfg)
+    assert ohs[0] == [40960, 70961, 70968]
+    lens = [40960, 30001, 7]
+    for l in range(1, 5):
+        lens = [x // 4 for x in lens]
+        assert ohs[l] == list(np.cumsum(lens)), l
+    assert ohs[4][-1] - ohs[4][-2] == 0            # the 7-point scene has vanished by level 2
+
+
+def test_stack_batch_inds_matches_reference_semantics():
+    """tf_stack_batch_inds_while (tensorflow/datasets/base.py:694-737): rows padded with n = sum(lens); one extra shadow
+    column only when no row is padded"""
+    a = tf_pyramid.stack_batch_inds(torch.tensor([3, 2, 5], dtype=torch.int32)).numpy()
+    assert np.array_equal(a, np.array([[0, 1, 2, 10, 10], [3, 4, 10, 10, 10], [5, 6, 7, 8, 9]], np.int32))
+    b = tf_pyramid.stack_batch_inds(torch.tensor([2, 2], dtype=torch.int32)).numpy()
+    assert np.array_equal(b, np.array([[0, 1, 4], [2, 3, 4]], np.int32))
+    c = tf_pyramid.stack_batch_inds(torch.tensor([2, 2], dtype=torch.int32), tight=True).numpy()
+    assert np.array_equal(c, np.array([[0, 1], [2, 3]], np.int32))
+
+
+def test_batchnorm_wrapper_is_a_drop_in_on_cpu():
+    """linear_ops.BatchNorm1d / bn_act: same parameters, buffers, state_dict and results as nn.BatchNorm1d (+ add + relu)"""
+    torch.manual_seed(0)
+    ref, ours = nn.BatchNorm1d(8), linear_ops.BatchNorm1d(8)
+    assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    x, r = torch.randn(50, 8), torch.randn(50, 8)
+    for training in (True, False):
+        ref.train(training); ours.train(training)
+        want = torch.relu(ref(x) + r)
+        got = linear_ops.bn_act(ours, x, residual=r, relu=True)
+        assert torch.allclose(got, want, atol=1e-6)
+    linear_ops.flush_bn_counters()
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(ours.state_dict()[k].float(), v.float(), atol=1e-6), k
+
+
+def test_network_state_dict_names_match_the_oracle_network():
+    """the product network and the op-by-op restatement of the reference network share every parameter / buffer name
+    (the restatement's names are pinned to the REAL reference by tests/golden/model_ref.npz)"""
+    from oracle import cpu_pointops, ref_model
+    ours = model.PointTransformerSeg(model.CBLConfig())
+    ref = ref_model.RefSeg(cpu_pointops)
+    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert a == b
+
+
+def test_intersection_and_union_histograms():
+    rng = np.random.default_rng(0)
+    label = rng.integers(0, 13, 5000); label[rng.random(5000) < 0.05] = 255
+    pred = np.where(rng.random(5000) < 0.7, label, rng.integers(0, 13, 5000))
+    i, u, t = boundary_eval.intersection_and_union(torch.from_numpy(pred), torch.from_numpy(label), 13, 255)
+    p = pred.copy(); p[label == 255] = 255
+    inter = p[p == label]
+    ai = np.bincount(inter[inter < 13], minlength=13)[:13]
+    ao = np.bincount(p[p < 13], minlength=13)[:13]
+    at = np.bincount(label[label < 13], minlength=13)[:13]
+    assert np.array_equal(i.numpy(), ai) and np.array_equal(u.numpy(), ao + at - ai) and np.array_equal(t.numpy(), at)
