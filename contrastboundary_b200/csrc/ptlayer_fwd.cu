@@ -439,6 +439,76 @@ extern "C" int cb_pt_rel(int n, int k, const float *p, const int *idx, float *re
     return CB_OK;
 }
 
+// F3, staged variant (k <= 16): a block owns PB = 256 / CS points.  v = relu(bn3(w2)) of those points is staged ONCE in
+// shared memory (the generic kernel above re-derives it CS times per element), thread (point, j) keeps its row of W4 and
+// its k logits in registers and reads v with broadcast LDS.128.
+template <int CS>
+__global__ void __launch_bounds__(256) k_pt_softmax_staged(int n, int k, const float *__restrict__ w2, const float *__restrict__ bn3,
+                                                           const float *__restrict__ w4, const float *__restrict__ b4,
+                                                           float *__restrict__ a)
+{
+    constexpr int PB = 256 / CS;
+    extern __shared__ __align__(16) float ss_sm[];             // [PB][k][CS]
+    const int tp = threadIdx.x / CS, tj = threadIdx.x % CS;
+    float wrow[CS];
+#pragma unroll
+    for (int i = 0; i < CS; i++) wrow[i] = __ldg(w4 + tj * CS + i);
+    const float bj = __ldg(b4 + tj);
+    const int tile_elems = PB * k * CS;
+    const int tiles = (n + PB - 1) / PB;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long base = (long long)tile * tile_elems;
+        const long long limit = (long long)n * k * CS;
+        for (int e = threadIdx.x; e < tile_elems; e += 256) {
+            const int i = e % CS;
+            float v = 0.f;
+            if (base + e < limit) v = fmaxf(__ldg(w2 + base + e) * __ldg(bn3 + i) + __ldg(bn3 + CS + i), 0.f);
+            ss_sm[e] = v;
+        }
+        __syncthreads();
+        const int pt = tile * PB + tp;
+        if (pt < n) {
+            float lg[16];
+            float mx = -3.0e38f;
+#pragma unroll
+            for (int kk = 0; kk < 16; kk++) {
+                lg[kk] = -3.0e38f;
+                if (kk < k) {
+                    const float *vr = ss_sm + (tp * k + kk) * CS;
+                    float acc = bj;
+#pragma unroll
+                    for (int i = 0; i < CS; i += 4) {
+                        const float4 v4 = *reinterpret_cast<const float4 *>(vr + i);
+                        acc += wrow[i] * v4.x; acc += wrow[i + 1] * v4.y; acc += wrow[i + 2] * v4.z; acc += wrow[i + 3] * v4.w;
+                    }
+                    lg[kk] = acc;
+                    mx = fmaxf(mx, acc);
+                }
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 16; kk++)
+                if (kk < k) { lg[kk] = expf(lg[kk] - mx); sum += lg[kk]; }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int kk = 0; kk < 16; kk++)
+                if (kk < k) a[((size_t)pt * k + kk) * CS + tj] = lg[kk] * inv;
+        }
+        __syncthreads();
+    }
+}
+
+template <int CS>
+static void pt_softmax_staged_launch(int n, int k, const float *w2, const float *bn3, const float *w4, const float *b4, float *a,
+                                     cudaStream_t st)
+{
+    constexpr int PB = 256 / CS;
+    const size_t smem = (size_t)PB * k * CS * sizeof(float);       // 256 * k floats <= 16 KB
+    int tiles = (n + PB - 1) / PB;
+    int g = tiles < 148 * 6 ? (tiles < 1 ? 1 : tiles) : 148 * 6;
+    k_pt_softmax_staged<CS><<<g, 256, smem, st>>>(n, k, w2, bn3, w4, b4, a);
+}
+
 int cb_pt_mma_enabled();
 void cb_pt_w2_mma(int c, int n, int k, int ld, const float *rel, const int *idx, const float *xq, const float *xk,
                   const float *w2p, const float *b2p, const float *smalld, const float *bn2, const float *w3, const float *b3,
@@ -478,7 +548,8 @@ static int pt_forward_c(int n, int k, int ld, const CbPtLayer *L, const float *r
     int g4 = (int)((tot + 255) / 256);
     if (g4 > 148 * 8) g4 = 148 * 8;
     if (g4 < 1) g4 = 1;
-    k_pt_softmax<<<g4, 256, smem4, st>>>(n, k, CS, w2buf, bn3, L->w4, L->b4, abuf);
+    if (k <= 16) pt_softmax_staged_launch<CS>(n, k, w2buf, bn3, L->w4, L->b4, abuf, st);
+    else k_pt_softmax<<<g4, 256, smem4, st>>>(n, k, CS, w2buf, bn3, L->w4, L->b4, abuf);
     k_pt_aggregate<C><<<grid, PT_THREADS, 0, st>>>(n, k, ld, rel, idx, xv, L->w2, L->b2, small, abuf, out);
     CB_COUNT(9);
     CB_CUDA_CHECK("cb_pt_layer_forward");
