@@ -70,3 +70,39 @@ def test_intersection_and_union_histograms():
     ao = np.bincount(p[p < 13], minlength=13)[:13]
     at = np.bincount(label[label < 13], minlength=13)[:13]
     assert np.array_equal(i.numpy(), ai) and np.array_equal(u.numpy(), ao + at - ai) and np.array_equal(t.numpy(), at)
+
+
+def test_trainer_checkpoint_round_trip_and_schedule(tmp_path):
+    """optimizer / scheduler / checkpoint format of the reference trainer (pytorch/tool/train.py:154-165,209-224,289-296)"""
+    from contrastboundary_b200 import trainer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(model._LatentMLP(6, 8), torch.nn.Linear(8, 13))
+    opt = trainer.build_optimizer(net, fused=False)
+    sch = trainer.build_scheduler(opt, epochs=100)
+    assert sch.milestones == {60: 1, 80: 1}
+    x, y = torch.randn(32, 6), torch.randint(0, 13, (32,))
+    for _ in range(3):
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(net(x), y).backward()
+        opt.step()
+        sch.step()
+    path = str(tmp_path / "model" / "model_last.pth")
+    trainer.save_checkpoint(path, 3, net, opt, sch, best_iou=0.42, is_best=True)
+    ckpt = torch.load(path, weights_only=False)
+    assert set(ckpt) == {"epoch", "state_dict", "optimizer", "scheduler", "best_iou", "is_best"}     # train.py:292-293
+    assert all(k.startswith("module.") for k in ckpt["state_dict"])                                  # DDP keys, test.py:107
+    assert (tmp_path / "model" / "model_best.pth").exists()
+    net2 = torch.nn.Sequential(model._LatentMLP(6, 8), torch.nn.Linear(8, 13))
+    opt2 = trainer.build_optimizer(net2, fused=False)
+    sch2 = trainer.build_scheduler(opt2, epochs=100)
+    epoch, best = trainer.resume(path, net2, opt2, sch2)
+    assert (epoch, best) == (3, 0.42) and sch2.last_epoch == 3
+    for a, b in zip(net.state_dict().values(), net2.state_dict().values()):
+        assert torch.equal(a, b)
+    assert torch.equal(opt.state_dict()["state"][0]["momentum_buffer"], opt2.state_dict()["state"][0]["momentum_buffer"])
+    net3 = torch.nn.Sequential(model._LatentMLP(6, 8), torch.nn.Linear(8, 13))
+    assert trainer.load_weights(path, net3) == 3 and torch.equal(net3[1].weight, net[1].weight)
+    # learning rate: 0.5 until epoch 60, 0.05 until 80, then 0.005
+    for _ in range(3, 85):
+        opt2.step(); sch2.step()
+    assert abs(opt2.param_groups[0]["lr"] - 0.005) < 1e-9
