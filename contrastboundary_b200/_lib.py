@@ -51,8 +51,9 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """torch's current stream (of `device`, default: the current device) as a C pointer"""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def check(rc, what):
@@ -70,8 +71,15 @@ def require_cuda(*tensors):
 def call(name, *args):
     f = getattr(lib(), name)
     conv = []
+    cur = None
     for a in args:
         if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                if cur is None:
+                    cur = torch.cuda.current_device()
+                if a.device.index != cur:          # the stream argument is the CURRENT device's stream
+                    raise CbopsError("%s: tensor on cuda:%d but the current device is cuda:%d (call torch.cuda.set_device)"
+                                     % (name, a.device.index, cur))
             conv.append(C.c_void_p(a.data_ptr()))
         elif isinstance(a, float):
             conv.append(C.c_float(a))

@@ -9,7 +9,7 @@
 
 void cb_set_error(const char *fmt, ...);
 extern unsigned long long g_cb_launches;   // kernels launched by this library (host-side count)
-#define CB_COUNT(n) (g_cb_launches += (n))
+#define CB_COUNT(n) ((void)__atomic_fetch_add(&g_cb_launches, (unsigned long long)(n), __ATOMIC_RELAXED))   // autograd / DDP threads launch too
 
 #define CB_REQUIRE(cond, code, ...)            \
     do {                                       \

@@ -544,9 +544,21 @@ int cb_knn_query_radius_impl(int m, int K, const float *xyz, int n, const float 
                              cudaStream_t st)
 {
     if (m == 0 || K == 0) return CB_OK;
-    CB_REQUIRE(K <= 256, CB_EUNSUPPORTED, "radius neighbours: row width %d > 256 unsupported", K);
+    CB_REQUIRE(K <= 2048, CB_EUNSUPPORTED, "radius neighbours: row width %d > 2048 unsupported", K);
     const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
     const int blocks = (m + 3) / 4;
+    const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
+    if (K > 256) {
+        // rows wider than the register top-K of k_knn_query (dense clouds during neighbourhood-limit calibration,
+        // datasets/base.py:199-294): every query takes the exact scene scan
+        k_flag_all<<<(m + 255) / 256, 256, 0, st>>>(m, v.hdr, v.flagged);
+        const int rblocks = m < 148 * 8 ? m : 148 * 8;
+        k_knn_replay<<<rblocks, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, nullptr, 0,
+                                                               v.hdr, v.flagged, 1, r2, pad_idx);
+        CB_COUNT(2);
+        CB_CUDA_CHECK("cb_batch_radius_neighbors");
+        return CB_OK;
+    }
     k_reset_flagged<<<1, 1, 0, st>>>(v.hdr);
 #define CB_LAUNCH_R(KPL)                                                                                          \
     k_knn_query<KPL><<<blocks, 128, 0, st>>>(m, K, new_xyz, new_offset, b, self_query, v.scenes, v.cells, v.sorted, \
@@ -556,7 +568,6 @@ int cb_knn_query_radius_impl(int m, int K, const float *xyz, int n, const float 
     else if (K <= 128) CB_LAUNCH_R(4);
     else CB_LAUNCH_R(8);
 #undef CB_LAUNCH_R
-    const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
     k_knn_replay<<<148, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, nullptr, 0, v.hdr,
                                                        v.flagged, 1, r2, pad_idx);
     CB_COUNT(3);

@@ -42,13 +42,14 @@ class TrainStep:
                                     self.cfg.contrast is not None, knn_stream=self.side2)
             ev = torch.cuda.Event()
             ev.record(self.side)
-        self._geo[id(batch)] = (levels, ev)
+        self._geo[id(batch)] = (batch, levels, ev)        # the batch object itself is kept: id() alone can be recycled
 
     def _take_geometry(self, batch):
         geo = self._geo.pop(id(batch), None)
-        if geo is None:
+        self._geo.clear()                                 # geometry prefetched for a batch that never came: drop it
+        if geo is None or geo[0] is not batch:
             return None
-        levels, ev = geo
+        _, levels, ev = geo
         main = torch.cuda.current_stream(self.device)
         main.wait_event(ev)
         for lv in levels:                                 # allocated on the side stream, consumed on `main`
@@ -160,7 +161,7 @@ class GraphTrainStep(TrainStep):
                 o += p.numel()
         self._packed = flag
 
-    def _eager_step(self, batch):
+    def _eager_step(self, batch, update=True):
         batch = to_device(batch, self.device)
         self._set_packed(False)
         self.opt.zero_grad(set_to_none=True)
@@ -180,7 +181,8 @@ class GraphTrainStep(TrainStep):
             for g in gs:
                 g.copy_(flat[o:o + g.numel()].view_as(g))
                 o += g.numel()
-        self.opt.step()
+        if update:
+            self.opt.step()
         return loss.detach()
 
     def stream_loss_and_grad(self, batch):
@@ -286,7 +288,7 @@ class GraphTrainStep(TrainStep):
         if slots is False:
             if self._eager_done < self.eager_warmup or not update:
                 self._eager_done += 1
-                return self._eager_step(batch)
+                return self._eager_step(batch, update)
             slots = None
             if len(self._sigs) < self.max_signatures:
                 try:
@@ -302,7 +304,7 @@ class GraphTrainStep(TrainStep):
                     self._packed = False
             self._sigs[sig] = slots
         if slots is None or not update:
-            return self._eager_step(batch)
+            return self._eager_step(batch, update)
         self._set_packed(True)                                          # the optimiser reads the packed gradient
         cur = next((s for s in slots if s.holds is batch), None)
         if cur is None:

@@ -52,6 +52,49 @@ class CBLConfig:
     multi: bool = True      # MultiHead(stage 'Ua', ftype latent, combine concat)
     fused: bool = True
 
+    @classmethod
+    def from_reference(cls, config, c=None, k=None, fused=True):
+        """CBLConfig from the reference's config node (util/config.py CfgNode of config/s3dis/*.yaml, or any mapping /
+        namespace with the same keys): what `pointtransformer_seg_repro(c=, k=, config=)` and `Loss(config)` read
+        (pointtransformer_seg.py:15-66, heads.py:13-95).  Options outside the shipped yaml's family raise."""
+        has = (lambda key: key in config) if hasattr(config, "__contains__") else (lambda key: hasattr(config, key))
+        get = (lambda key, d=None: (config[key] if isinstance(config, dict) else getattr(config, key)) if has(key) else d)
+
+        def sub(node, key, d=None):
+            if node is None:
+                return d
+            if isinstance(node, dict):
+                return node.get(key, d)
+            try:
+                return getattr(node, key) if key in node else d
+            except TypeError:
+                return getattr(node, key, d)
+        kw = dict(fea_dim=int(c if c is not None else get("fea_dim", 6)),
+                  classes=int(k if k is not None else (get("num_classes") or get("classes") or 13)), fused=fused)
+        for name in ("planes", "share_planes", "base_fdim", "nstride", "ignore_label"):
+            if has(name) and get(name) not in (None, ""):
+                kw[name] = get(name)
+        if has("nsample") and get("nsample"):
+            kw["nsample"] = list(get("nsample"))        # reaches the contrast head only (yaml:57, heads.py:68)
+        multi = get("multi")
+        kw["multi"] = bool(multi)
+        if multi:
+            if (sub(multi, "stage"), sub(multi, "ftype"), sub(multi, "combine")) != ("Ua", "latent", "concat"):
+                raise NotImplementedError("MultiHead: only stage 'Ua' / ftype 'latent' / combine 'concat' (the shipped yaml) is built")
+        ch = get("contrast")
+        if ch:
+            w = sub(ch, "weight", "w.1")
+            t = sub(ch, "temperature", None)
+            cc = ContrastCfg(stage=sub(ch, "stage", "Ua"), contrast=sub(ch, "contrast", "softnn"), ftype=sub(ch, "ftype", "latent"),
+                             dist=sub(ch, "dist", "l2"), temperature=None if t in (None, "") else float(t),
+                             weight=float(w[1:]) if isinstance(w, str) else float(w))     # 'w.1' -> .1 (heads.py:241)
+            if cc.contrast != "softnn" or cc.dist != "l2" or sub(ch, "pos", "cnt") != "cnt" or sub(ch, "project", None):
+                raise NotImplementedError("ContrastHead: only contrast softnn / dist l2 / pos cnt without projection is built")
+            kw["contrast"] = cc
+        else:
+            kw["contrast"] = None
+        return cls(**kw)
+
 
 # ------------------------------------------------------------------------------------------------
 # geometry: everything that depends on coordinates only
@@ -429,14 +472,26 @@ class PointTransformerSeg(nn.Module):
             for blk in list(decs[l])[1:]:
                 x = blk(levels[l], x)
             up[l] = x
-        stages = {"levels": levels, "down": down, "up": up}
+        # the reference's stage_list (pointtransformer_seg.py:102-135) + the geometry object under 'levels'
+        stage_list = {"inputs": inputs, "levels": levels,
+                      "down": [{"p_out": lv.p, "f_out": f, "offset": lv.o} for lv, f in zip(levels, down)],
+                      "up": [{"p_out": lv.p, "f_out": f, "offset": lv.o} for lv, f in zip(levels, up)]}
         if self.head is not None:
             logits, latents = self.head(up, levels)
-            stages["latent"] = latents
+            for st, lat in zip(stage_list["up"], latents):
+                st["latent"] = lat                                  # heads.py:57
         else:
             logits = self.cls(up[0])
         flush_bn_counters()           # one multi-tensor increment for every BatchNorm of this forward
-        return logits, stages
+        return logits, stage_list
+
+
+def pointtransformer_seg_repro(**kwargs):
+    """pointtransformer_seg.py:139-143: `pointtransformer_seg_repro(c=6, k=13, config=cfg)` with the reference's config node"""
+    config = kwargs.get("config")
+    if isinstance(config, CBLConfig):
+        return PointTransformerSeg(config)
+    return PointTransformerSeg(CBLConfig.from_reference(config, kwargs.get("c", 6), kwargs.get("k", 13)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -445,13 +500,57 @@ class PointTransformerSeg(nn.Module):
 _EPS = 1e-12   # basic_operators.py:7
 
 
-class ContrastHead(nn.Module):
-    """heads.py:63-253, configuration of the shipped yaml (softnn / l2 / label / cnt / T=1 / w=0.1)."""
+def _parse_stage(stage, num_layers):
+    """'Ua' -> [('up',0)..('up',4)], 'D012_U34' -> down 0,1,2 + up 3,4   (model/utils.py:27-36)"""
+    import re
+    stage = stage.replace("a", "".join(str(i) for i in range(num_layers)))
+    toks = [t.strip("_") for t in re.split(r"(\d+)", stage) if t and t.strip("_")]
+    assert len(toks) % 2 == 0, f"invalid stage compound: {toks} from stage={stage}"
+    names = {"D": "down", "down": "down", "U": "up", "up": "up"}
+    return [(names[n], int(d)) for n, ds in zip(toks[0::2], toks[1::2]) for d in ds]
 
-    def __init__(self, cfg: CBLConfig):
+
+def _levels_of(stage_list, cfg: CBLConfig):
+    """geometry of a stage_list: the product model's own (`levels`), or — for a stage_list that came from the
+    REFERENCE's model code — rebuilt from p_out / offset with the two searches the reference's head runs itself
+    (heads.py:192, basic_operators.py:33)."""
+    levels = stage_list.get("levels")
+    if levels is not None and levels[0].cbl_idx is not None:
+        return levels
+    if levels is None:
+        levels = []
+        for st in stage_list["up"]:
+            lv = Level()
+            lv.p, lv.o, lv.n = st["p_out"].contiguous(), st["offset"], st["p_out"].shape[0]
+            levels.append(lv)
+        stage_list["levels"] = levels
+    kr = 1
+    for l, lv in enumerate(levels):
+        if l > 0:
+            kr *= cfg.nstride[l - 1]
+            lv.label_idx, _ = pointops.knnquery(kr, levels[0].p, lv.p, levels[0].o, lv.o)
+        lv.cbl_idx, _ = pointops.knnquery(cfg.nsample[l], lv.p, lv.p, lv.o, lv.o)
+    return levels
+
+
+class ContrastHead(nn.Module):
+    """heads.py:63-253, configuration of the shipped yaml (softnn / l2 / label / cnt / T=1 / w=0.1).
+    Same constructor and call as the reference: `ContrastHead(head_cfg, config).forward(output, target, stage_list)
+    -> list of per-stage losses` (heads.py:66,248-253); `ContrastHead(CBLConfig)` is the short form."""
+
+    def __init__(self, head_cfg, config=None):
         super().__init__()
+        if config is None and isinstance(head_cfg, CBLConfig):
+            cfg = head_cfg
+        elif isinstance(config, CBLConfig):
+            cfg = config
+        else:
+            cfg = CBLConfig.from_reference(config)
         self.cfg = cfg
+        self.head_cfg = cfg.contrast
         self.fused = cfg.fused
+        self.stages = _parse_stage(cfg.contrast.stage, len(cfg.planes))
+        self.ftype = "f_out" if cfg.contrast.ftype in ("out", "fout") else cfg.contrast.ftype
 
     def subscene_labels(self, l, levels, target):
         """basic_operators.py:9-50: one-hot at level 0, mean one-hot of the kr nearest full-res points above."""
@@ -463,7 +562,8 @@ class ContrastHead(nn.Module):
 
     def stage_loss(self, l, levels, latent, target):
         cc = self.cfg.contrast
-        if self.fused:
+        # the fused kernel covers the shipped widths; anything else takes the op-by-op path on the same operators
+        if self.fused and latent.shape[1] in (32, 64, 72) and levels[l].cbl_idx.shape[1] <= 65:
             from . import cbl
             return cbl.cbl_stage_loss(self, l, levels, latent, target)
         labels = self.subscene_labels(l, levels, target)                        # (m, ncls)
@@ -487,22 +587,24 @@ class ContrastHead(nn.Module):
         loss = (loss * pm).sum() / pm.sum().clamp(min=1.0)
         return loss * cc.weight
 
-    def forward(self, stages, target):
-        levels, latents = stages["levels"], stages["latent"]
-        return [self.stage_loss(l, levels, latents[l], target) for l in range(len(levels))]
+    def forward(self, output, target, stage_list):
+        levels = _levels_of(stage_list, self.cfg)
+        return [self.stage_loss(i, levels, stage_list[n][i][self.ftype], target) for n, i in self.stages]
 
 
 class Loss(nn.Module):
-    """pointtransformer_seg.py:15-25: stack [cross-entropy, cbl_0 .. cbl_4]"""
+    """pointtransformer_seg.py:15-25: `Loss(config).forward(output, target, stage_list)` -> stacked
+    [cross-entropy, cbl_0 .. cbl_4]; `config` = the reference's config node or a CBLConfig."""
 
-    def __init__(self, cfg: CBLConfig):
+    def __init__(self, config):
         super().__init__()
-        self.cfg = cfg
-        self.contrast_head = ContrastHead(cfg) if cfg.contrast is not None else None
+        cfg = config if isinstance(config, CBLConfig) else CBLConfig.from_reference(config)
+        self.cfg = self.config = cfg
+        self.contrast_head = ContrastHead(cfg.contrast, cfg) if cfg.contrast is not None else None
         self.xen = nn.CrossEntropyLoss(ignore_index=cfg.ignore_label)
 
-    def forward(self, output, target, stages):
-        losses = [self.xen(output, target)]
+    def forward(self, output, target, stage_list):
+        loss_list = [self.xen(output, target)]
         if self.contrast_head is not None:
-            losses += self.contrast_head(stages, target)
-        return torch.stack(losses)
+            loss_list += self.contrast_head(output, target, stage_list)
+        return torch.stack(loss_list)

@@ -72,15 +72,16 @@ class PtAttentionFn(Function):
                                      L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(out), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf),
                                      L.ptr(stats), L.ptr(w0buf), L.stream())
         L.check(rc, "cb_pt_layer_forward")
-        ctx.save_for_backward(rel, idx, qkv, w2buf, abuf, bnbuf, *params)
-        ctx.w0buf = w0buf
+        ctx.has_w0 = w0buf is not None
+        ctx.save_for_backward(rel, idx, qkv, w2buf, abuf, bnbuf, *params, *((w0buf,) if w0buf is not None else ()))
         ctx.training = training
         return out
 
     @staticmethod
     def backward(ctx, gout):
         rel, idx, qkv, w2buf, abuf, bnbuf = ctx.saved_tensors[:6]
-        params = ctx.saved_tensors[6:]
+        params = ctx.saved_tensors[6:20]
+        w0buf = ctx.saved_tensors[20] if ctx.has_w0 else None
         n, k = idx.shape
         c = qkv.shape[1] // 3
         cs = c // 8
@@ -99,10 +100,8 @@ class PtAttentionFn(Function):
         ps = _param_struct(params, (params[0],) * 6, 0.0, 0.0, ctx.training)   # running stats unused in backward
         rc = lib.cb_pt_layer_backward(C.c_int(n), C.c_int(k), C.c_int(c), C.c_int(ld), C.byref(ps), L.ptr(rel), L.ptr(idx), L.ptr(xq),
                                       L.ptr(xk), L.ptr(xv), L.ptr(w2buf), L.ptr(abuf), L.ptr(bnbuf), L.ptr(gout),
-                                      L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.ptr(ctx.w0buf), L.stream())
+                                      L.ptr(gxq), L.ptr(gxk), L.ptr(gxv), L.ptr(gbuf), L.ptr(scratch), L.ptr(w0buf), L.stream())
         L.check(rc, "cb_pt_layer_backward")
-        ctx.w0buf = None
-        PtAttentionFn.debug_last = (scratch, gbuf, bnbuf)
         grads, o = [], 0
         for sz, p in zip(sizes, params):
             grads.append(gbuf[o:o + sz].view_as(p))

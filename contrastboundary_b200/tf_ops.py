@@ -124,10 +124,13 @@ def grid_subsampling(points, features=None, labels=None, sampleDl=0.1, verbose=0
     return outs[0] if len(outs) == 1 else tuple(outs)
 
 
-def tf_batch_neighbors(queries, supports, q_batches, s_batches, radius, limit=None):
+def tf_batch_neighbors(queries, supports, q_batches, s_batches, radius, limit=None, exact_width=False):
     """radius neighbours for stacked clouds -> int32 (Nq, max_count) padded with Ns   (tf_ops.py:165-168).
     `limit` (optional) = neighborhood_limits[layer]: return only the nearest `limit` columns, which is what
-    the caller keeps anyway (datasets/base.py:762) and avoids the device->host read of the max count."""
+    the caller keeps anyway (datasets/base.py:762).  Width contract: with `limit` the result is EXACTLY `limit`
+    columns wide (columns past the batch-wide max count hold the shadow index Ns) and no device->host read
+    happens; `exact_width=True` reproduces the reference's `neighbors[:, :limit]` shape, min(max_count, limit),
+    at the price of one host sync."""
     q = _to_cuda(queries, torch.float32)
     s = _to_cuda(supports, torch.float32)
     same = (queries is supports)
@@ -143,7 +146,10 @@ def tf_batch_neighbors(queries, supports, q_batches, s_batches, radius, limit=No
     rc = lib.cb_radius_count(C.c_int(nq), L.ptr(q), C.c_int(ns), L.ptr(s), L.ptr(qo), L.ptr(so), C.c_int(b), C.c_float(float(radius)),
                              L.ptr(counts), L.ptr(mx), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
     L.check(rc, "cb_radius_count")
-    width = int(limit) if limit is not None else int(mx.item())
+    if limit is None:
+        width = int(mx.item())
+    else:
+        width = min(int(limit), int(mx.item())) if exact_width else int(limit)
     out = torch.empty((nq, width), dtype=torch.int32, device=q.device)
     if width > 0 and nq > 0:
         rc = lib.cb_radius_fill(C.c_int(nq), C.c_int(width), L.ptr(q), C.c_int(ns), L.ptr(s), L.ptr(qo), L.ptr(so), C.c_int(b),

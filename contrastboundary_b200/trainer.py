@@ -47,7 +47,11 @@ def save_checkpoint(path, epoch, model, optimizer, scheduler, best_iou, is_best=
     if ddp_prefix:
         sd = _with_prefix(sd, "module.")
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    torch.save({"epoch": epoch, "state_dict": sd, "optimizer": optimizer.state_dict(), "scheduler": scheduler.state_dict(),
+    osd = optimizer.state_dict()
+    # `fused` is an implementation switch of THIS process' optimiser, not training state: a reference resume
+    # (train.py:214) would load it into its own SGD's param_groups
+    osd = {"state": osd["state"], "param_groups": [{k: v for k, v in g.items() if k != "fused"} for g in osd["param_groups"]]}
+    torch.save({"epoch": epoch, "state_dict": sd, "optimizer": osd, "scheduler": scheduler.state_dict(),
                 "best_iou": best_iou, "is_best": is_best}, path)
     if is_best:
         shutil.copyfile(path, os.path.join(os.path.dirname(os.path.abspath(path)), "model_best.pth"))
@@ -64,6 +68,9 @@ def resume(path, model, optimizer, scheduler, map_location=None):
     """train.py:209-224 -> (start_epoch, best_iou)"""
     ckpt = torch.load(path, map_location=map_location, weights_only=False)
     model.load_state_dict(_strip_prefix(ckpt["state_dict"]), strict=True)
-    optimizer.load_state_dict(ckpt["optimizer"])
+    osd = ckpt["optimizer"]
+    cur = optimizer.state_dict()["param_groups"]
+    groups = [dict(g, **({"fused": c["fused"]} if "fused" in c and "fused" not in g else {})) for g, c in zip(osd["param_groups"], cur)]
+    optimizer.load_state_dict({"state": osd["state"], "param_groups": groups})
     scheduler.load_state_dict(ckpt["scheduler"])
     return ckpt["epoch"], ckpt["best_iou"]

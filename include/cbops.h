@@ -315,6 +315,39 @@ int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const 
  * (mma.sync m16n8k8 TF32 with 3xTF32 error compensation, ptlayer_mma.cu); 0: FP32 SIMT kernels.  Returns the setting. */
 int cb_pt_set_tensor_cores(int on);
 
+/* ------------------------------------------------------------------------------------------------
+ * The reference's OWN native ABI (compat.cu): the ten `extern "C"` launchers its pybind glue calls,
+ * with the reference's exact names and argument lists, so that the unmodified glue
+ * (pytorch/lib/pointops/src/<op>/<op>_cuda.cpp + pointops_api.cpp) links against libcbops.so in place of
+ * its own .cu objects.  Declarations: knnquery_cuda_kernel.h:10-17, sampling_cuda_kernel.h,
+ * grouping_cuda_kernel.h, interpolation_cuda_kernel.h, subtraction_cuda_kernel.h,
+ * aggregation_cuda_kernel.h:14-21.  They launch on the stream given to cb_compat_set_stream (default NULL =
+ * the legacy default stream the reference launches on); knnquery reads the scene / support counts back
+ * from the device offsets (one stream synchronise per call) and uses a library-owned grow-only workspace.
+ * Being `void`, they report failures on stderr + cb_last_error_string().
+ * ---------------------------------------------------------------------------------------------- */
+void cb_compat_set_stream(void *stream);
+void knnquery_cuda_launcher(int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                            const int *new_offset, int *idx, float *dist2);
+void furthestsampling_cuda_launcher(int b, int n, const float *xyz, const int *offset, const int *new_offset,
+                                    float *tmp, int *idx);
+void grouping_forward_cuda_launcher(int m, int nsample, int c, const float *input, const int *idx, float *output);
+void grouping_backward_cuda_launcher(int m, int nsample, int c, const float *grad_output, const int *idx,
+                                     float *grad_input);
+void interpolation_forward_cuda_launcher(int n, int c, int k, const float *input, const int *idx, const float *weight,
+                                         float *output);
+void interpolation_backward_cuda_launcher(int n, int c, int k, const float *grad_output, const int *idx,
+                                          const float *weight, float *grad_input);
+void subtraction_forward_cuda_launcher(int n, int nsample, int c, const float *input1, const float *input2,
+                                       const int *idx, float *output);
+void subtraction_backward_cuda_launcher(int n, int nsample, int c, const int *idx, const float *grad_output,
+                                        float *grad_input1, float *grad_input2);
+void aggregation_forward_cuda_launcher(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                                       const float *weight, const int *idx, float *output);
+void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                                        const float *weight, const int *idx, const float *grad_output,
+                                        float *grad_input, float *grad_position, float *grad_weight);
+
 #ifdef __cplusplus
 }
 #endif

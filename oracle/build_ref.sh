@@ -50,4 +50,27 @@ if [ ! -f $OUT/pointops_cuda.so ]; then
   g++ -shared -o $OUT/pointops_cuda.so $OUT/obj/*_h.o $OUT/obj/*_k.o -L$TL -ltorch -ltorch_cpu -ltorch_python -lc10 \
       -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$TL
 fi
-echo "[build_ref] ok: $(ls $OUT/*.so | tr '\n' ' ')"
+
+# ---- drop-in proof: the reference's UNMODIFIED pybind glue linked against libcbops.so ---------------------
+# (the ten *_cuda_launcher symbols come from contrastboundary_b200/csrc/compat.cu instead of the reference's .cu files)
+CB=../contrastboundary_b200
+if [ -f $CB/libcbops.so ] && { [ ! -f $OUT/dropin/pointops_cuda.so ] || [ $CB/csrc/compat.cu -nt $OUT/dropin/pointops_cuda.so ]; }; then
+  PY=${PYTHON:-python}
+  TL=$($PY -c "import torch,os;print(os.path.join(os.path.dirname(torch.__file__),'lib'))")
+  mkdir -p $OUT/dropin
+  g++ -shared -o $OUT/dropin/pointops_cuda.so $OUT/obj/*_h.o -L$CB -l:libcbops.so -L$TL -ltorch -ltorch_cpu -ltorch_python -lc10 \
+      -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$TL -Wl,-rpath,'$ORIGIN/../../../contrastboundary_b200'
+fi
+
+# ---- the reference's Python model code, for tests that run it on top of this repo's operators -------------
+# copied (not committed: baseline/_ref is git-ignored) because /root/reference does not exist on the GPU box
+B=../baseline/_ref/pytorch
+if [ ! -f $B/model/blocks.py ]; then
+  mkdir -p $B/lib/pointops/functions $B/util
+  cp -r $REF/pytorch/model $B/
+  cp $REF/pytorch/lib/pointops/functions/*.py $B/lib/pointops/functions/
+  cp $REF/pytorch/util/config.py $REF/pytorch/util/voxelize.py $REF/pytorch/util/data_util.py $B/util/
+  chmod -R u+w $B
+  touch $B/lib/__init__.py $B/lib/pointops/__init__.py $B/util/__init__.py
+fi
+echo "[build_ref] ok: $(ls $OUT/*.so $OUT/dropin/*.so 2>/dev/null | tr '\n' ' ')"

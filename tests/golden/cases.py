@@ -115,6 +115,11 @@ def model_batch():
     return b
 
 
+def model_batch_cfg2():
+    """BASELINE configs[1]: 4 x 40960-point scenes — the first batch bench.py times (seed 5000)"""
+    return S.make_batch(4, 40960, 5000)
+
+
 def deterministic_init(model, seed=0):
     """Fill every parameter / BN buffer from a per-name seeded generator, so that the reference model,
     the oracle restatement and the product model (same state_dict names) get identical weights

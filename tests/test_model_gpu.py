@@ -1,6 +1,9 @@
 """GPU parity of the full network (product model on libcbops) against the golden vectors made by
-the REAL reference model code on CPU (tests/golden/model_ref.npz).  Tolerance: logits / loss
-1e-4 relative (BASELINE.json north_star); gradient norms 1e-3 relative (float scatter order)."""
+the REAL reference model code on CPU (tests/golden/model_ref.npz: 4096 + 3000 points; model_ref_cfg2.npz:
+the benchmark configuration, 4 x 40960 points, through the very object bench.py times — GraphTrainStep).
+Tolerance: logits / loss / latents 1e-4 relative (BASELINE.json north_star) against both the reference's
+float32 and float64 runs; gradients: error against the float64 run within GRAD_FACTOR x the reference's own
+float32 error (per parameter tensor)."""
 import json
 import os
 import sys
@@ -30,38 +33,64 @@ def run_product(fused):
     return ts.model, out, loss, stages
 
 
-def check_against_golden(mdl, out, loss, stages, g, tol):
-    ref_logits = g["logits"]
-    err = np.abs(out.detach().cpu().numpy() - ref_logits).max() / np.abs(ref_logits).max()
-    assert err < tol, f"logits rel err {err}"
-    l, rl = loss.detach().cpu().numpy(), g["loss"]
-    assert np.allclose(l, rl, rtol=tol, atol=1e-7), (l, rl)
-    for i in range(5):
-        a, b = stages["latent"][i].detach().cpu().numpy()[:64], g[f"latent/{i}"]
-        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-6) < tol * 5, f"latent {i}"
-    norms = json.loads(bytes(g["grad_norms_json"]).decode())
-    params = dict(mdl.named_parameters())
-    assert set(norms) == {n for n, p in params.items() if p.grad is not None}
-    worst = 0.0
-    for name, ref in norms.items():
+GRAD_FACTOR = 6.0     # product's gradient error vs float64 may be this many times the REFERENCE's own fp32 error ...
+GRAD_FLOOR = 3e-3     # ... or this, whichever is larger (parameters whose reference error is ~0)
+
+
+def _json(g, key):
+    return json.loads(bytes(g[key]).decode())
+
+
+def check_grads_against_f64(named_grads, g, report=None):
+    """named_grads: {name: gradient tensor}.  The yardstick is the float64 run of the REAL reference model; the
+    allowance per parameter is a multiple of the error the reference's own float32 run has against it
+    (tests/golden/make_golden_model.py explains why no flat 1e-4 exists for these gradients: the reference's own
+    fp32-vs-fp64 error is 5e-3 median, 4e-2 .. 6e-2 worst)."""
+    norms64, ref_err = _json(g, "f64/grad_norms_json"), _json(g, "ref32_err_json")
+    assert set(norms64) == set(named_grads), set(norms64) ^ set(named_grads)
+    rows = []
+    for name, n64 in norms64.items():
         if cases.grad_is_analytically_zero(name):
             continue
-        rel = abs(float(params[name].grad.norm()) - ref) / max(ref, 1e-6)
-        worst = max(worst, rel)
-        # gradients through the 3-channel BatchNorm of linear_p are differences of large terms: even the
-        # reference's own CUDA-vs-CPU runs differ by ~1e-2 there
-        # (measured run-to-run with float atomics: 2e-2 .. 6e-2), hence the loose bound for exactly these parameters
-        # every other gradient norm: measured spread 0.5e-2 .. 2.1e-2 over runs (float atomics, 40 layers) -> 4e-2
-        lim = 1e-1 if ("linear_p.0.weight" in name or "linear_p.1." in name) else 400 * tol
-        assert rel < lim, (name, rel)    # first-layer grads carry 40 layers of summation-order noise
-    for name in cases.GOLDEN_GRADS:
-        if "linear_p.0.weight" in name:
-            continue
-        a, b = params[name].grad.cpu().numpy(), g["grad/" + name]
-        # element-wise agreement up to ReLU-subgradient flips accumulated over 40 layers; direction must match
-        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-9) < 5e-2, name
+        ours = named_grads[name]
+        key = "f64/grad/" + name
+        if key in g.files:        # full tensor stored: error of the difference
+            err = float((ours.double().cpu() - torch.from_numpy(g[key]).double()).norm()) / max(n64, 1e-30)
+        else:                     # norm only
+            err = abs(float(ours.double().norm()) - n64) / max(n64, 1e-30)
+        lim = max(GRAD_FACTOR * ref_err[name], GRAD_FLOOR)
+        rows.append((err / lim, err, ref_err[name], name))
+    rows.sort(reverse=True)
+    if report is not None:
+        report.extend(rows)
+    print("worst gradient errors vs float64 (ratio to allowance, ours, reference fp32's own):")
+    for r in rows[:8]:
+        print("  %.2f  %.2e  %.2e  %s" % r)
+    print("  median ours %.2e, median reference-fp32 %.2e" % (float(np.median([r[1] for r in rows])),
+                                                             float(np.median([r[2] for r in rows]))))
+    assert rows[0][0] < 1.0, rows[0]
+    # and on the whole the product must be as accurate as the reference's fp32 run, not GRAD_FACTOR times worse
+    assert np.median([r[1] for r in rows]) < 2.0 * np.median([r[2] for r in rows]) + 1e-4
+
+
+def check_against_golden(mdl, out, loss, stages, g, tol):
+    rows = g["rows"] if "rows" in g.files else None
+    o = out.detach().cpu().numpy()
+    o = o if rows is None else o[rows]
+    for tag in ("", "f64/"):            # the reference's fp32 run and its fp64 run: both within tol
+        ref_logits = g[tag + "logits"]
+        err = np.abs(o - ref_logits).max() / np.abs(ref_logits).max()
+        assert err < tol, f"logits rel err {err} ({tag or 'f32'})"
+        l, rl = loss.detach().cpu().numpy(), g[tag + "loss"]
+        assert np.allclose(l, rl, rtol=tol, atol=1e-7), (l, rl)
+        for i in range(5):
+            a, b = stages["up"][i]["latent"].detach().cpu().numpy()[:64], g[tag + f"latent/{i}"]
+            assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-6) < tol * 5, f"latent {i}"
+    check_grads_against_f64({n: p.grad for n, p in mdl.named_parameters() if p.grad is not None}, g)
+    for name in cases.GOLDEN_GRADS:     # direction of the stored full gradients
+        a, b = dict(mdl.named_parameters())[name].grad.cpu().numpy(), g["f64/grad/" + name]
         cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
-        assert cos > 0.9995, (name, cos)
+        assert cos > 0.998, (name, cos)
 
 
 def test_unfused_model_matches_reference(golden_dir):
@@ -110,3 +139,54 @@ def test_fused_cbl_matches_unfused():
         assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0]) + 1e-9, (l, res[True][0], res[False][0])
         ref = res[False][1]
         assert float((res[True][1] - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-12, l
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the benchmark configuration (BASELINE configs[1]: 4 x 40960 points), through GraphTrainStep
+# ----------------------------------------------------------------------------------------------------------
+def _cfg2_engine():
+    from contrastboundary_b200 import engine, model
+    dev = torch.device("cuda", 0)
+    # lr = 0: the optimiser runs (it is part of the step) but the parameters stay at the golden's initialisation
+    gts = engine.GraphTrainStep(model.CBLConfig(), dev, eager_warmup=1, lr=0.0, momentum=0.0, weight_decay=0.0, seed=0)
+    cases.deterministic_init(gts.model, 0)
+    hb = engine.host_batch_from_numpy(cases.model_batch_cfg2(), pin=False)
+    return gts, engine.to_device(hb, dev)
+
+
+def test_benchmark_config_graph_replay_matches_reference(golden_dir):
+    """the kernels that produce the bench number (cluster FPS, tensor-core linears inside the network, graph replay)
+    against the REAL reference model at 4 x 40960 points: loss 1e-4, gradients at the reference's own fp32 accuracy"""
+    g = np.load(os.path.join(golden_dir, "model_ref_cfg2.npz"))
+    gts, batch = _cfg2_engine()
+    losses, flats = [], []
+    for s in range(4):                   # step 0 eager (stream mode), step 1 captures + replays, steps 2-3 replay
+        losses.append(gts.step(batch).cpu().numpy())
+        if gts._packed:
+            flats.append(gts.flat.clone())
+    assert gts.graph_error is None, gts.graph_error
+    assert len(flats) == 3 and gts.launches_per_step > 100
+    for tag in ("", "f64/"):
+        for l in losses:
+            np.testing.assert_allclose(l, g[tag + "loss"], rtol=1e-4, atol=1e-7)
+    names = {id(p): n for n, p in gts.model.named_parameters()}
+    grads, o = {}, 0
+    for p in gts._gparams:
+        grads[names[id(p)]] = flats[-1][o:o + p.numel()].view_as(p)
+        o += p.numel()
+    check_grads_against_f64(grads, g)
+    # replay-to-replay reproducibility of the packed gradient
+    d = float((flats[-1] - flats[-2]).norm() / flats[-1].norm())
+    nbits = int((flats[-1] != flats[-2]).sum())
+    print(f"replay-to-replay gradient difference: rel {d:.3e}, {nbits} of {flats[-1].numel()} elements differ")
+    assert d < 2e-2
+
+
+def test_benchmark_config_stream_mode_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_ref_cfg2.npz"))
+    gts, batch = _cfg2_engine()
+    out, stages = gts.model(batch, None)
+    loss = gts.criterion(out, batch["point_labels"], stages)
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    check_against_golden(gts.model, out, loss, stages, g, 1e-4)

@@ -150,8 +150,8 @@ def test_oracle_gather_ops_consistency():
 
 def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "cbops.h")).read()
-    names = sorted(set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", hdr)))
-    assert len(names) >= 15
+    names = sorted(set(re.findall(r"\b(cb_[a-z0-9_]+|[a-z]+(?:_forward|_backward)?_cuda_launcher)\s*\(", hdr)))
+    assert len(names) >= 15 and sum(n.endswith("_cuda_launcher") for n in names) == 10
     lib_path = os.path.join(ROOT, "contrastboundary_b200", "libcbops.so")
     if not os.path.exists(lib_path):
         from contrastboundary_b200 import build
