@@ -316,6 +316,27 @@ int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const 
 int cb_pt_set_tensor_cores(int on);
 
 /* ------------------------------------------------------------------------------------------------
+ * f1  the step BEFORE the path, on the device (dataprep.cu): voxelize + data_prepare + collate
+ *     pytorch/util/voxelize.py:4-16,38-56   pytorch/util/data_util.py:45-92   pytorch/util/s3dis.py:94-130
+ * coord / feat are float32 or float64 device arrays (coord_is_f64); the arithmetic (shift, coord / voxel_size, floor,
+ * squared crop distance) runs in that dtype, as NumPy's does; outputs are float32 / int64 like the torch tensors the
+ * reference builds.  Bit-exact: voxel keys (FNV64-1A), occupied voxels, counts, voxel order, crop distances, both
+ * min-shifts, feat / 255.  Defined modulo (reference = NumPy global RNG / unstable sort): the point kept per voxel,
+ * the order among equal crop distances, the shuffle permutation.  See dataprep.cu for every argument.
+ * cb_voxelize      = voxelize(coord, voxel_size, 'fnv', mode=1) -> idx_sort (n), count (first *nvox entries), *nvox
+ * cb_data_prepare  = data_prepare of ONE cloud, appended to a batch buffer at the DEVICE-side row offset row_offset[0];
+ *                    row_offset[1] = row_offset[0] + kept count (chain the calls of a batch over a (B+1)-long array
+ *                    starting at 0: its tail is the collate `offset`).  No device->host read anywhere.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cb_data_prepare_workspace_bytes(int n);
+int cb_voxelize(const void *coord, int coord_is_f64, int n, double voxel_size, int *idx_sort, int *count, int *nvox,
+                unsigned long long *keys_sorted, void *workspace, size_t workspace_bytes, void *stream);
+int cb_data_prepare(const void *coord, const void *feat, int coord_is_f64, int fdim, const long long *label, int n,
+                    double voxel_size, int voxel_max, int pick_mode, int centre_mode, int shuffle, unsigned long long seed,
+                    float feat_div, int *row_offset, int out_capacity, float *out_coord, float *out_feat,
+                    long long *out_label, int *out_index, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The reference's OWN native ABI (compat.cu): the ten `extern "C"` launchers its pybind glue calls,
  * with the reference's exact names and argument lists, so that the unmodified glue
  * (pytorch/lib/pointops/src/<op>/<op>_cuda.cpp + pointops_api.cpp) links against libcbops.so in place of

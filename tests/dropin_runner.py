@@ -71,18 +71,9 @@ def main(mode):
     res["loss_ref"] = [float(x) for x in g["loss"]]
     res["latent_err"] = [float(np.abs(stage_list["up"][i]["latent"].detach().cpu().numpy()[:64] - g[f"latent/{i}"]).max()
                                / max(np.abs(g[f"latent/{i}"]).max(), 1e-6)) for i in range(5)]
-    norms64 = json.loads(bytes(g["f64/grad_norms_json"]).decode())
-    ref_err = json.loads(bytes(g["ref32_err_json"]).decode())
-    worst = (0.0, "")
-    for name, p in model.named_parameters():
-        if p.grad is None or cases.grad_is_analytically_zero(name):
-            continue
-        err = abs(float(p.grad.double().norm()) - norms64[name]) / max(norms64[name], 1e-30)
-        ratio = err / max(6.0 * ref_err[name], 3e-3)
-        if ratio > worst[0]:
-            worst = (ratio, name)
-    res["grad_worst_ratio"], res["grad_worst_name"] = worst
-    import ctypes
+    rows, med, med_ref = cases.grad_rows_vs_f64({n: p.grad for n, p in model.named_parameters() if p.grad is not None}, g)
+    res["grad_worst_ratio"], res["grad_worst"] = rows[0][0], ["%.2f %.2e %.2e %s" % r for r in rows[:5]]
+    res["grad_median"], res["grad_median_ref"] = med, med_ref
     loaded = [l.split()[-1] for l in open("/proc/self/maps") if l.rstrip().endswith(".so") and ("cbops" in l or "pointops_cuda" in l)]
     res["loaded"] = sorted(set(os.path.relpath(x, ROOT) for x in loaded))
     print("DROPIN " + json.dumps(res))

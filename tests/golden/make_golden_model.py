@@ -12,8 +12,8 @@ Each case runs the reference twice on identical inputs and weights (cases.determ
 Why both: the gradient of this network is badly conditioned in fp32 (40 layers of train-mode BatchNorm, ReLU
 flips near 0, a 3-channel BatchNorm inside every attention layer): the reference's own fp32 run differs from
 its own fp64 run by up to several 1e-2 (relative, per parameter tensor) although losses agree to 1e-6.  The
-golden therefore stores, per parameter, the float64 gradient norm and the reference's own fp32 error
-`ref32_err = |g32 - g64| / |g64|`; the GPU tests require the product's error against float64 to stay within
+golden therefore stores, per parameter, the float64 gradient norm and the reference's own fp32 errors
+`ref32_err = |g32 - g64| / |g64|` and `ref32_norm_err = | |g32| - |g64| | / |g64|`; the GPU tests require the product's error against float64 to stay within
 a small multiple of the reference's own.
 
 Stored: `logits` / `loss` / `grad/<name>` / `grad_norms_json` / `latent/<i>` from the float32 run (small case:
@@ -97,6 +97,8 @@ def generate(pts, CfgNode, b, out_path, rows=None):
         res[tag + "bn_running_mean/enc1.0.bn"] = model.enc1[0].bn.running_mean.numpy().astype(np.float32)
     err = {n: float((grads[""][n] - g).norm() / g.norm().clamp(min=1e-300)) for n, g in grads["f64/"].items()}
     res["ref32_err_json"] = np.frombuffer(json.dumps(err).encode(), dtype=np.uint8)
+    nerr = {n: float(abs(grads[""][n].norm() - g.norm()) / g.norm().clamp(min=1e-300)) for n, g in grads["f64/"].items()}
+    res["ref32_norm_err_json"] = np.frombuffer(json.dumps(nerr).encode(), dtype=np.uint8)
     if rows is not None:
         res["rows"] = rows
     np.savez_compressed(out_path, **res)

@@ -31,6 +31,7 @@ def _check(res):
         assert abs(a - b) <= 1e-4 * abs(b) + 1e-7, res
     assert max(res["latent_err"]) < 5e-4, res
     assert res["grad_worst_ratio"] < 1.0, res
+    assert res["grad_median"] < 2.0 * res["grad_median_ref"] + 1e-4, res
     assert any("libcbops.so" in l for l in res["loaded"]), res
 
 

@@ -2,8 +2,8 @@
 the REAL reference model code on CPU (tests/golden/model_ref.npz: 4096 + 3000 points; model_ref_cfg2.npz:
 the benchmark configuration, 4 x 40960 points, through the very object bench.py times — GraphTrainStep).
 Tolerance: logits / loss / latents 1e-4 relative (BASELINE.json north_star) against both the reference's
-float32 and float64 runs; gradients: error against the float64 run within GRAD_FACTOR x the reference's own
-float32 error (per parameter tensor)."""
+float32 and float64 runs; gradients: error against the float64 run within cases.GRAD_FACTOR x the reference's own
+float32 error on that parameter tensor (or the reference's 99th-percentile error): cases.grad_rows_vs_f64."""
 import json
 import os
 import sys
@@ -33,44 +33,8 @@ def run_product(fused):
     return ts.model, out, loss, stages
 
 
-GRAD_FACTOR = 6.0     # product's gradient error vs float64 may be this many times the REFERENCE's own fp32 error ...
-GRAD_FLOOR = 3e-3     # ... or this, whichever is larger (parameters whose reference error is ~0)
-
-
-def _json(g, key):
-    return json.loads(bytes(g[key]).decode())
-
-
-def check_grads_against_f64(named_grads, g, report=None):
-    """named_grads: {name: gradient tensor}.  The yardstick is the float64 run of the REAL reference model; the
-    allowance per parameter is a multiple of the error the reference's own float32 run has against it
-    (tests/golden/make_golden_model.py explains why no flat 1e-4 exists for these gradients: the reference's own
-    fp32-vs-fp64 error is 5e-3 median, 4e-2 .. 6e-2 worst)."""
-    norms64, ref_err = _json(g, "f64/grad_norms_json"), _json(g, "ref32_err_json")
-    assert set(norms64) == set(named_grads), set(norms64) ^ set(named_grads)
-    rows = []
-    for name, n64 in norms64.items():
-        if cases.grad_is_analytically_zero(name):
-            continue
-        ours = named_grads[name]
-        key = "f64/grad/" + name
-        if key in g.files:        # full tensor stored: error of the difference
-            err = float((ours.double().cpu() - torch.from_numpy(g[key]).double()).norm()) / max(n64, 1e-30)
-        else:                     # norm only
-            err = abs(float(ours.double().norm()) - n64) / max(n64, 1e-30)
-        lim = max(GRAD_FACTOR * ref_err[name], GRAD_FLOOR)
-        rows.append((err / lim, err, ref_err[name], name))
-    rows.sort(reverse=True)
-    if report is not None:
-        report.extend(rows)
-    print("worst gradient errors vs float64 (ratio to allowance, ours, reference fp32's own):")
-    for r in rows[:8]:
-        print("  %.2f  %.2e  %.2e  %s" % r)
-    print("  median ours %.2e, median reference-fp32 %.2e" % (float(np.median([r[1] for r in rows])),
-                                                             float(np.median([r[2] for r in rows]))))
-    assert rows[0][0] < 1.0, rows[0]
-    # and on the whole the product must be as accurate as the reference's fp32 run, not GRAD_FACTOR times worse
-    assert np.median([r[1] for r in rows]) < 2.0 * np.median([r[2] for r in rows]) + 1e-4
+def check_grads_against_f64(named_grads, g, what=""):
+    return cases.assert_grads_vs_f64(named_grads, g, what)
 
 
 def check_against_golden(mdl, out, loss, stages, g, tol):

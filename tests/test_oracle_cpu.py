@@ -188,3 +188,31 @@ def test_boundary_mask_oracle_matches_real_reference(golden_dir):
         assert np.array_equal(bv, g[f"{case}/bound_valid"]) and np.array_equal(pv, g[f"{case}/plain_valid"])
         c = boundary.get_boundary_mask(lab, idx, valid_mask=valid, get_cnt=True)
         assert np.array_equal(c, g[f"{case}/cnt"])
+
+
+# ---- batch preparation restatement (oracle/dataprep.py) pinned by the reference's own functions ----------
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_dataprep_restatement_matches_reference_golden(dt):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    from oracle import dataprep as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dataprep_ref.npz"))
+    coord, feat, label = cases.raw_cloud(dt)
+    c0 = coord - coord.min(0)
+    key = D.voxel_keys(c0, cases.DATAPREP_VOXEL)
+    assert np.array_equal(key, g[f"{dt}/keys"])
+    idx_sort, count = D.voxelize(c0, cases.DATAPREP_VOXEL, mode=1)
+    assert np.array_equal(count, g[f"{dt}/count"])
+    assert np.array_equal(np.unique(key), g[f"{dt}/unique_keys"])
+    for tag, vmax, split, shuf in (("val_nocrop", None, "val", False), ("val_crop", cases.DATAPREP_VOXEL_MAX, "val", False),
+                                   ("train_crop", cases.DATAPREP_VOXEL_MAX, "train", True)):
+        np.random.seed(cases.DATAPREP_SEED)
+        c, f, l, _ = D.data_prepare(coord, feat, label, split=split, voxel_size=cases.DATAPREP_VOXEL, voxel_max=vmax,
+                                    shuffle_index=shuf, rng="numpy")
+        assert np.array_equal(c.view(np.uint32), g[f"{dt}/{tag}/coord"].view(np.uint32)), tag
+        assert np.array_equal(f.view(np.uint32), g[f"{dt}/{tag}/feat"].view(np.uint32)), tag
+        assert np.array_equal(l, g[f"{dt}/{tag}/label"]), tag
+    # deterministic variant: one point per voxel, voxels in ascending key order, crop = the voxel_max nearest
+    c, f, l, index = D.data_prepare(coord, feat, label, split="val", voxel_size=cases.DATAPREP_VOXEL, voxel_max=cases.DATAPREP_VOXEL_MAX)
+    assert len(set(key[index].tolist())) == cases.DATAPREP_VOXEL_MAX == len(index)
