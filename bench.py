@@ -31,10 +31,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json configs[] (1-based): 2 = PT+CBL (the metric's "
+                    "configuration, default), 3 = ConvNet(AdaptiveWeight)+CBL on the device-built radius pyramid")
+    ap.add_argument("--sweep", action="store_true", help="config 5: the KNN+gather grid N x K x C -> profiles/knn_gather_sweep.json")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=360.0)
     ap.add_argument("--no-pipeline", action="store_true", help="compute each batch's geometry inside its own step (no look-ahead)")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python (stream mode) instead of replaying CUDA graphs")
     return ap.parse_args()
@@ -85,20 +89,26 @@ class Clocks:
 # reference arm / cpu_baseline: the reference's network restated op-by-op (oracle/ref_model.py) on
 # the box's host cores with the C restatement of its kernels (oracle/) — bounded sample.
 # --------------------------------------------------------------------------------------------------
+WORKLOAD = (f"Point-Transformer+CBL fwd+bwd+SGD, {SCENES_PER_GPU} x {POINTS_PER_SCENE}-pt synthetic S3DIS-shape scenes per GPU, "
+            f"K=16 (stage 0: 8), C=32->512, CBL nsample [36,24,24,24,24]")
+
+
 def cpu_reference_run(steps, warmup, budget_s):
+    """the reference's CPU path: its own model code (oracle/reference_runner.py) on torch-CPU + the C/OpenMP restatement of
+    its pointops kernels, all host threads.  Runs the FULL workload (4 x 40960 points per step, the batches bench.py's own arm
+    times) whenever (steps + warmup) of them fit `budget_s`; otherwise a bounded sample (fewer scenes, then fewer points)."""
     import torch
     from contrastboundary_b200 import synthetic
     import oracle
-    from oracle import cpu_pointops, ref_model
+    from oracle import reference_runner
     cores = os.cpu_count() or 1
     torch.manual_seed(0)
-    model = ref_model.RefSeg(cpu_pointops)
-    crit = ref_model.RefLoss(cpu_pointops)
+    model, crit, what = reference_runner.build("cpu")
     opt = torch.optim.SGD(model.parameters(), lr=0.5, momentum=0.9, weight_decay=1e-4)
     model.train()
 
-    def one(n_pts, seed):
-        b = synthetic.make_batch(1, [n_pts], seed)
+    def one(n_scenes, n_pts, seed):
+        b = synthetic.make_batch(n_scenes, n_pts, seed)
         inputs = {k: torch.from_numpy(b[k]) for k in ("points", "features", "offset")}
         target = torch.from_numpy(b["point_labels"])
         t0 = time.perf_counter()
@@ -111,31 +121,37 @@ def cpu_reference_run(steps, warmup, budget_s):
 
     # "all the host threads it can use": pick the thread count that maximises throughput on a probe
     # (torch's CPU kernels on these small (n,k,c) tensors get SLOWER when oversubscribed across sockets)
-    best_t, t_probe = cores, None
+    best_t, t8, t4 = cores, None, None
     for t in sorted({min(cores, x) for x in (8, 16, 32, 64, cores)}):
         torch.set_num_threads(t)
         oracle.set_num_threads(t)
-        one(4096, 0)
-        dt = one(8192, 1)
-        if t_probe is None or dt < t_probe:
-            best_t, t_probe = t, dt
+        d4 = one(1, 4096, 0)
+        d8 = one(1, 8192, 1)
+        if t8 is None or d8 < t8:
+            best_t, t8, t4 = t, d8, d4
     cores = best_t
     torch.set_num_threads(cores)
     oracle.set_num_threads(cores)
-    n_pts = POINTS_PER_SCENE
-    # cost model: brute-force search ~ n^2, dense ~ n  -> be conservative with n^2
-    est_full = t_probe * (POINTS_PER_SCENE / 8192.0) ** 2
+    # cost model t(n) = a n + b n^2 per scene (dense part linear, brute-force searches quadratic), fitted on the two probes
+    bq = max((t8 - 2.0 * t4) / (8192.0 ** 2 - 2.0 * 4096.0 ** 2), 0.0)
+    al = max((t4 - bq * 4096.0 ** 2) / 4096.0, 1e-9)
+    est = lambda sc, n: sc * (al * n + bq * n * n)
     total = max(steps + warmup, 1)
-    if est_full * total > budget_s:
-        n_pts = int(max(4096, min(POINTS_PER_SCENE, 8192 * (budget_s / total / max(t_probe, 1e-3)) ** 0.5)))
-        n_pts = (n_pts // 1024) * 1024
+    n_scenes, n_pts = SCENES_PER_GPU, POINTS_PER_SCENE
+    while est(n_scenes, n_pts) * total > budget_s and n_scenes > 1:
+        n_scenes //= 2
+    while est(n_scenes, n_pts) * total > budget_s and n_pts > 4096:
+        n_pts -= 4096
+    full = (n_scenes, n_pts) == (SCENES_PER_GPU, POINTS_PER_SCENE)
     for w in range(warmup):
-        one(n_pts, 100 + w)
-    ts = [one(n_pts, 200 + s) for s in range(steps)]
+        one(n_scenes, n_pts, 5000 + w)
+    ts = [one(n_scenes, n_pts, 5000 + warmup + s) for s in range(steps)]
     dt = float(np.sum(ts))
-    return {"value": steps * n_pts / dt, "ms_per_step": 1e3 * dt / steps, "cores": cores, "n_pts": n_pts,
-            "sample": f"1 scene x {n_pts} pts per step (full config is 4 x {POINTS_PER_SCENE}); fwd+bwd+SGD of the "
-                      f"restated reference network, torch CPU ({cores} threads) + C/OpenMP restatement of pointops"}
+    sample = (("the full workload: " if full else f"bounded sample (full config is {SCENES_PER_GPU} x {POINTS_PER_SCENE}): ")
+              + f"{n_scenes} scene(s) x {n_pts} pts per step; fwd+bwd+SGD of {what}, torch CPU ({cores} threads) + C/OpenMP "
+                f"restatement of the reference's pointops kernels")
+    return {"value": steps * n_scenes * n_pts / dt, "ms_per_step": 1e3 * dt / steps, "cores": cores, "n_pts": n_pts,
+            "n_scenes": n_scenes, "full": full, "sample": sample}
 
 
 def run_reference(args):
@@ -147,12 +163,77 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PT+CBL fwd+bwd+SGD, reference CPU path (oracle port), bounded sample", "sample": r["sample"]},
+        "config": {"workload": WORKLOAD, "global_batch_scenes": r["n_scenes"], "points_per_scene": r["n_pts"],
+                   "full_workload": r["full"], "parallelism": "host cores", "sample": r["sample"]},
         "cpu_baseline": {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# gpu_baseline = B1 of BASELINE.md §3, the north star's >= 10x denominator: the reference's own model code on the
+# reference's own pointops CUDA kernels (compiled unmodified for sm_100a, oracle/_ref/pointops_cuda.so), same B200, same
+# batches, same step.  Runs in a child process (`--impl stock-gpu`) AFTER this arm's timed regions.
+# --------------------------------------------------------------------------------------------------
+def run_stock_gpu(args):
+    import torch
+    from contrastboundary_b200 import synthetic
+    from oracle import reference_runner
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    model, crit, what = reference_runner.build("stock-gpu")
+    model, crit = model.to(dev), crit.to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.5, momentum=0.9, weight_decay=1e-4)
+    model.train()
+    batches = []
+    for i in range(3):
+        b = synthetic.make_batch(SCENES_PER_GPU, POINTS_PER_SCENE, 5000 + i)
+        batches.append(({k: torch.from_numpy(b[k]).to(dev) for k in ("points", "features", "offset")},
+                        torch.from_numpy(b["point_labels"]).to(dev)))
+
+    def step(i):
+        inputs, target = batches[i % len(batches)]
+        opt.zero_grad(set_to_none=True)
+        out, up = model(inputs)
+        loss = crit(out, target, up)
+        loss.sum().backward()
+        opt.step()
+        return loss
+
+    for w in range(max(args.warmup, 1)):
+        step(w)
+    torch.cuda.synchronize()
+    clocks = Clocks(dev.index)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in range(args.steps):
+        loss = step(s_)
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    loaded = sorted({l.split()[-1] for l in open("/proc/self/maps") if "pointops_cuda" in l or "libcbops" in l})
+    print("STOCK " + json.dumps({
+        "what": f"B1: {what} + the reference's stock pointops CUDA kernels (oracle/_ref/pointops_cuda.so, sm_100a), torch CUDA fp32",
+        "value": SCENES_PER_GPU * POINTS_PER_SCENE / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "workload": WORKLOAD, "clocks": clk, "loss": [round(float(x), 5) for x in loss],
+        "native_loaded": [os.path.relpath(x, ROOT) for x in loaded]}))
+
+
+def gpu_baseline_subprocess(steps=5, warmup=2, timeout=600):
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "stock-gpu", "--steps", str(steps), "--warmup", str(warmup)],
+                           capture_output=True, text=True, timeout=timeout)
+        for l in r.stdout.splitlines():
+            if l.startswith("STOCK "):
+                return json.loads(l[6:])
+        return {"unavailable": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:                                   # the baseline must never take the bench down
+        return {"unavailable": repr(e)[:300]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -353,8 +434,7 @@ def run_ours(args):
         "metric": METRIC, "value": pts_per_step * args.steps / t_val, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_val / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Point-Transformer+CBL fwd+bwd+SGD, {SCENES_PER_GPU} x {POINTS_PER_SCENE}-pt synthetic "
-                               f"S3DIS-shape scenes per GPU, K=16 (stage 0: 8), C=32->512, CBL nsample [36,24,24,24,24]",
+        "config": {"workload": WORKLOAD,
                    "global_batch_scenes": world * SCENES_PER_GPU, "parallelism": f"dp{world}",
                    "fused": bool(cfg.fused),
                    "launch_mode": ("CUDA graphs: geometry graph + network(fwd+loss+bwd) graph per slot, 2 slots; optimizer"
@@ -371,8 +451,13 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_roofline:
         line["roofline"] = roofline_knn_gather(torch, dev)
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        # B1: the reference's stock pointops CUDA build on this same GPU, after the timed regions, in a child process
+        del ts
+        torch.cuda.empty_cache()
+        line["gpu_baseline"] = gpu_baseline_subprocess()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(1, 0, 60.0)
+        r = cpu_reference_run(1, 0, 45.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
         print(json.dumps(line))
@@ -380,9 +465,97 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------
+# config 5: KNN + gather microbench grid -> profiles/knn_gather_sweep.json
+# --------------------------------------------------------------------------------------------------
+def run_sweep(args):
+    import torch
+    from contrastboundary_b200 import _lib, fused, synthetic
+    _lib.lib()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_r = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+
+    def timed(fn, iters):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            flush_r.sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            fn()
+            b.record(st)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return float(np.mean(ts))
+
+    clocks = Clocks(0)
+    clocks.start()
+    points = []
+    for e in range(14, 21):
+        n = 1 << e
+        xyz = torch.from_numpy(synthetic.make_scene(n, 4242 + e)[0]).to(dev)
+        off = torch.tensor([n], dtype=torch.int32, device=dev)
+        for c in (64, 256):
+            feat = torch.randn(n, c, device=dev)
+            for k in (16, 32, 64):
+                alg = 12 * n + 4 * n * c + 8 * n * k + 4 * n * k * c
+                rec = {"N": n, "K": k, "C": c, "alg_bytes": alg}
+                try:
+                    grid = fused.grid_build(xyz, off, k)
+                    out = fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off)
+                    iters = 10 if alg < (4 << 30) else 3
+                    tk = timed(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, out), iters)
+                    del out
+                    tc = timed(lambda: fused.knn_gather(k, xyz, xyz, feat, off, off), iters)
+                    rec.update({"kernel_us": tk * 1e6, "kernel_gbs": alg / tk / 1e9, "kernel_frac": alg / tk / 1e9 / peak,
+                                "operator_us": tc * 1e6, "operator_gbs": alg / tc / 1e9, "operator_frac": alg / tc / 1e9 / peak})
+                    del grid
+                except Exception as ex:                      # e.g. the 68.7 GB output of N=2^20, K=64, C=256 on a busy GPU
+                    rec["skipped"] = repr(ex)[:200]
+                    torch.cuda.empty_cache()
+                points.append(rec)
+                print(json.dumps(rec), file=sys.stderr, flush=True)
+            del feat
+            torch.cuda.empty_cache()
+    clk = clocks.stop()
+    ok = [p for p in points if "kernel_frac" in p]
+    res = {"what": "config 5: fused KNN + neighbour-feature gather (cb_knn_gather), single synthetic S3DIS-shape scene of N points, "
+                   "self query; kernel = cb_knn_gather_grid on a prebuilt grid, operator = cb_knn_gather incl. the grid build",
+           "alg_bytes": "12N + 4NC + 8NK + 4NKC (SURVEY 8d)", "peak_gbs": peak, "peak_source": peak_src,
+           "l2": "between timed iterations a 256 MiB buffer is zeroed and another is read", "clocks": clk, "points": points,
+           "summary": {"n_points": len(points), "n_measured": len(ok),
+                       "operator_frac_min": min(p["operator_frac"] for p in ok) if ok else None,
+                       "operator_frac_median": float(np.median([p["operator_frac"] for p in ok])) if ok else None,
+                       "operator_frac_max": max(p["operator_frac"] for p in ok) if ok else None,
+                       "points_at_or_above_0.70_operator": sum(p["operator_frac"] >= 0.70 for p in ok),
+                       "points_at_or_above_0.70_kernel": sum(p["kernel_frac"] >= 0.70 for p in ok)}}
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "profiles", "knn_gather_sweep.json"), "w"), indent=1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "knn_gather_sweep.json"), "w"), indent=1)
+    print(json.dumps({"sweep": "profiles/knn_gather_sweep.json", **res["summary"]}))
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.sweep:
+        run_sweep(a)
+    elif a.impl == "reference":
         run_reference(a)
+    elif a.impl == "stock-gpu":
+        run_stock_gpu(a)
+    elif a.config == 3:
+        from contrastboundary_b200 import bench_convnet
+        bench_convnet.run(a, Clocks, ROOT)
     else:
         run_ours(a)

@@ -71,9 +71,10 @@ def main(mode):
     res["loss_ref"] = [float(x) for x in g["loss"]]
     res["latent_err"] = [float(np.abs(stage_list["up"][i]["latent"].detach().cpu().numpy()[:64] - g[f"latent/{i}"]).max()
                                / max(np.abs(g[f"latent/{i}"]).max(), 1e-6)) for i in range(5)]
-    rows, med, med_ref = cases.grad_rows_vs_f64({n: p.grad for n, p in model.named_parameters() if p.grad is not None}, g)
-    res["grad_worst_ratio"], res["grad_worst"] = rows[0][0], ["%.2f %.2e %.2e %s" % r for r in rows[:5]]
-    res["grad_median"], res["grad_median_ref"] = med, med_ref
+    rep = cases.grad_report_vs_f64({n: p.grad for n, p in model.named_parameters() if p.grad is not None}, g)
+    cases.print_grad_report(rep, mode)
+    res["grad_failures"] = cases.grad_failures(rep)
+    res["grad_quantiles"] = {str(q): v for q, v in rep["quantiles"].items()}
     loaded = [l.split()[-1] for l in open("/proc/self/maps") if l.rstrip().endswith(".so") and ("cbops" in l or "pointops_cuda" in l)]
     res["loaded"] = sorted(set(os.path.relpath(x, ROOT) for x in loaded))
     print("DROPIN " + json.dumps(res))

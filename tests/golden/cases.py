@@ -182,48 +182,79 @@ def grad_is_analytically_zero(name):
 
 
 # ---- gradient parity against the float64 run of the REAL reference model ------------------------------
-GRAD_FACTOR = 3.0
+GRAD_QUANTILES = (50, 90, 99)      # compared quantiles of the per-tensor gradient error
+GRAD_FACTOR = 2.0                  # ours may be at most this many times the reference's own fp32 error at each quantile
+FLIP_FRACTION = 0.002              # components of a stored gradient tensor that may sit on a flipped ReLU sub-gradient
 
 
-def grad_rows_vs_f64(named_grads, g):
-    """named_grads {name: torch gradient}, g = np.load(model_ref*.npz).  Yardstick: the reference model run in float64.
-    Allowance per parameter tensor: GRAD_FACTOR x the error the reference's OWN float32 run has on that tensor, or the
-    99th percentile of the reference's own fp32 errors over all tensors, whichever is larger (these gradients are
-    ill-conditioned in fp32 — make_golden_model.py — and WHICH tensors get the large errors differs between two fp32
-    realisations, e.g. the reference on CPU vs the reference on GPU).  Error = |g - g64| / |g64| where the golden stores
-    the full float64 tensor (GOLDEN_GRADS), else | |g| - |g64| | / |g64|.
-    -> rows (err / allowance, err, reference's own err, name) sorted worst first, median ours, median reference."""
+def grad_report_vs_f64(named_grads, g):
+    """named_grads {name: torch gradient}, g = np.load(model_ref*.npz).  Yardstick: the REAL reference model run in float64.
+
+    The gradients of this network are ill-conditioned in fp32 (make_golden_model.py): the reference's OWN float32 run is
+    5e-4 (median) .. 3e-2 (worst tensor) away from its float64 run, and WHICH tensors carry the large errors differs
+    between two fp32 realisations (the reference on CPU vs the reference on torch-CUDA already disagree tensor by tensor).
+    So the comparison is between error DISTRIBUTIONS over the ~440 parameter tensors: at every quantile in
+    GRAD_QUANTILES the product's error | |g| - |g64| | / |g64| may be at most GRAD_FACTOR x the reference-fp32 run's.
+    For the tensors stored in full (GOLDEN_GRADS) the element-wise error |g - g64| / |g64| is checked too, after
+    discarding the FLIP_FRACTION largest component differences (a ReLU whose pre-activation is within rounding of 0 takes
+    the other sub-gradient: one component jumps, the rest agree)."""
     import json
+    import math
     import numpy as np
     import torch
     ld = lambda k: json.loads(bytes(g[k]).decode())
     norms64, ref_d, ref_n = ld("f64/grad_norms_json"), ld("ref32_err_json"), ld("ref32_norm_err_json")
     assert set(norms64) == set(named_grads), set(norms64) ^ set(named_grads)
     live = [n for n in norms64 if not grad_is_analytically_zero(n)]
-    p99_d = float(np.percentile([ref_d[n] for n in live], 99))
-    p99_n = float(np.percentile([ref_n[n] for n in live], 99))
-    rows, ours_n = [], []
+    ours_n, full = {}, []
     for name in live:
         n64 = max(norms64[name], 1e-30)
         gr = named_grads[name].detach().double().cpu()
-        en = abs(float(gr.norm()) - n64) / n64
-        ours_n.append(en)
+        ours_n[name] = abs(float(gr.norm()) - n64) / n64
         key = "f64/grad/" + name
         if key in g.files:
-            err, ref, p99 = float((gr - torch.from_numpy(g[key]).double()).norm()) / n64, ref_d[name], p99_d
-        else:
-            err, ref, p99 = en, ref_n[name], p99_n
-        rows.append((err / max(GRAD_FACTOR * ref, p99), err, ref, name))
-    rows.sort(reverse=True)
-    return rows, float(np.median(ours_n)), float(np.median([ref_n[n] for n in live]))
+            d = (gr - torch.from_numpy(g[key]).double()).reshape(-1)
+            r = max(1, int(math.ceil(FLIP_FRACTION * d.numel())))
+            a = d.abs().sort(descending=True).values
+            full.append({"name": name, "err": float(d.norm()) / n64, "err_robust": float(a[r:].norm()) / n64, "dropped": r,
+                         "top_share": float(a[0] ** 2 / max(float((a ** 2).sum()), 1e-300)), "ref_err": ref_d[name]})
+    qs = {q: (float(np.percentile(list(ours_n.values()), q)), float(np.percentile([ref_n[n] for n in live], q)))
+          for q in GRAD_QUANTILES + (100,)}
+    worst = sorted(((ours_n[n], ref_n[n], n) for n in live), reverse=True)[:8]
+    p99_d = float(np.percentile([ref_d[n] for n in live], 99))
+    return {"quantiles": qs, "worst": worst, "full": full, "ref_p99_diff": p99_d}
+
+
+def grad_failures(rep):
+    bad = []
+    for q in GRAD_QUANTILES:
+        o, r = rep["quantiles"][q]
+        if not o <= GRAD_FACTOR * r + 1e-4:
+            bad.append(f"quantile {q}: ours {o:.2e} > {GRAD_FACTOR} x reference-fp32 {r:.2e}")
+    o, r = rep["quantiles"][100]
+    if not o <= 2 * GRAD_FACTOR * r:       # the maximum of a heavy-tailed sample: looser
+        bad.append(f"max: ours {o:.2e} > {2 * GRAD_FACTOR} x reference-fp32 {r:.2e}")
+    for f in rep["full"]:
+        lim = max(3.0 * f["ref_err"], rep["ref_p99_diff"])
+        if not f["err_robust"] <= lim:
+            bad.append(f"{f['name']}: element-wise error {f['err_robust']:.2e} (after dropping {f['dropped']}) > {lim:.2e}")
+    return bad
+
+
+def print_grad_report(rep, what=""):
+    print(f"{what} gradient error vs the float64 reference run (ours / the reference's own fp32 run):")
+    for q, (o, r) in rep["quantiles"].items():
+        print(f"    quantile {q:3d}: {o:.2e} / {r:.2e}")
+    for o, r, n in rep["worst"][:5]:
+        print(f"    worst tensors: {o:.2e} / {r:.2e}  {n}")
+    for f in rep["full"]:
+        print("    full tensor %-45s err %.2e  after dropping %d: %.2e  (largest component = %.0f%% of the error)  ref %.2e"
+              % (f["name"], f["err"], f["dropped"], f["err_robust"], 100 * f["top_share"], f["ref_err"]))
 
 
 def assert_grads_vs_f64(named_grads, g, what=""):
-    rows, med, med_ref = grad_rows_vs_f64(named_grads, g)
-    print(f"{what} worst gradient errors vs float64 (ratio to allowance, ours, the reference fp32 run's own):")
-    for r in rows[:6]:
-        print("    %.2f  %.2e  %.2e  %s" % r)
-    print("    median norm error: ours %.2e, reference fp32 %.2e" % (med, med_ref))
-    assert rows[0][0] < 1.0, rows[0]
-    assert med < 2.0 * med_ref + 1e-4, (med, med_ref)     # on the whole as accurate as the reference's own fp32 run
-    return rows
+    rep = grad_report_vs_f64(named_grads, g)
+    print_grad_report(rep, what)
+    bad = grad_failures(rep)
+    assert not bad, bad
+    return rep

@@ -73,14 +73,18 @@ def test_data_prepare_given_centre_and_hashed_pick():
     oc, of, ol, _ = O.data_prepare(coord, feat, label, split="val", voxel_size=VS, voxel_max=VMAX, centre=123)
     assert np.array_equal(_np(c).view(np.uint32), oc.view(np.uint32)) and np.array_equal(_np(l), ol)
     # hashed per-voxel pick + hashed centre + shuffle (train split): a valid sample of the same distribution
-    c2, f2, l2, _ = P.data_prepare(coord, feat, label, split="train", voxel_size=VS, voxel_max=VMAX, shuffle_index=True, seed=9,
-                                   pick="random")
+    kw = dict(split="train", voxel_size=VS, voxel_max=VMAX, shuffle_index=True, seed=9, pick="random")
+    b = P.prepare_batch([(coord, feat, label)], **kw)
+    c2, index = b["points"], _np(b["index"])
     assert c2.shape == (VMAX, 3) and float(c2.min()) == 0.0
-    keys = O.voxel_keys(_np(c2).astype(np.float32), VS)
-    assert len(np.unique(keys)) > 0.97 * VMAX                             # still (almost) one point per voxel after the re-shift
-    c3, _, _, _ = P.data_prepare(coord, feat, label, split="train", voxel_size=VS, voxel_max=VMAX, shuffle_index=True, seed=9,
-                                 pick="random")
-    assert torch.equal(c2, c3)                                            # counter-based RNG: reproducible
+    keys0 = O.voxel_keys(coord - coord.min(0), VS)
+    assert len(np.unique(keys0[index])) == VMAX                          # one point per (original) voxel
+    assert np.array_equal(_np(b["point_labels"]), label[index])
+    unshuffled = P.prepare_batch([(coord, feat, label)], **dict(kw, shuffle_index=False))
+    assert not np.array_equal(_np(unshuffled["index"]), index)
+    assert np.array_equal(np.sort(_np(unshuffled["index"])), np.sort(index))      # the shuffle is a permutation of the crop
+    b3 = P.prepare_batch([(coord, feat, label)], **kw)
+    assert torch.equal(c2, b3["points"])                                  # counter-based RNG: reproducible
 
 
 def test_prepare_batch_collate():

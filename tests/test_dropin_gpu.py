@@ -20,6 +20,7 @@ DROPIN = os.path.join(ROOT, "oracle", "_ref", "dropin", "pointops_cuda.so")
 def _run(mode):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_runner.py"), mode], capture_output=True, text=True,
                        timeout=900)
+    print(r.stdout[-3000:])
     lines = [l for l in r.stdout.splitlines() if l.startswith("DROPIN ")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-4000:])
     return json.loads(lines[-1][7:])
@@ -30,8 +31,7 @@ def _check(res):
     for a, b in zip(res["loss"], res["loss_ref"]):
         assert abs(a - b) <= 1e-4 * abs(b) + 1e-7, res
     assert max(res["latent_err"]) < 5e-4, res
-    assert res["grad_worst_ratio"] < 1.0, res
-    assert res["grad_median"] < 2.0 * res["grad_median_ref"] + 1e-4, res
+    assert not res["grad_failures"], res
     assert any("libcbops.so" in l for l in res["loaded"]), res
 
 
