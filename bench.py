@@ -466,6 +466,37 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------------
+# config 3 (ConvNet + CBL, bench_convnet.py): its CPU baseline leg — the oracle side stays out of the package
+# --------------------------------------------------------------------------------------------------
+def convnet_cpu_pyramid_baseline(pts, lens):
+    """the reference's own C++ operators (oracle/_ref/libref_cpu.so = its sources compiled unmodified) building the same
+    5-level pyramid on one host thread, as the TF op runs them"""
+    import oracle
+    from contrastboundary_b200.tf_pyramid import PyramidConfig
+    cfg = PyramidConfig()
+    if oracle.have_ref_cpu():
+        nb, sub, kind = oracle.ref_batch_neighbors, oracle.ref_batch_grid_subsampling, "reference"
+    else:
+        nb, sub, kind = oracle.batch_neighbors, oracle.batch_grid_subsampling, "port"
+    t0 = time.perf_counter()
+    dl, r = cfg.first_subsampling_dl, cfg.first_subsampling_dl * cfg.density_parameter / 2
+    p, l = pts, lens
+    for lvl in range(cfg.num_layers - 1):
+        nb(p, p, l, l, r)
+        pp, pl = sub(p, l, 2 * dl)
+        nb(pp, p, pl, l, r)
+        nb(p, pp, l, pl, 2 * r)
+        p, l, dl, r = pp, pl, dl * 2, r * 2
+    nb(p, p, l, l, r)
+    dt = time.perf_counter() - t0
+    return {"value": len(pts) / dt, "unit": "points/s", "cores": 1, "kind": kind,
+            "sample": f"INPUT PYRAMID ONLY (grid subsampling + radius neighbours, 5 levels) of one batch of {len(lens)} x "
+                      f"{int(lens[0])} points with the reference's own C++ operators, single thread as the TF op runs them "
+                      f"({dt * 1e3:.0f} ms); the TF network itself cannot run here (no TensorFlow)"}
+
+
+
+# --------------------------------------------------------------------------------------------------
 # config 5: KNN + gather microbench grid (SURVEY §8(d)) -> profiles/knn_gather_sweep.json
 # --------------------------------------------------------------------------------------------------
 def run_sweep(args):
@@ -513,6 +544,7 @@ def run_sweep(args):
                 try:
                     grid = fused.grid_build(xyz, off, k)
                     out = fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off)
+                    rec["replayed_queries"] = int(grid[:32].view(torch.int32)[1])     # CbGridHeader.flagged_count: exact-tie replays
                     iters = 10 if alg < (4 << 30) else 3
                     tk = timed(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, out), iters)
                     del out
@@ -556,6 +588,6 @@ if __name__ == "__main__":
         run_stock_gpu(a)
     elif a.config == 3:
         from contrastboundary_b200 import bench_convnet
-        bench_convnet.run(a, Clocks, ROOT)
+        bench_convnet.run(a, Clocks, ROOT, convnet_cpu_pyramid_baseline)
     else:
         run_ours(a)

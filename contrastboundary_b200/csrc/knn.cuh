@@ -282,9 +282,17 @@ struct CbTopKB {
                 const int src = __ffs(pass) - 1;
                 pass &= pass - 1;
                 if (K == 32 * KPL) {        // the evicted entry is the current last one
-                    const float old_last = cb_key_d(entry(32 * KPL - 1));
-                    insert(cb_shfl_key(c, src));
-                    if (cb_key_d(entry(32 * KPL - 1)) == old_last) tie_val = old_last;
+                    // `pass` was taken against the threshold at the START of the batch: after an earlier insertion of
+                    // this batch the candidate may no longer belong to the list.  Only a candidate that really evicts
+                    // (or equals) the last entry can create a boundary tie; one above it is simply dropped.
+                    const cb_key cc = cb_shfl_key(c, src);
+                    const float cdv = cb_key_d(cc), old_last = cb_key_d(entry(32 * KPL - 1));
+                    if (cdv < old_last) {
+                        insert(cc);
+                        if (cb_key_d(entry(32 * KPL - 1)) == old_last) tie_val = old_last;
+                    } else if (cdv == old_last) {
+                        tie_val = old_last;
+                    }
                 } else {
                     insert(cb_shfl_key(c, src));
                 }

@@ -316,6 +316,28 @@ int cb_pt_layer_backward(int n, int k, int c, int ld, const CbPtLayer *L, const 
 int cb_pt_set_tensor_cores(int on);
 
 /* ------------------------------------------------------------------------------------------------
+ * config 3 (ConvNet = AdaptiveWeight ResNet + CBL, TF tree): the device operators around cb_adaptive_weight_* (convnet_ops.cu)
+ * cb_ind_max_pool_*      ind_max_pool, tensorflow/models/basic_operators.py:155-172 (strided-bottleneck shortcut,
+ *                        models/backbone/resnet.py:268): out[i,c] = max_k [x ; colmin][inds[i,k], c]; colmin (c) = the
+ *                        column minima of x (the reference's shadow row); arg (n2,c) uint8 saved for the backward
+ *                        (255 = shadow row won); grad_x zero-filled by the caller.  c % 4 == 0, k < 255.
+ * cb_label_vote_idx      hard sub-scene label = arg-max (first maximum) of the histogram of target[label_idx[i,:]], entries
+ *                        outside [0, n_valid) skipped (head.py:25-49 with reduction 'max', :117-131)
+ * cb_label_vote_radius   the same vote over ALL supports within `radius` of the query (head.py:158-176 runs a radius
+ *                        search with r_sample[i-1] for stages >= 2 and gathers thousands of labels per coarse point; here
+ *                        the histogram is built inside the search).  workspace >= cb_knn_workspace_bytes(ns, 0, b).
+ * ---------------------------------------------------------------------------------------------- */
+int cb_ind_max_pool_forward(int n2, int k, int c, int n1, const float *x, const float *colmin, const int *inds, float *out,
+                            unsigned char *arg, void *stream);
+int cb_ind_max_pool_backward(int n2, int k, int c, const int *inds, const unsigned char *arg, const float *grad_out,
+                             float *grad_x, void *stream);
+int cb_label_vote_idx(int m, int kr, int ncls, int n_valid, const int *label_idx, const long long *target, int *cls,
+                      void *stream);
+int cb_label_vote_radius(int nq, const float *queries, int ns, const float *supports, const int *q_offset,
+                         const int *s_offset, int b, float radius, int ncls, const long long *target, int *cls,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * f1  the step BEFORE the path, on the device (dataprep.cu): voxelize + data_prepare + collate
  *     pytorch/util/voxelize.py:4-16,38-56   pytorch/util/data_util.py:45-92   pytorch/util/s3dis.py:94-130
  * coord / feat are float32 or float64 device arrays (coord_is_f64); the arithmetic (shift, coord / voxel_size, floor,

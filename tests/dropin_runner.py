@@ -73,7 +73,7 @@ def main(mode):
                                / max(np.abs(g[f"latent/{i}"]).max(), 1e-6)) for i in range(5)]
     rep = cases.grad_report_vs_f64({n: p.grad for n, p in model.named_parameters() if p.grad is not None}, g)
     cases.print_grad_report(rep, mode)
-    res["grad_failures"] = cases.grad_failures(rep)
+    res["grad_failures"] = cases.grad_failures(rep, cases.GRAD_FACTOR_TORCH_CUDA)
     res["grad_quantiles"] = {str(q): v for q, v in rep["quantiles"].items()}
     loaded = [l.split()[-1] for l in open("/proc/self/maps") if l.rstrip().endswith(".so") and ("cbops" in l or "pointops_cuda" in l)]
     res["loaded"] = sorted(set(os.path.relpath(x, ROOT) for x in loaded))

@@ -1,0 +1,114 @@
+"""BASELINE configs[2] — ConvNet (AdaptiveWeight ResNet) + CBL on the device pyramid (contrastboundary_b200/convnet.py).
+
+PARITY UNPINNED against TensorFlow (not installable here).  Checkers: the independent NumPy float64 restatement of the
+reference source oracle/tf_convnet_np.py (forward, loss, head geometry) and central finite differences of ITS loss for the
+gradients — no autograd on the checker side.  Tolerances: logits / loss 1e-4 relative (north_star), directional
+derivatives 5e-3 (fp32 gradient vs float64 finite difference)."""
+import numpy as np
+import pytest
+import torch
+
+from contrastboundary_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(sizes, seed, dev):
+    scenes = [synthetic.make_scene(n, seed + i) for i, n in enumerate(sizes)]
+    return {"points": torch.from_numpy(np.concatenate([s[0] for s in scenes])).to(dev),
+            "colors": torch.from_numpy(np.concatenate([s[1] for s in scenes])).to(dev),
+            "point_labels": torch.from_numpy(np.concatenate([s[2] for s in scenes])).to(dev),
+            "lens": torch.tensor(sizes, dtype=torch.int32, device=dev)}
+
+
+def _np_inputs(inputs):
+    out = {}
+    for k, v in inputs.items():
+        if isinstance(v, (tuple, list)):
+            out[k] = [t.cpu().numpy().astype(np.int64) if t.dtype in (torch.int32, torch.int64) else t.cpu().numpy() for t in v]
+        elif isinstance(v, torch.Tensor):
+            out[k] = v.cpu().numpy()
+    return out
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from contrastboundary_b200 import convnet
+    dev = torch.device("cuda", 0)
+    ts = convnet.ConvNetTrainStep(convnet.ConvNetConfig(), dev, seed=1)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():                       # non-trivial batch-norm parameters and biases
+        for name, p in ts.model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g).to(dev))
+    batch = _batch([4000, 3500], 300, dev)
+    inputs = ts.build_inputs(batch)
+    return convnet, ts, batch, inputs
+
+
+def test_forward_and_loss_match_float64_restatement(setup):
+    from oracle import tf_convnet_np as R
+    convnet, ts, batch, inputs = setup
+    logits, stage_list = ts.model(inputs)
+    loss = ts.criterion(logits, inputs["point_labels"], stage_list)
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in ts.model.state_dict().items() if v.dtype.is_floating_point}
+    rl, rloss, rlat, (up_idx0, cls) = R.forward(P, _np_inputs(inputs), ts.cfg)
+    geo = stage_list["geometry"]
+    for i in range(1, 5):                       # head geometry: exact (integer / index work)
+        assert np.array_equal(geo["up_idx0"][i].cpu().numpy().astype(np.int64), up_idx0[i]), f"nearest-upsample index, stage {i}"
+        assert np.array_equal(geo["cls"][i].cpu().numpy().astype(np.int64), cls[i]), f"hard sub-scene labels, stage {i}"
+    err = np.abs(logits.detach().cpu().numpy() - rl).max() / np.abs(rl).max()
+    assert err < 1e-4, err
+    for i in range(5):
+        a, b = stage_list["up"][i]["latent"].detach().cpu().numpy(), rlat[i]
+        assert np.abs(a - b).max() / max(np.abs(b).max(), 1e-9) < 2e-4, i
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), rloss, rtol=1e-4, atol=1e-7)
+    assert (rloss[1:] > 0).sum() >= 3           # the boundary loss is active on most stages of this batch
+
+
+def test_gradients_match_float64_finite_differences(setup):
+    from oracle import tf_convnet_np as R
+    convnet, ts, batch, inputs = setup
+    ts.model.zero_grad(set_to_none=True)
+    logits, stage_list = ts.model(inputs)
+    ts.criterion(logits, inputs["point_labels"], stage_list).sum().backward()
+    params = dict(ts.model.named_parameters())
+    P0 = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in ts.model.state_dict().items() if v.dtype.is_floating_point}
+    npin = _np_inputs(inputs)
+    groups = {"1x1 kernels": lambda n: n.endswith("weights.weight"), "fc_1 (position -> weight)": lambda n: ".fc_1." in n,
+              "batch-norm affine": lambda n: ".bn." in n or ".pool_bn." in n, "classifier": lambda n: n.startswith("multiscale.linear")}
+    rng = np.random.default_rng(0)
+    for gname, sel in groups.items():
+        names = [n for n in params if sel(n)]
+        assert names, gname
+        d = {n: rng.standard_normal(params[n].shape) for n in names}
+        eps = 2e-4 / np.sqrt(sum(float((v ** 2).sum()) for v in d.values())) * np.sqrt(sum(float((P0[n] ** 2).sum()) for n in names))
+        lp = R.forward({**P0, **{n: P0[n] + eps * d[n] for n in names}}, npin, ts.cfg)[1].sum()
+        lm = R.forward({**P0, **{n: P0[n] - eps * d[n] for n in names}}, npin, ts.cfg)[1].sum()
+        fd = (lp - lm) / (2 * eps)
+        an = sum(float((params[n].grad.double().cpu().numpy() * d[n]).sum()) for n in names)
+        print(f"directional derivative, {gname}: float64 finite difference {fd:.6e}, CUDA gradient {an:.6e}")
+        assert abs(fd - an) <= 5e-3 * abs(fd) + 1e-7, (gname, fd, an)
+
+
+def test_ind_max_pool_and_label_votes(setup):
+    convnet, ts, batch, inputs = setup
+    from oracle import tf_convnet_np as R
+    x = torch.randn(inputs["points"][0].shape[0], 72, device="cuda", requires_grad=True)
+    pools = inputs["pools"][0]
+    y = convnet.ind_max_pool(x, pools)
+    ref = R.ind_max_pool(x.detach().cpu().numpy(), pools.cpu().numpy().astype(np.int64))
+    assert np.array_equal(y.detach().cpu().numpy(), ref)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xs = torch.cat([x.detach(), x.detach().min(0, keepdim=True)[0]], 0).requires_grad_(True)
+    xs[pools.long()].max(1)[0].backward(gy)
+    assert torch.allclose(x.grad, xs.grad[:-1], atol=1e-5)
+
+
+def test_train_step_learns(setup):
+    convnet, ts, batch, inputs = setup
+    ts2 = convnet.ConvNetTrainStep(convnet.ConvNetConfig(), torch.device("cuda", 0), seed=2)
+    losses = [ts2.step(batch, inputs).cpu().numpy() for _ in range(6)]
+    assert np.isfinite(losses).all()
+    assert losses[-1][0] < losses[0][0]                                     # cross entropy goes down on a repeated batch
