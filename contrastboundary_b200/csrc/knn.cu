@@ -129,8 +129,8 @@ __device__ __forceinline__ long long cb_dims(float ex, float ey, float ez, float
 }
 
 // phase 0: trial grid from the bbox-volume heuristic; phase 1: final grid from measured occupancy
-__global__ void k_params(CbGridHeader *hdr, CbScene *scenes, const unsigned *bbox, const int *occ,
-                         const int *__restrict__ offset, int b, int n, int nsample, int cap, int phase, float occ_factor)
+__device__ void cb_params_block(CbGridHeader *hdr, CbScene *scenes, const unsigned *bbox, const int *occ,
+                                const int *__restrict__ offset, int b, int n, int nsample, int cap, int phase, float occ_factor)
 {
     const float target = cb_target_occ(nsample, occ_factor);
     for (int s = threadIdx.x; s < b; s += blockDim.x) {
@@ -185,6 +185,12 @@ __global__ void k_params(CbGridHeader *hdr, CbScene *scenes, const unsigned *bbo
         hdr->total_cells = base;
         hdr->trial = phase == 0;
     }
+}
+
+__global__ void k_params(CbGridHeader *hdr, CbScene *scenes, const unsigned *bbox, const int *occ,
+                         const int *__restrict__ offset, int b, int n, int nsample, int cap, int phase, float occ_factor)
+{
+    cb_params_block(hdr, scenes, bbox, occ, offset, b, n, nsample, cap, phase, occ_factor);
 }
 
 // count points per cell.  trial: also measure occupied cells at h and 2h.
@@ -288,6 +294,155 @@ __global__ void k_zero_cells(int *cells, int *coarse, const CbGridHeader *hdr, i
         cells[i] = 0;
         if (zero_coarse) coarse[i] = 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole grid build as ONE cooperative kernel: the ten phases above separated by grid-wide barriers instead of
+// kernel boundaries (a build of a 40960-point scene is ~6 us of work behind ~55 us of launch latency otherwise).
+// Same arithmetic, same results as the multi-kernel path (the counting sort's ranks are atomics in both).
+// ---------------------------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+__global__ void __launch_bounds__(256) k_grid_build_fused(const float *__restrict__ xyz, int n, const int *__restrict__ offset, int b,
+                                                          int nsample, float occ_factor, CbGridHeader *hdr, CbScene *scenes,
+                                                          unsigned *bbox, int *occ, int *tile_sums, int *cells, int *coarse,
+                                                          int *point_cell, int *point_rank, float4 *sorted, int trial_cap,
+                                                          int cell_cap)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    // phase 0: init
+    for (int i = gtid; i < b * 6; i += gsize) bbox[i] = (i % 6 < 3) ? 0xffffffffu : 0u;
+    for (int i = gtid; i < b * 2; i += gsize) occ[i] = 0;
+    if (gtid == 0) { hdr->total_cells = 0; hdr->flagged_count = 0; hdr->n = n; hdr->b = b; hdr->trial = 1; }
+    grid.sync();
+    // phase 1: bounding boxes
+    {
+        const int lane = threadIdx.x & 31;
+        for (int base = gtid - lane; base < n; base += gsize) {
+            const int i = base + lane;
+            const bool valid = i < n;
+            const int ic = valid ? i : n - 1;
+            const int s = cb_scene_of(ic, offset, b);
+            const unsigned ux = cb_f2ord(__ldg(xyz + 3 * ic)), uy = cb_f2ord(__ldg(xyz + 3 * ic + 1)), uz = cb_f2ord(__ldg(xyz + 3 * ic + 2));
+            const int s0 = __shfl_sync(CB_FULL_MASK, s, 0);
+            if (__all_sync(CB_FULL_MASK, s == s0)) {
+                unsigned mnx = __reduce_min_sync(CB_FULL_MASK, ux), mny = __reduce_min_sync(CB_FULL_MASK, uy), mnz = __reduce_min_sync(CB_FULL_MASK, uz);
+                unsigned mxx = __reduce_max_sync(CB_FULL_MASK, ux), mxy = __reduce_max_sync(CB_FULL_MASK, uy), mxz = __reduce_max_sync(CB_FULL_MASK, uz);
+                if (lane == 0) {
+                    unsigned *bb = bbox + 6 * s0;
+                    atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMin(bb + 2, mnz);
+                    atomicMax(bb + 3, mxx); atomicMax(bb + 4, mxy); atomicMax(bb + 5, mxz);
+                }
+            } else if (valid) {
+                unsigned *bb = bbox + 6 * s;
+                atomicMin(bb + 0, ux); atomicMin(bb + 1, uy); atomicMin(bb + 2, uz);
+                atomicMax(bb + 3, ux); atomicMax(bb + 4, uy); atomicMax(bb + 5, uz);
+            }
+        }
+    }
+    grid.sync();
+    for (int phase = 0; phase < 2; phase++) {
+        // trial grid (phase 0) / final grid (phase 1): parameters, zero the cell counters, count
+        if (blockIdx.x == 0) cb_params_block(hdr, scenes, bbox, occ, offset, b, n, nsample, phase == 0 ? trial_cap : cell_cap, phase, occ_factor);
+        grid.sync();
+        const int total = hdr->total_cells + 1;
+        for (int i = gtid; i < total; i += gsize) {
+            cells[i] = 0;
+            if (phase == 0) coarse[i] = 0;
+        }
+        grid.sync();
+        for (int i = gtid; i < n; i += gsize) {
+            const int s = cb_scene_of(i, offset, b);
+            const CbScene sc = scenes[s];
+            const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+            int cx = (int)floorf(cb_cellf(x, sc.ox, sc.inv_h)), cy = (int)floorf(cb_cellf(y, sc.oy, sc.inv_h)),
+                cz = (int)floorf(cb_cellf(z, sc.oz, sc.inv_h));
+            cx = min(max(cx, 0), sc.nx - 1); cy = min(max(cy, 0), sc.ny - 1); cz = min(max(cz, 0), sc.nz - 1);
+            const int cell = sc.cell_base + (cz * sc.ny + cy) * sc.nx + cx;
+            const int rank = atomicAdd(cells + cell, 1);
+            if (phase == 0) {
+                if (rank == 0) atomicAdd(occ + 2 * s, 1);
+                const int hx = (sc.nx + 1) >> 1, hy = (sc.ny + 1) >> 1;
+                const int cc = sc.cell_base + ((cz >> 1) * hy + (cy >> 1)) * hx + (cx >> 1);
+                if (atomicExch(coarse + cc, 1) == 0) atomicAdd(occ + 2 * s + 1, 1);
+            } else {
+                point_cell[i] = cell;
+                point_rank[i] = rank;
+            }
+        }
+        grid.sync();
+    }
+    // exclusive scan of cells[0 .. total_cells]: per-tile scans, then the tile offsets
+    const int total = hdr->total_cells + 1;
+    const int ntiles = (total + CB_SCAN_TILE - 1) / CB_SCAN_TILE;
+    __shared__ int warp_sums[8];
+    __shared__ int red[256];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tile0 = tile * CB_SCAN_TILE;
+        int v[8];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tile0 + t * 8 + k;
+            v[k] = i < total ? cells[i] : 0;
+            sum += v[k];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(CB_FULL_MASK, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __syncthreads();                       // warp_sums of the previous tile are consumed
+        if (lane == 31) warp_sums[w] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int k = 0; k < w; k++) woff += warp_sums[k];
+        int run = woff + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tile0 + t * 8 + k;
+            if (i < total) cells[i] = run;
+            run += v[k];
+        }
+        if (t == 255) tile_sums[tile] = run;
+    }
+    grid.sync();
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tile == 0) continue;
+        int acc = 0;
+        for (int k = t; k < tile; k += 256) acc += tile_sums[k];
+        __syncthreads();                       // red[] of the previous tile is consumed
+        red[t] = acc;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (t < s) red[t] += red[t + s];
+            __syncthreads();
+        }
+        const int off = red[0];
+        const int tile0 = tile * CB_SCAN_TILE;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tile0 + t * 8 + k;
+            if (i < total) cells[i] += off;
+        }
+    }
+    grid.sync();
+    // counting-sort scatter: supports re-ordered by cell as (x, y, z, original index)
+    for (int i = gtid; i < n; i += gsize) {
+        const int pos = cells[point_cell[i]] + point_rank[i];
+        sorted[pos] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), __int_as_float(i));
+    }
+}
+
+static int g_grid_fused = 1;   // 1: one cooperative kernel (default) | 0: the multi-kernel build | 2: fused unless the stream is capturing
+extern "C" int cb_grid_set_fused(int mode)
+{
+    if (mode >= 0 && mode <= 2) g_grid_fused = mode;
+    return g_grid_fused;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -484,9 +639,54 @@ __global__ void k_reset_flagged(CbGridHeader *hdr) { hdr->flagged_count = 0; }
 // ---------------------------------------------------------------------------------------------
 static int grid_blocks(int n, int threads) { int g = (n + threads - 1) / threads; return g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g); }
 
+static int cb_grid_build_fused(const float *xyz, int n, const int *offset, int b, int nsample_hint, const CbGridView &v,
+                               cudaStream_t st)
+{
+    static int max_blocks = 0;
+    if (max_blocks == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_build_fused, 256, 0);
+        max_blocks = per_sm * sms;
+        if (max_blocks < 1) max_blocks = -1;
+    }
+    if (max_blocks < 0) return 1;
+    int blocks = (n + 255) / 256;
+    if (blocks > 148 * 3) blocks = 148 * 3;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    float occ = g_occ_factor;
+    CbGridHeader *hdr = v.hdr; CbScene *scenes = v.scenes; unsigned *bbox = v.bbox; int *occp = v.occ, *tile_sums = v.tile_sums;
+    int *cells = v.cells, *coarse = v.coarse, *point_cell = v.point_cell, *point_rank = v.point_rank;
+    float4 *sorted = v.sorted;
+    int trial_cap = v.trial_cap, cell_cap = v.cell_cap;
+    void *args[] = {(void *)&xyz, (void *)&n, (void *)&offset, (void *)&b, (void *)&nsample_hint, (void *)&occ, (void *)&hdr,
+                    (void *)&scenes, (void *)&bbox, (void *)&occp, (void *)&tile_sums, (void *)&cells, (void *)&coarse,
+                    (void *)&point_cell, (void *)&point_rank, (void *)&sorted, (void *)&trial_cap, (void *)&cell_cap};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_grid_build_fused, dim3(blocks), dim3(256), args, 0, st);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 1;
+    }
+    CB_COUNT(1);
+    return 0;
+}
+
 int cb_grid_build_impl(const float *xyz, int n, const int *offset, int b, int nsample_hint, const CbGridView &v,
                            cudaStream_t st)
 {
+    if (g_grid_fused && n > 0) {
+        bool use = true;
+        if (g_grid_fused == 2) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) use = false;
+        }
+        if (use && cb_grid_build_fused(xyz, n, offset, b, nsample_hint, v, st) == 0) {
+            CB_CUDA_CHECK("cb_grid_build");
+            return CB_OK;
+        }
+    }
     const int ib = (b * 6 + 127) / 128;
     k_bbox_init<<<ib, 128, 0, st>>>(v.bbox, v.occ, b, v.hdr, n);
     if (n > 0) k_bbox<<<grid_blocks(n, 256), 256, 0, st>>>(xyz, n, offset, b, v.bbox);

@@ -151,7 +151,8 @@ def bn_act(bn, x, residual=None, relu=True):
     """act(bn(x) [+ residual]) for a BatchNorm1d module `bn` on an (n, c) tensor: the reference's
     relu(bn(.)) / relu(bn3(.) + identity) patterns (blocks.py:76,127-133) in two kernels per direction."""
     if (FUSED_BN and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
-            and bn.track_running_stats and bn.momentum is not None and bn.affine and x.shape[0] > 0):
+            and bn.track_running_stats and bn.momentum is not None and bn.affine and x.shape[0] > 0
+            and not isinstance(bn, nn.SyncBatchNorm)):
         if bn.training:
             bump_bn_counter(bn)
         return _BnActFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum),

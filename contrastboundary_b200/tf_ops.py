@@ -161,6 +161,25 @@ def tf_batch_neighbors(queries, supports, q_batches, s_batches, radius, limit=No
 batch_neighbors = tf_batch_neighbors
 
 
+def radius_counts(queries, supports, q_batches, s_batches, radius):
+    """number of supports within `radius` of every query (strict, nanoflann arithmetic) -> int32 (Nq): the row lengths of
+    tf_batch_neighbors without materialising the rows (what the reference's calibration needs of them:
+    `np.sum(neighb_mat < neighb_mat.shape[0], axis=1)`, datasets/base.py:266, and `len(neighb)` of :173-175)"""
+    q = _to_cuda(queries, torch.float32)
+    s = q if queries is supports else _to_cuda(supports, torch.float32)
+    ql, sl = _to_cuda(q_batches, torch.int32), _to_cuda(s_batches, torch.int32)
+    qo, so = _offsets(ql), _offsets(sl)
+    nq, ns, b = q.shape[0], s.shape[0], ql.shape[0]
+    lib = L.lib()
+    ws = L.workspace(lib.cb_knn_workspace_bytes(ns, nq, b), q.device, "knn")
+    counts = torch.empty(max(nq, 1), dtype=torch.int32, device=q.device)
+    mx = torch.zeros(1, dtype=torch.int32, device=q.device)
+    rc = lib.cb_radius_count(C.c_int(nq), L.ptr(q), C.c_int(ns), L.ptr(s), L.ptr(qo), L.ptr(so), C.c_int(b), C.c_float(float(radius)),
+                             L.ptr(counts), L.ptr(mx), L.ptr(ws), C.c_size_t(ws.numel()), L.stream())
+    L.check(rc, "cb_radius_count")
+    return counts[:nq]
+
+
 def tf_knn_search(query_pts, support_pts, k):
     """[B,M,3] queries, [B,N,3] supports -> int32 [B,M,k] indices local to each batch element (tf_ops.py:117-129)"""
     q = _to_cuda(query_pts, torch.float32)

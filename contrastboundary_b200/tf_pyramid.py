@@ -79,3 +79,69 @@ def segmentation_inputs_radius(stacked_points, stacked_features, point_labels, s
         "in_batches": stack_batch_inds(input_lens[0]), "out_batches": stack_batch_inds(input_lens[-1]),
         "point_labels": tf_ops._to_cuda(point_labels, torch.int64) if point_labels is not None else None,
     }
+
+
+# ------------------------------------------------------------------------------------------------------
+# calibration of the pyramid (tensorflow/datasets/base.py:158-294) — SURVEY 8(f) row 2
+# ------------------------------------------------------------------------------------------------------
+def calibrate_neighbors(batches, cfg: PyramidConfig = None, keep_ratio=0.8, samples_threshold=10000):
+    """`neighborhood_limits` of every layer = the `keep_ratio` percentile of the neighbourhood sizes seen in the batches
+    (Dataset.calibrate_neighbors, base.py:199-294).  `batches` yields (stacked_points (N,3), stacks_lengths (B,)).
+    The reference runs its whole input pipeline with the limits set to the upper bound hist_n and counts the valid entries of
+    every neighbour row on the host; here only the COUNTS are computed (cb_radius_count) and histogrammed on the device.
+    Like the reference, neighbourhoods of hist_n or more points fall outside the histogram (base.py:267)."""
+    import math
+    cfg = cfg or PyramidConfig()
+    nl = cfg.num_layers
+    hist_n = int(math.ceil(4.0 / 3.0 * math.pi * (cfg.density_parameter + 1) ** 3))            # base.py:207
+    hists = None
+    for stacked_points, stacks_lengths in batches:
+        pts = tf_ops._to_cuda(stacked_points, torch.float32)
+        lens = tf_ops._to_cuda(stacks_lengths, torch.int32)
+        if hists is None:
+            hists = torch.zeros((nl, hist_n), dtype=torch.int64, device=pts.device)
+        dl, r = cfg.first_subsampling_dl, cfg.first_subsampling_dl * cfg.density_parameter / 2.0
+        for layer in range(nl):
+            counts = tf_ops.radius_counts(pts, pts, lens, lens, r).long()
+            hists[layer] += torch.bincount(counts[counts < hist_n], minlength=hist_n)[:hist_n]    # :266-268
+            if layer + 1 < nl:
+                pts, lens = tf_ops.tf_batch_subsampling(pts, lens, 2 * dl)
+                r, dl = 2 * r, 2 * dl
+        if int(hists.sum(1).min()) >= samples_threshold:                                         # :249
+            break
+    cumsum = torch.cumsum(hists.t(), 0)                                                           # :286
+    percentiles = (cumsum < keep_ratio * cumsum[hist_n - 1, :].double()).sum(0)                   # :287
+    return [int(v) for v in percentiles.cpu()]
+
+
+def calibrate_batches(clouds, in_radius, batch_size, rng=None, n_samples=10000):
+    """`batch_limit` (the point budget of a batch) such that batches hold `batch_size` input spheres on average
+    (Dataset.calibrate_batches, base.py:158-197).  clouds: list of (n,3) arrays (the sub-sampled training clouds).  The sphere
+    sizes come from cb_radius_count on the device; the proportional corrector is the reference's, driven by `rng`
+    (numpy Generator; the reference uses the global np.random state)."""
+    import numpy as np
+    rng = rng or np.random.default_rng()
+    N = (n_samples // len(clouds)) + 1
+    sizes = []
+    for cloud in clouds:
+        pts = np.asarray(cloud, dtype=np.float32)
+        pick = rng.choice(pts.shape[0], size=min(N, pts.shape[0]), replace=False)
+        # (the reference adds noise to a COPY and then queries the un-noised picks, base.py:170-173)
+        q = np.ascontiguousarray(pts[pick])
+        one = np.array([len(q)], np.int32), np.array([pts.shape[0]], np.int32)
+        sizes += tf_ops.radius_counts(q, pts, one[0], one[1], in_radius).cpu().tolist()
+    sizes = np.sort(np.asarray(sizes))
+    lim = float(sizes[-1] * batch_size)                                                           # :179
+    acc, max_b = 0, 0
+    for i, s in enumerate(sizes):                                                                 # :181-187
+        acc += s
+        if acc > lim:
+            max_b = i
+            break
+    estim_b = 0.0
+    for i in range(10000):                                                                        # :189-196
+        rand_shapes = rng.choice(sizes, size=max_b, replace=False)
+        b = np.sum(np.cumsum(rand_shapes) < lim)
+        estim_b += (b - estim_b) / min(i + 1, 100)
+        lim += 10.0 * (batch_size - estim_b)
+    return lim

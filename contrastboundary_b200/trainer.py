@@ -74,3 +74,112 @@ def resume(path, model, optimizer, scheduler, map_location=None):
     optimizer.load_state_dict({"state": osd["state"], "param_groups": groups})
     scheduler.load_state_dict(ckpt["scheduler"])
     return ckpt["epoch"], ckpt["best_iou"]
+
+
+# ------------------------------------------------------------------------------------------------------
+# the rest of the trainer's per-step / per-epoch bookkeeping (train.py:148-149,265-284,315-345)
+# ------------------------------------------------------------------------------------------------------
+def build_model(cfg=None, sync_bn=False, device=None):
+    """`Model(c=, k=, config=)` + the `sync_bn` switch of train.py:147-149.
+    sync_bn=False (the reference's shipped setting): the fused libcbops layers with per-rank BatchNorm statistics.
+    sync_bn=True: `nn.SyncBatchNorm.convert_sync_batchnorm(model)` exactly as the reference does it; the statistics of a
+    synchronised BatchNorm need a collective in the middle of what the fused layer kernels compute in one pass, so this
+    option runs the network op by op (model.set_fused(False)) on the stand-alone operators."""
+    import torch.nn as nn
+    from .model import CBLConfig, PointTransformerSeg
+    cfg = cfg or CBLConfig()
+    model = PointTransformerSeg(cfg)
+    if sync_bn:
+        model.set_fused(False)
+        model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    return model.to(device) if device is not None else model
+
+
+def pack_step_metrics(loss, output, target, classes, ignore_label=255):
+    """everything the reference all-reduces per step (train.py:328-338: loss * n, count, intersection, union, target —
+    five collectives and an `.item()`), packed into ONE float64 device vector of 2 + len(loss) + 3 * classes entries:
+    [n, len(loss), loss * n ..., intersection ..., union ..., target ...].  No host synchronisation."""
+    from .boundary_eval import intersection_and_union
+    n = target.shape[0]
+    pred = output.max(1)[1]
+    i, u, t = intersection_and_union(pred, target, classes, ignore_label)
+    head = torch.tensor([float(n), float(loss.numel())], dtype=torch.float64, device=loss.device)
+    return torch.cat([head, loss.detach().double() * n, i.double(), u.double(), t.double()])
+
+
+class MetricsAccumulator:
+    """AverageMeter bookkeeping of train()/validate() (train.py:300-306,339-356) without per-step host reads: packed
+    step metrics are summed on the device, all-reduced once per `reduce_every` steps (ONE collective of 46 doubles for the
+    shipped 6-loss / 13-class configuration, off the critical path) and read back once per epoch."""
+
+    def __init__(self, classes, reduce_every=1):
+        self.classes, self.reduce_every = classes, max(1, int(reduce_every))
+        self.total = None          # reduced sums
+        self.pending = None
+        self.steps = 0
+
+    def update(self, packed):
+        self.pending = packed.clone() if self.pending is None else self.pending + packed
+        self.steps += 1
+        if self.steps % self.reduce_every == 0:
+            self._flush()
+
+    def _flush(self):
+        if self.pending is None:
+            return
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            nl = self.pending[1].clone()
+            dist.all_reduce(self.pending)                                      # one collective for everything
+            self.pending[1] = nl                                               # (the loss count is not a sum over ranks)
+        self.total = self.pending if self.total is None else self.total + self.pending
+        self.pending = None
+
+    def summary(self):
+        """-> (loss vector averaged over points, mIoU, mAcc, allAcc)   (train.py:358-364); one device->host read"""
+        self._flush()
+        t = self.total.cpu().numpy()
+        nl = int(round(t[1] / max(self.steps, 1)))                             # entry 1 = (#losses) summed over the steps
+        n = t[0]
+        loss = t[2:2 + nl] / max(n, 1.0)
+        k = self.classes
+        inter, union, target = t[2 + nl:2 + nl + k], t[2 + nl + k:2 + nl + 2 * k], t[2 + nl + 2 * k:2 + nl + 3 * k]
+        iou = inter / (union + 1e-10)
+        acc = inter / (target + 1e-10)
+        return loss, float(iou.mean()), float(acc.mean()), float(inter.sum() / (target.sum() + 1e-10))
+
+
+class ScalarLog:
+    """`writer.add_scalar(tag, value, epoch)` of train.py:265-284 (loss_train, loss_train_<i>, mIoU_train, mAcc_train,
+    allAcc_train and the *_val twins).  Uses TensorBoard's SummaryWriter when the package is importable, and always
+    appends the same records to <save_path>/scalars.jsonl."""
+
+    def __init__(self, save_path):
+        import json
+        self._json = json
+        os.makedirs(save_path, exist_ok=True)
+        self.path = os.path.join(save_path, "scalars.jsonl")
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            self.tb = SummaryWriter(save_path)
+        except Exception:
+            self.tb = None
+
+    def add_scalar(self, tag, value, step):
+        value = float(value)
+        with open(self.path, "a") as f:
+            f.write(self._json.dumps({"tag": tag, "value": value, "step": int(step)}) + "\n")
+        if self.tb is not None:
+            self.tb.add_scalar(tag, value, step)
+
+    def log_epoch(self, split, loss, miou, macc, allacc, epoch):
+        self.add_scalar(f"loss_{split}", float(sum(loss)), epoch)
+        for i, v in enumerate(loss):
+            self.add_scalar(f"loss_{split}_{i}", v, epoch)
+        self.add_scalar(f"mIoU_{split}", miou, epoch)
+        self.add_scalar(f"mAcc_{split}", macc, epoch)
+        self.add_scalar(f"allAcc_{split}", allacc, epoch)
+
+    def close(self):
+        if self.tb is not None:
+            self.tb.close()

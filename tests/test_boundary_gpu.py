@@ -60,3 +60,46 @@ def test_full_resolution_room_boundary_iou(kr):
         assert np.array_equal(res[f"{name}-u"].cpu().numpy(), ao + at - ai)
         assert np.array_equal(res[f"{name}-t"].cpu().numpy(), at)
     assert 0 < ob.sum() < n and 0 < op.sum() < n
+
+
+def test_voting_crops_follow_reference_loop():
+    """regular_crops vs the loop of pytorch/tool/test.py:199-216 restated in NumPy with the same initial potentials"""
+    from contrastboundary_b200 import synthetic, voting
+    coord = synthetic.make_scene(9000, 77)[0].astype(np.float64)
+    pot = np.random.default_rng(3).random(len(coord)) * 1e-3
+    vmax = 4000
+    # reference loop (test.py:199-216)
+    coord_p, idx_uni, ref = pot.copy(), np.array([]), []
+    while idx_uni.size != len(coord):
+        init_idx = np.argmin(coord_p)
+        dist = np.sum(np.power(coord - coord[init_idx], 2), 1)
+        idx_crop = np.argsort(dist, kind="stable")[:vmax]
+        d = dist[idx_crop]
+        coord_p[idx_crop] += np.square(1 - d / np.max(d))
+        ref.append(idx_crop)
+        idx_uni = np.unique(np.concatenate((idx_uni, idx_crop)))
+    ours = list(voting.regular_crops(torch.from_numpy(coord).cuda(), vmax, potentials=torch.from_numpy(pot).cuda()))
+    assert len(ours) == len(ref) and len(ref) >= 3
+    for (idx_crop, c_sub), r in zip(ours, ref):
+        assert np.array_equal(np.sort(idx_crop.cpu().numpy()), np.sort(r))      # same crop (order inside equal distances aside)
+        assert float(c_sub.min()) == 0.0
+
+
+def test_vote_room_accumulates_every_point():
+    from contrastboundary_b200 import synthetic, voting
+    rng = np.random.default_rng(5)
+    base = synthetic.make_scene(6000, 78)[0]
+    coord = np.concatenate([base, base + rng.normal(0, 0.004, base.shape).astype(np.float32)])   # ~2 points per voxel
+    feat = rng.integers(0, 256, coord.shape).astype(np.float32)
+    seen = []
+
+    def model(inputs):                       # logits = a one-hot of the crop's scene slot: counts how often a point is predicted
+        n = inputs["points"].shape[0]
+        assert inputs["offset"][-1] == n and float(inputs["features"].max()) <= 1.0
+        seen.append(n)
+        return torch.ones(n, 13, device="cuda"), None
+    cum = voting.vote_room(model, torch.from_numpy(coord).cuda(), torch.from_numpy(feat).cuda(), 13, voxel_size=0.04, voxel_max=3000,
+                           generator=torch.Generator(device="cuda").manual_seed(0))
+    assert cum.shape == (len(coord), 13)
+    assert float(cum.min()) >= 1.0                                              # every point of the room received at least one vote
+    assert len(seen) >= 1 and sum(seen) == int(cum[:, 0].sum())

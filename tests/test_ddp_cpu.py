@@ -56,6 +56,22 @@ def _worker(rank, world, port, out_dir):
     hs = [torch.zeros(1) for _ in range(world)]
     dist.all_gather(hs, h)
     assert len({round(float(v), 4) for v in hs}) == world, "ranks got identical scenes"
+    # one coalesced metrics all-reduce per step (trainer.MetricsAccumulator) == the reference's five (train.py:328-338)
+    from contrastboundary_b200 import trainer
+    logits = ddp(x).detach()
+    lossv = torch.stack([torch.nn.functional.cross_entropy(logits, y), torch.tensor(0.25 * (rank + 1))])
+    acc = trainer.MetricsAccumulator(13)
+    acc.update(trainer.pack_step_metrics(lossv, logits, y, 13))
+    loss_avg, miou, macc, allacc = acc.summary()
+    n = torch.tensor([float(len(y))])
+    ln = lossv.double() * len(y)
+    dist.all_reduce(n), dist.all_reduce(ln)
+    assert np.allclose(loss_avg, (ln / n).numpy(), rtol=1e-12)
+    pred = logits.max(1)[1]
+    inter = torch.bincount(pred[pred == y], minlength=13).double()
+    tgt = torch.bincount(y, minlength=13).double()
+    dist.all_reduce(inter), dist.all_reduce(tgt)
+    assert abs(allacc - float(inter.sum() / (tgt.sum() + 1e-10))) < 1e-12
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from contrastboundary_b200 import boundary_eval, linear_ops, model, tf_pyramid
+from contrastboundary_b200 import boundary_eval, linear_ops, model, tf_pyramid, trainer
 
 
 def test_level_offsets_follow_the_reference_rule():
@@ -106,3 +106,41 @@ def test_trainer_checkpoint_round_trip_and_schedule(tmp_path):
     for _ in range(3, 85):
         opt2.step(); sch2.step()
     assert abs(opt2.param_groups[0]["lr"] - 0.005) < 1e-9
+
+
+
+def test_trainer_metrics_scalars_and_sync_bn_option(tmp_path):
+    """train.py:148-149 (sync_bn), :265-284 (scalars), :328-364 (per-step metrics -> epoch averages)"""
+    import json
+    import torch.nn as nn
+    rng = np.random.default_rng(0)
+    acc = trainer.MetricsAccumulator(13, reduce_every=2)
+    tot_n, tot_loss, ti, tu, tt = 0, np.zeros(6), np.zeros(13), np.zeros(13), np.zeros(13)
+    for step in range(5):
+        n = int(rng.integers(50, 90))
+        logits = torch.from_numpy(rng.standard_normal((n, 13)).astype(np.float32))
+        target = torch.from_numpy(rng.integers(0, 13, n))
+        target[:3] = 255                                                     # ignored points
+        loss = torch.from_numpy(rng.random(6).astype(np.float32))
+        acc.update(trainer.pack_step_metrics(loss, logits, target, 13, 255))
+        pred = logits.max(1)[1].numpy().copy()
+        tg = target.numpy()
+        pred[tg == 255] = 255                                               # util/common_util.py:40-52
+        tot_n += n
+        tot_loss += loss.numpy().astype(np.float64) * n
+        for c in range(13):
+            ti[c] += np.sum((pred == c) & (tg == c)); tt[c] += np.sum(tg == c)
+            tu[c] += np.sum(pred == c) + np.sum(tg == c) - np.sum((pred == c) & (tg == c))
+    loss_avg, miou, macc, allacc = acc.summary()
+    assert np.allclose(loss_avg, tot_loss / tot_n, rtol=1e-12)
+    assert abs(miou - np.mean(ti / (tu + 1e-10))) < 1e-12 and abs(macc - np.mean(ti / (tt + 1e-10))) < 1e-12
+    assert abs(allacc - ti.sum() / (tt.sum() + 1e-10)) < 1e-12
+    log = trainer.ScalarLog(str(tmp_path / "run"))
+    log.log_epoch("train", loss_avg, miou, macc, allacc, 1)
+    log.close()
+    tags = [json.loads(l)["tag"] for l in open(tmp_path / "run" / "scalars.jsonl")]
+    assert tags == ["loss_train"] + [f"loss_train_{i}" for i in range(6)] + ["mIoU_train", "mAcc_train", "allAcc_train"]
+    m = trainer.build_model(sync_bn=True)
+    assert any(isinstance(x, nn.SyncBatchNorm) for x in m.modules()) and not any(type(x) is nn.BatchNorm1d for x in m.modules())
+    assert all(not x.fused for x in m.modules() if hasattr(x, "fused") and isinstance(x, (model.PointTransformerLayer, model.TransitionDown)))
+    assert set(trainer.build_model().state_dict()) == set(m.state_dict())   # same checkpoint keys either way
