@@ -48,37 +48,70 @@ __global__ void __launch_bounds__(AW_THREADS) k_aw(int n, int k, int c, int n0, 
     }
     const int pad = __ldg(pad_num);
     const int warps = gridDim.x * (AW_THREADS / 32);
+    const float inv_r = 1.0f;   // (the division by radius is kept per element, as the reference: dp / radius)
+    (void)inv_r;
     for (int pt = blockIdx.x * (AW_THREADS / 32) + wib; pt < n; pt += warps) {
         const float qx = __ldg(qpts + 3 * pt), qy = __ldg(qpts + 3 * pt + 1), qz = __ldg(qpts + 3 * pt + 2);
+        float acc[AW_CPL], g[AW_CPL];
+#pragma unroll
+        for (int i = 0; i < AW_CPL; i++) acc[i] = 0.f;
+        // count of "valid" neighbours as the reference counts them (idx < max idx)
         int cnt = 0;
         for (int k0 = 0; k0 < k; k0 += 32) {
             const int kk = k0 + lane;
             cnt += __popc(__ballot_sync(CB_FULL_MASK, kk < k && __ldg(idx + (size_t)pt * k + kk) < pad));
         }
         const float inv = 1.0f / ((float)cnt + 1e-5f);
-        float acc[AW_CPL], g[AW_CPL];
 #pragma unroll
-        for (int i = 0; i < AW_CPL; i++) {
-            acc[i] = 0.f;
-            g[i] = (MODE == 1 && live[i]) ? __ldg(gout + (size_t)pt * c + ch0 + lane + 32 * i) * inv : 0.f;
-        }
-        for (int kk = 0; kk < k; kk++) {
-            const int j = __ldg(idx + (size_t)pt * k + kk);
-            if (j >= n0) continue;                                     // shadow neighbour: zero feature row
-            const float dx = (__ldg(spts + 3 * j) - qx) / radius, dy = (__ldg(spts + 3 * j + 1) - qy) / radius,
-                        dz = (__ldg(spts + 3 * j + 2) - qz) / radius;
-#pragma unroll
-            for (int i = 0; i < AW_CPL; i++) {
-                if (!live[i]) continue;
-                const int ch = ch0 + lane + 32 * i;
-                const float f = __ldg(feat + (size_t)j * c + ch);
-                const float w = w0[i] * dx + w1[i] * dy + w2[i] * dz + bb[i];
-                if (MODE == 0) {
-                    acc[i] += w * f;
+        for (int i = 0; i < AW_CPL; i++) g[i] = (MODE == 1 && live[i]) ? __ldg(gout + (size_t)pt * c + ch0 + lane + 32 * i) * inv : 0.f;
+        // neighbours in chunks of 32: lane kk fetches ITS neighbour's index and relative position (one parallel gather
+        // instead of K serial broadcast loads), then the chunk is walked 4 neighbours at a time with all feature loads
+        // of the 4 rows in flight together
+        for (int k0 = 0; k0 < k; k0 += 32) {
+            const int kk = k0 + lane;
+            int jl = n0;
+            float dxl = 0.f, dyl = 0.f, dzl = 0.f;
+            if (kk < k) {
+                jl = __ldg(idx + (size_t)pt * k + kk);
+                if (jl >= 0 && jl < n0) {
+                    dxl = (__ldg(spts + 3 * jl) - qx) / radius; dyl = (__ldg(spts + 3 * jl + 1) - qy) / radius;
+                    dzl = (__ldg(spts + 3 * jl + 2) - qz) / radius;
                 } else {
-                    atomicAdd(gfeat + (size_t)j * c + ch, g[i] * w);
-                    const float gf = g[i] * f;
-                    aW[i][0] += gf * dx; aW[i][1] += gf * dy; aW[i][2] += gf * dz; ab[i] += gf;
+                    jl = n0;
+                }
+            }
+            const int kend = min(32, k - k0);
+            for (int u0 = 0; u0 < kend; u0 += 4) {
+                int j[4];
+                float dx[4], dy[4], dz[4], f[4][AW_CPL];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int src = min(u0 + u, 31);
+                    j[u] = __shfl_sync(CB_FULL_MASK, jl, src);
+                    dx[u] = __shfl_sync(CB_FULL_MASK, dxl, src); dy[u] = __shfl_sync(CB_FULL_MASK, dyl, src);
+                    dz[u] = __shfl_sync(CB_FULL_MASK, dzl, src);
+                    if (u0 + u >= kend) j[u] = n0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int i = 0; i < AW_CPL; i++)
+                        f[u][i] = (j[u] < n0 && live[i]) ? __ldg(feat + (size_t)j[u] * c + ch0 + lane + 32 * i) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j[u] >= n0) continue;                          // shadow neighbour: zero feature row (warp-uniform)
+#pragma unroll
+                    for (int i = 0; i < AW_CPL; i++) {
+                        if (!live[i]) continue;
+                        const float w = w0[i] * dx[u] + w1[i] * dy[u] + w2[i] * dz[u] + bb[i];
+                        if (MODE == 0) {
+                            acc[i] += w * f[u][i];
+                        } else {
+                            atomicAdd(gfeat + (size_t)j[u] * c + ch0 + lane + 32 * i, g[i] * w);
+                            const float gf = g[i] * f[u][i];
+                            aW[i][0] += gf * dx[u]; aW[i][1] += gf * dy[u]; aW[i][2] += gf * dz[u]; ab[i] += gf;
+                        }
+                    }
                 }
             }
         }
@@ -102,7 +135,7 @@ __global__ void __launch_bounds__(AW_THREADS) k_aw(int n, int k, int c, int n0, 
 static dim3 aw_grid(int n, int c)
 {
     int gx = (n + AW_THREADS / 32 - 1) / (AW_THREADS / 32);
-    if (gx > 148 * 4) gx = 148 * 4;
+    if (gx > 148 * 8) gx = 148 * 8;
     if (gx < 1) gx = 1;
     return dim3(gx, (c + 32 * AW_CPL - 1) / (32 * AW_CPL));
 }

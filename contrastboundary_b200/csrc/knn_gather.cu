@@ -575,10 +575,10 @@ __global__ void k_regather_flagged(int K, int c, const float *__restrict__ feat,
 
 static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const float *new_xyz, const float *feat,
                              const int *offset, const int *new_offset, int b, int n, int *idx, float *dist2, float *grouped,
-                             const CbGridView &v, cudaStream_t st)
+                             const CbGridView &v, cudaStream_t st, bool fresh_grid = false)
 {
     if (m == 0) return CB_OK;
-    cb_knn_reset_flagged(v, st);
+    if (!fresh_grid) cb_knn_reset_flagged(v, st);      // a grid built a moment ago already has flagged_count = 0
     const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
     int slab = g_kg_chunk_bytes;
     if (slab < c * 4) slab = c * 4;
@@ -730,5 +730,5 @@ extern "C" int cb_knn_gather(int m, int nsample, int c, const float *xyz, int n,
     CB_REQUIRE(workspace_bytes >= need, CB_EWORKSPACE, "cb_knn_gather: workspace %zu < %zu", workspace_bytes, need);
     int rc = cb_grid_build_impl(xyz, n, offset, b, nsample, v, st);
     if (rc) return rc;
-    return knn_gather_launch(m, nsample, c, xyz, new_xyz, feat, offset, new_offset, b, n, idx, dist2, grouped, v, st);
+    return knn_gather_launch(m, nsample, c, xyz, new_xyz, feat, offset, new_offset, b, n, idx, dist2, grouped, v, st, true);
 }

@@ -49,3 +49,72 @@ def test_hard_labels_and_nearest_index_brute_force():
     assert up[2].shape == (600,) and cls[2].shape == (15,) and (up[2] <= 15).all()
     d = ((p0[:, None] - p2[None]) ** 2).sum(-1)
     assert np.array_equal(np.where(d.min(1) < 0.09, d.argmin(1), 15), up[2])
+
+
+# ---- the torch module composition of contrastboundary_b200/convnet.py against the NumPy restatement, in float64 on the CPU -------
+def _cpu_pyramid(pts, feats, labels, lens, cfg):
+    """tf_pyramid.segmentation_inputs_radius with the CPU restatements of the reference operators (oracle/tfops_oracle.cpp)"""
+    import oracle
+    dl, r = cfg.first_subsampling_dl, cfg.first_subsampling_dl * cfg.density_parameter / 2
+    nl, lim = cfg.num_layers, cfg.neighborhood_limits
+    P, N, PO, UP, LE = [None] * nl, [None] * nl, [None] * nl, [None] * nl, [None] * nl
+    UP[0] = np.zeros((0, 1), np.int32)
+    for l in range(nl - 1):
+        nb = oracle.batch_neighbors(pts, pts, lens, lens, r)[:, :lim[l]]
+        pp, pl = oracle.batch_grid_subsampling(pts, lens, 2 * dl)
+        po = oracle.batch_neighbors(pp, pts, pl, lens, r)[:, :lim[l]]
+        up = oracle.batch_neighbors(pts, pp, lens, pl, 2 * r)[:, :lim[l]]
+        P[l], N[l], PO[l], UP[l + 1], LE[l] = pts, nb, po, up, lens
+        pts, lens, r, dl = pp, pl, 2 * r, 2 * dl
+    P[nl - 1], LE[nl - 1] = pts, lens
+    N[nl - 1] = oracle.batch_neighbors(pts, pts, lens, lens, r)[:, :lim[nl - 1]]
+    PO[nl - 1] = np.zeros((0, 1), np.int32)
+    return {"points": P, "neighbors": N, "pools": PO, "upsamples": UP, "batches_len": LE, "features": feats, "point_labels": labels}
+
+
+def test_convnet_modules_match_float64_restatement_and_finite_differences(monkeypatch):
+    """convnet.ConvNetSeg / ConvNetLoss with the libcbops operators swapped for plain-torch twins (the CUDA operators cannot run
+    here), float64, CPU: (1) logits and every loss term equal the NumPy restatement to 1e-6 — the module wiring (radii, strides,
+    shortcuts, upsampling, heads) is the restatement's; (2) autograd equals float64 central differences of the RESTATEMENT's loss."""
+    from contrastboundary_b200 import convnet, linear_ops, synthetic, tf_pyramid
+    sizes = [1600, 1300]
+    scenes = [synthetic.make_scene(n, 300 + i) for i, n in enumerate(sizes)]
+    pts = np.concatenate([s[0] for s in scenes])
+    feats = np.concatenate([np.ones((len(pts), 1), np.float32), np.concatenate([s[1] for s in scenes]), pts[:, 2:3]], 1)
+    labels = np.concatenate([s[2] for s in scenes])
+    cfg = convnet.ConvNetConfig()
+    inp = _cpu_pyramid(pts, feats, labels, np.array(sizes, np.int32), tf_pyramid.PyramidConfig())
+    monkeypatch.setattr(convnet, "adaptive_weight", lambda q, s, nb, f, w, b, r: T.adaptive_weight(q, s, nb, f, w, b, r))
+    monkeypatch.setattr(convnet, "ind_max_pool", lambda x, inds: torch.cat([x, x.min(0, keepdim=True)[0].detach()], 0)[inds.long()].max(1)[0])
+    monkeypatch.setattr(convnet, "tf_contrast_loss", lambda f, nb, c, t, w: T.contrast_loss(f, nb, c.long(), t, w))
+    monkeypatch.setattr(linear_ops, "FUSED_BN", False)
+    torch.manual_seed(1)
+    model = convnet.ConvNetSeg(cfg).double().train()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g).double())
+    as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double() if a.dtype.kind == "f" else torch.from_numpy(np.ascontiguousarray(a))
+    tin = {k: ([as_t(a) for a in v] if isinstance(v, list) else as_t(v)) for k, v in inp.items()}
+    P0 = {k: v.detach().numpy().astype(np.float64) for k, v in model.state_dict().items() if v.dtype.is_floating_point}
+    rl, rloss, _, (up0, cls) = R.forward(P0, inp, cfg)
+    geo = {"up_idx0": [None] + [torch.from_numpy(u) for u in up0[1:]], "cls": [torch.from_numpy(np.asarray(c)).int() for c in cls]}
+    logits, sl = model(tin, geo)
+    loss = convnet.ConvNetLoss(cfg)(logits, tin["point_labels"], sl)
+    # (1e-6, not 1e-12: oracle/tf_model.py keeps TF's float32 neighbour count `cnt + 1e-5`)
+    assert np.abs(logits.detach().numpy() - rl).max() < 1e-6 * np.abs(rl).max()
+    np.testing.assert_allclose(loss.detach().numpy(), rloss, rtol=1e-6, atol=1e-12)
+    loss.sum().backward()
+    params = dict(model.named_parameters())
+    rng = np.random.default_rng(0)
+    for gname, sel, rel in (("1x1 kernels", lambda n: n.endswith("weights.weight"), 2e-8), ("fc_1", lambda n: ".fc_1." in n, 2e-9),
+                            ("batch norm", lambda n: ".bn." in n or ".pool_bn." in n, 2e-8)):
+        names = [n for n in params if sel(n)]
+        d = {n: rng.standard_normal(params[n].shape) for n in names}
+        eps = rel / np.sqrt(sum(float((v ** 2).sum()) for v in d.values())) * np.sqrt(sum(float((P0[n] ** 2).sum()) for n in names))
+        lp = R.forward({**P0, **{n: P0[n] + eps * d[n] for n in names}}, inp, cfg)[1].sum()
+        lm = R.forward({**P0, **{n: P0[n] - eps * d[n] for n in names}}, inp, cfg)[1].sum()
+        fd = (lp - lm) / (2 * eps)
+        an = sum(float((params[n].grad.numpy() * d[n]).sum()) for n in names)
+        assert abs(fd - an) <= 2e-3 * abs(fd), (gname, fd, an)

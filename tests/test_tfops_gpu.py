@@ -183,3 +183,40 @@ def _pad_cols(a, width):
         return a
     assert (a[:, width:] == a.max()).all()
     return a[:, :width]
+
+
+def test_calibrate_neighbors_and_batches():
+    """tf_pyramid.calibrate_neighbors / calibrate_batches (tensorflow/datasets/base.py:158-294) against the same procedure
+    evaluated with the CPU restatement of the reference's radius search"""
+    import math
+    import oracle
+    from contrastboundary_b200 import synthetic, tf_pyramid
+    cfg = tf_pyramid.PyramidConfig()
+    batches = []
+    for s in range(2):
+        clouds = [synthetic.make_scene(5000, 900 + 10 * s + i)[0] for i in range(2)]
+        batches.append((np.concatenate(clouds).astype(np.float32), np.array([5000, 5000], np.int32)))
+    limits = tf_pyramid.calibrate_neighbors(batches, cfg, keep_ratio=0.8, samples_threshold=10 ** 9)
+    hist_n = int(math.ceil(4 / 3 * math.pi * (cfg.density_parameter + 1) ** 3))
+    hists = np.zeros((cfg.num_layers, hist_n), np.int64)
+    for pts, lens in batches:
+        dl, r = cfg.first_subsampling_dl, cfg.first_subsampling_dl * cfg.density_parameter / 2
+        for layer in range(cfg.num_layers):
+            nb = oracle.batch_neighbors(pts, pts, lens, lens, r)
+            counts = np.sum(nb < nb.shape[0], axis=1)                       # base.py:266
+            hists[layer] += np.bincount(counts, minlength=hist_n)[:hist_n]
+            if layer + 1 < cfg.num_layers:
+                pts, lens = oracle.batch_grid_subsampling(pts, lens, 2 * dl)
+                r, dl = 2 * r, 2 * dl
+    cumsum = np.cumsum(hists.T, axis=0)
+    ref = np.sum(cumsum < (0.8 * cumsum[hist_n - 1, :]), axis=0)            # base.py:286-287
+    assert limits == [int(v) for v in ref], (limits, ref)
+    assert all(5 < v < 80 for v in limits)
+    clouds = [synthetic.make_scene(20000, 950 + i)[0] for i in range(2)]
+    lim = tf_pyramid.calibrate_batches(clouds, in_radius=1.0, batch_size=4, rng=np.random.default_rng(0), n_samples=400)
+    # the proportional corrector converges to a budget of ~batch_size average spheres
+    sizes = []
+    for c in clouds:
+        d = np.random.default_rng(1).choice(len(c), 100, replace=False)
+        sizes += [int((((c - c[i]) ** 2).sum(1) < 1.0).sum()) for i in d]
+    assert 2.5 * np.mean(sizes) < lim < 6.0 * np.mean(sizes), (lim, np.mean(sizes))
