@@ -1,0 +1,248 @@
+// umma_linear.cu — tall-skinny FP32 linear layers on the 5th-generation tensor cores (Blackwell, sm_100a):
+//     Y (n x N) = A (n x K) . B^T (+ bias)      B = W (N x K, forward) or W^T (dgrad: W is K x N)
+// tcgen05.mma kind::tf32 issued by ONE thread per CTA, operands in shared memory (K-major core-matrix layout, no
+// swizzle, written by the CTA's threads while they split every FP32 value into TF32 hi + lo), accumulator in TENSOR
+// MEMORY (TMEM, 128 lanes x N columns), completion through tcgen05.commit -> mbarrier, epilogue tcgen05.ld -> registers
+// -> + bias -> global.  3xTF32 error compensation (hi*hi + lo*hi + hi*lo, FP32 accumulate) keeps the FP32 parity of
+// tc_gemm.cu (1e-5 against float64) — the reference runs these layers as FP32 cuBLAS GEMMs (nn.Linear in
+// pytorch/model/blocks.py:33,72,76,108,127-131).
+// The legacy warp-level path (mma.sync, tc_gemm.cu) stays as the fallback for shapes this kernel does not take
+// (K % 8 != 0, N % 16 != 0) and behind cb_linear_set_umma(0).
+#include "common.cuh"
+
+#define UM_THREADS 128
+#define UM_KC 32                       // K floats staged per chunk (4 MMA k-steps of 8)
+
+__device__ __forceinline__ unsigned um_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void um_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void um_mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): in 16-byte units
+//   bits [0,14) start address, [16,30) leading byte offset (between the two 16-byte K chunks of one MMA),
+//   [32,46) stride byte offset (between 8-row groups), [46,48) version = 1, [61,64) layout type = 0
+__device__ __forceinline__ unsigned long long um_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes)
+{
+    return (unsigned long long)((smem_addr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((unsigned long long)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, one 128 x N x 8 TF32 MMA (cute::SM100_MMA_TF32_SS)
+__device__ __forceinline__ void um_mma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                            unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void um_split(float x, float &hi, float &lo)
+{
+    unsigned h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));          // round to nearest TF32 (10-bit mantissa)
+    hi = __uint_as_float(h);
+    lo = x - hi;                                                   // exact in FP32; the MMA reads its TF32 part
+}
+
+// element (row, kf) of a staged tile, kf in [0, UM_KC): core matrix (row / 8, kf / 4) of 8 rows x 16 bytes
+__device__ __forceinline__ unsigned um_off(int row, int kf)
+{
+    return (unsigned)(((row >> 3) * (UM_KC / 4) + (kf >> 2)) * 128 + (row & 7) * 16 + (kf & 3) * 4);
+}
+
+template <int TRANS_B>
+__global__ void __launch_bounds__(UM_THREADS) k_umma_linear(int n, int K, int N, int ncols, const float *__restrict__ A, int lda,
+                                                            const float *__restrict__ W, const float *__restrict__ bias,
+                                                            float *__restrict__ Y, int ldy, int n0 /* first output column */,
+                                                            int ldw)
+{
+    extern __shared__ __align__(1024) unsigned char um_smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ unsigned tmem_slot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned a_hi = um_smem_u32(um_smem), a_lo = a_hi + 128 * UM_KC * 4;
+    const unsigned b_hi = a_lo + 128 * UM_KC * 4, b_lo = b_hi + (unsigned)N * UM_KC * 4;
+    unsigned char *pa_hi = um_smem, *pa_lo = pa_hi + 128 * UM_KC * 4, *pb_hi = pa_lo + 128 * UM_KC * 4,
+                  *pb_lo = pb_hi + (size_t)N * UM_KC * 4;
+    const unsigned bar = um_smem_u32(&mbar);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(&tmem_slot)), "r"((unsigned)ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        um_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_slot;
+    const long long row0 = (long long)blockIdx.x * 128;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
+    unsigned phase = 0;
+    for (int k0 = 0; k0 < K; k0 += UM_KC) {
+        const int kc = min(UM_KC, K - k0);                 // multiple of 8
+        // ---- stage the A chunk: lane -> (row % 8, 16-byte chunk % 4): 64 contiguous bytes of 8 rows per warp instruction,
+        //      128 contiguous bytes of shared memory per 8 lanes (conflict free)
+        for (int it = warp; it < 16 * (UM_KC / 16); it += UM_THREADS / 32) {
+            const int g = it % 16, cq = it / 16;                       // 8-row group, quad of 16-byte chunks
+            const int row = g * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
+            const int kf = c * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kf < kc && row0 + row < n) v = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(row0 + row) * lda + k0 + kf));
+            float4 h, l;
+            um_split(v.x, h.x, l.x); um_split(v.y, h.y, l.y); um_split(v.z, h.z, l.z); um_split(v.w, h.w, l.w);
+            const unsigned o = um_off(row, kf);
+            *reinterpret_cast<float4 *>(pa_hi + o) = h;
+            *reinterpret_cast<float4 *>(pa_lo + o) = l;
+        }
+        // ---- stage the B chunk (N rows)
+        if (!TRANS_B) {                                     // W is (N x K): same mapping as A
+            const int groups = N / 8;
+            for (int it = warp; it < groups * (UM_KC / 16); it += UM_THREADS / 32) {
+                const int g = it % groups, cq = it / groups;
+                const int row = g * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
+                const int kf = c * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kf < kc) v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(n0 + row) * ldw + k0 + kf));
+                float4 h, l;
+                um_split(v.x, h.x, l.x); um_split(v.y, h.y, l.y); um_split(v.z, h.z, l.z); um_split(v.w, h.w, l.w);
+                const unsigned o = um_off(row, kf);
+                *reinterpret_cast<float4 *>(pb_hi + o) = h;
+                *reinterpret_cast<float4 *>(pb_lo + o) = l;
+            }
+        } else {                                            // W is (K x N): B(row, kf) = W[k0 + kf][n0 + row]
+            for (int e = tid; e < N * UM_KC; e += UM_THREADS) {
+                const int row = e % N, kf = e / N;
+                float v = 0.f;
+                if (kf < kc) v = __ldg(W + (size_t)(k0 + kf) * ldw + n0 + row);
+                float h, l;
+                um_split(v, h, l);
+                const unsigned o = um_off(row, kf);
+                *reinterpret_cast<float *>(pb_hi + o) = h;
+                *reinterpret_cast<float *>(pb_lo + o) = l;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned lbo = 128, sbo = (UM_KC / 4) * 128;
+            for (int s = 0; s < kc / 8; s++) {
+                const unsigned adv = (unsigned)s * 256;                   // two 16-byte K chunks per MMA
+                const unsigned long long dah = um_desc(a_hi + adv, lbo, sbo), dal = um_desc(a_lo + adv, lbo, sbo);
+                const unsigned long long dbh = um_desc(b_hi + adv, lbo, sbo), dbl = um_desc(b_lo + adv, lbo, sbo);
+                um_mma_tf32(tmem, dah, dbh, idesc, (k0 > 0 || s > 0) ? 1u : 0u);
+                um_mma_tf32(tmem, dal, dbh, idesc, 1u);
+                um_mma_tf32(tmem, dah, dbl, idesc, 1u);
+            }
+            // completion of every MMA issued so far -> one arrival on the mbarrier (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        }
+        um_mbar_wait(bar, phase);                           // the staged chunk may be overwritten / the accumulator read
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // ---- epilogue: warp w owns TMEM lanes 32w .. 32w+31 = output rows; 8 columns per tcgen05.ld
+    const long long row = row0 + warp * 32 + lane;
+    for (int col = 0; col < N; col += 8) {
+        unsigned r[8];
+        const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)col;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < n) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[e] = __uint_as_float(r[e]) + (bias ? __ldg(bias + n0 + col + e) : 0.f);
+            float4 *dst = reinterpret_cast<float4 *>(Y + (size_t)row * ldy + n0 + col);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
+}
+
+static int g_umma = 1;      // 1: tcgen05 path for the shapes it takes (default) | 0: mma.sync kernels (tc_gemm.cu)
+extern "C" int cb_linear_set_umma(int on)
+{
+    if (on == 0 || on == 1) g_umma = on;
+    return g_umma;
+}
+int cb_umma_enabled() { return g_umma; }
+
+bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int lda, int ldy)
+{
+    return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && lda % 4 == 0 && ldy % 4 == 0 &&
+           (((uintptr_t)A | (uintptr_t)Y) & 15) == 0;
+}
+
+// Y (n x N) = A (n x K) . B^T (+ bias); trans_b = 0: W is (N x K) (forward), 1: W is (K x N) (dgrad).  N is processed in
+// column blocks of <= 256 (one TMEM allocation each).
+int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W, int trans_b, const float *bias, float *Y, int ldy,
+                   cudaStream_t st)
+{
+    const int ldw = trans_b ? N : K;
+    for (int c0 = 0; c0 < N; c0 += 256) {
+        const int nb = N - c0 < 256 ? N - c0 : 256;
+        int ncols = 32;
+        while (ncols < nb) ncols <<= 1;
+        const size_t smem = (size_t)(2 * 128 + 2 * nb) * UM_KC * 4;
+        const int blocks = (n + 127) / 128;
+        if (trans_b) {
+            cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_umma_linear<1><<<blocks, UM_THREADS, smem, st>>>(n, K, nb, ncols, A, lda, W, bias, Y, ldy, c0, ldw);
+        } else {
+            cudaFuncSetAttribute(k_umma_linear<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_umma_linear<0><<<blocks, UM_THREADS, smem, st>>>(n, K, nb, ncols, A, lda, W, bias, Y, ldy, c0, ldw);
+        }
+        CB_COUNT(1);
+    }
+    return CB_OK;
+}
+
+// stand-alone entry point (tests, microbench): see include/cbops.h
+extern "C" int cb_umma_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream)
+{
+    CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && X && W && Y, CB_EINVAL, "cb_umma_linear_forward: bad arguments");
+    CB_REQUIRE(ci % 8 == 0 && co % 16 == 0 && ((((uintptr_t)X | (uintptr_t)Y) & 15) == 0), CB_EUNSUPPORTED,
+               "cb_umma_linear_forward: needs ci %% 8 == 0, co %% 16 == 0, 16-byte aligned X / Y");
+    if (n == 0) return CB_OK;
+    cb_umma_linear(n, ci, co, X, ci, W, 0, b, Y, co, (cudaStream_t)stream);
+    CB_CUDA_CHECK("cb_umma_linear_forward");
+    return CB_OK;
+}
+
+extern "C" int cb_umma_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, void *stream)
+{
+    CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && G && W && dX, CB_EINVAL, "cb_umma_linear_dgrad: bad arguments");
+    CB_REQUIRE(co % 8 == 0 && ci % 16 == 0 && ((((uintptr_t)G | (uintptr_t)dX) & 15) == 0), CB_EUNSUPPORTED,
+               "cb_umma_linear_dgrad: needs co %% 8 == 0, ci %% 16 == 0, 16-byte aligned G / dX");
+    if (n == 0) return CB_OK;
+    cb_umma_linear(n, co, ci, G, co, W, 1, nullptr, dX, ci, (cudaStream_t)stream);      // dX = G (n x co) . W (co x ci)
+    CB_CUDA_CHECK("cb_umma_linear_dgrad");
+    return CB_OK;
+}

@@ -300,6 +300,16 @@ int cb_bn_act_backward(long long n, int c, const float *x, const float *y, const
  * wgrad).  Returns the setting in force. */
 int cb_linear_set_tensor_cores(int on);
 
+/* tall-skinny linear layers on the 5th-generation tensor cores (umma_linear.cu): tcgen05.mma kind::tf32 issued by one thread
+ * per CTA, operands staged in shared memory as TF32 hi + lo (3xTF32: FP32 parity, 1e-5 vs float64), accumulator in tensor
+ * memory (TMEM), tcgen05.ld epilogue.  cb_linear_forward / cb_linear_dgrad route here when the shape allows
+ * (ci % 8 == 0 and co % 16 == 0, resp. co % 8 == 0 and ci % 16 == 0; 16-byte aligned rows); cb_linear_set_umma(0) returns
+ * to the mma.sync kernels.  Same math as the nn.Linear calls of pytorch/model/blocks.py:33,72,76,108,127-131. */
+int cb_umma_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream);
+int cb_umma_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, void *stream);
+int cb_linear_set_umma(int on);
+int cb_grid_set_fused(int mode);   /* 1 (default): the search-grid build is ONE cooperative kernel; 0: ten small kernels; 2: fused unless capturing */
+
 /* backward of cb_pt_layer_forward.  grad_xk / grad_xv (n,c) and grad_params must be ZERO-FILLED by the
  * caller (scatter / accumulation targets); grad_xq is overwritten.  grad_params layout (floats):
  * [dW1 9][db1 3][dbn1_w 3][dbn1_b 3][dW2 3c][db2 c][dbn2_w c][dbn2_b c][dW3 c*c/8][db3 c/8][dbn3_w c/8]
