@@ -221,10 +221,19 @@ void cb_tc_linear_dgrad(int n, int ci, int co, const float *G, const float *W, f
 void cb_tc_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float *dW, float *db, const float *xsc,
                         const float *xsh, cudaStream_t st);
 
+bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int lda, int ldy);
+int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W, int trans_b, const float *bias, float *Y, int ldy,
+                   cudaStream_t st);
+
 extern "C" int cb_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream)
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && X && W && Y, CB_EINVAL, "cb_linear_forward: bad arguments");
     if (n == 0) return CB_OK;
+    if (cb_tc_enabled() && cb_umma_shape_ok(n, ci, co, X, Y, ci, co)) {      // tcgen05 + TMEM (umma_linear.cu)
+        cb_umma_linear(n, ci, co, X, ci, W, 0, b, Y, co, (cudaStream_t)stream);
+        CB_CUDA_CHECK("cb_linear_forward");
+        return CB_OK;
+    }
     if (cb_tc_enabled()) {
         cb_tc_linear_forward(n, ci, co, X, W, b, Y, (cudaStream_t)stream);
         CB_COUNT(1);
@@ -241,6 +250,11 @@ extern "C" int cb_linear_dgrad(int n, int ci, int co, const float *G, const floa
 {
     CB_REQUIRE(n >= 0 && ci > 0 && co > 0 && G && W && dX, CB_EINVAL, "cb_linear_dgrad: bad arguments");
     if (n == 0) return CB_OK;
+    if (cb_tc_enabled() && cb_umma_shape_ok(n, co, ci, G, dX, co, ci)) {     // dX = G (n x co) . W (co x ci)
+        cb_umma_linear(n, co, ci, G, co, W, 1, nullptr, dX, ci, (cudaStream_t)stream);
+        CB_CUDA_CHECK("cb_linear_dgrad");
+        return CB_OK;
+    }
     if (cb_tc_enabled()) {
         cb_tc_linear_dgrad(n, ci, co, G, W, dX, (cudaStream_t)stream);
         CB_COUNT(1);
