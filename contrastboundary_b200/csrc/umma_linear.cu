@@ -186,6 +186,203 @@ __global__ void __launch_bounds__(UM_THREADS) k_umma_linear(int n, int K, int N,
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: persistent, warp-specialised, pipelined.  One CTA per SM walks the 128-row tiles:
+//   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> + bias -> global      (warp w <-> TMEM lanes 32w..32w+31)
+//   warps 4-7  producers  global A rows -> TF32 hi / lo -> shared memory core-matrix layout, UM2_STAGES-deep ring
+//   warp  8    one lane issues every tcgen05.mma; tcgen05.commit releases ring slots / publishes accumulators
+// W (hi / lo, all of K) is staged ONCE per CTA.  Two accumulators in TMEM (2 x N columns): the MMAs of tile t+1 run while
+// the epilogue drains tile t.  Four mbarrier families: full[s] (4 producer warps -> MMA), empty[s] (commit -> producers),
+// tfull[b] (commit -> epilogue), tempty[b] (4 epilogue warps -> MMA).
+// ---------------------------------------------------------------------------------------------
+#define UM2_THREADS 288
+#define UM2_STAGES 3
+
+__device__ __forceinline__ void um_mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int TRANS_B>
+__global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, int N, int ncols, int ntiles, const float *__restrict__ A,
+                                                                 int lda, const float *__restrict__ W, const float *__restrict__ bias,
+                                                                 float *__restrict__ Y, int ldy, int n0, int ldw)
+{
+    extern __shared__ __align__(1024) unsigned char um_smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * UM2_STAGES + 4];
+    __shared__ unsigned tmem_slot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunk = (K + UM_KC - 1) / UM_KC;
+    const unsigned w_bytes = (unsigned)N * UM_KC * 4;                 // one K chunk of W (hi or lo)
+    // layout: [W hi chunks][W lo chunks][stage 0: A hi, A lo][stage 1 ...]
+    unsigned char *pw_hi = um_smem, *pw_lo = pw_hi + (size_t)nchunk * w_bytes;
+    unsigned char *pa = pw_lo + (size_t)nchunk * w_bytes;
+    const unsigned sw_hi = um_smem_u32(pw_hi), sw_lo = um_smem_u32(pw_lo), sa = um_smem_u32(pa);
+    const unsigned a_stage = 2 * 128 * UM_KC * 4;
+    const unsigned b_full = um_smem_u32(&bars[0]), b_empty = um_smem_u32(&bars[UM2_STAGES]), b_tfull = um_smem_u32(&bars[2 * UM2_STAGES]),
+                   b_tempty = um_smem_u32(&bars[2 * UM2_STAGES + 2]);
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(&tmem_slot)), "r"((unsigned)ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < UM2_STAGES; s++) { um_mbar_init(b_full + 8 * s, 4); um_mbar_init(b_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { um_mbar_init(b_tfull + 8 * b, 1); um_mbar_init(b_tempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- W, once: every thread helps
+    for (int j = 0; j < nchunk; j++) {
+        const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
+        unsigned char *dh = pw_hi + (size_t)j * w_bytes, *dl = pw_lo + (size_t)j * w_bytes;
+        if (!TRANS_B) {
+            const int groups = N / 8;
+            for (int it = warp; it < groups * (UM_KC / 16); it += UM2_THREADS / 32) {
+                const int g = it % groups, cq = it / groups;
+                const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kf < kc) v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(n0 + row) * ldw + k0 + kf));
+                float4 h, l;
+                um_split(v.x, h.x, l.x); um_split(v.y, h.y, l.y); um_split(v.z, h.z, l.z); um_split(v.w, h.w, l.w);
+                const unsigned o = um_off(row, kf);
+                *reinterpret_cast<float4 *>(dh + o) = h;
+                *reinterpret_cast<float4 *>(dl + o) = l;
+            }
+        } else {
+            for (int e = tid; e < N * UM_KC; e += UM2_THREADS) {
+                const int row = e % N, kf = e / N;
+                float v = 0.f;
+                if (kf < kc) v = __ldg(W + (size_t)(k0 + kf) * ldw + n0 + row);
+                float h, l;
+                um_split(v, h, l);
+                const unsigned o = um_off(row, kf);
+                *reinterpret_cast<float *>(dh + o) = h;
+                *reinterpret_cast<float *>(dl + o) = l;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_slot;
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const unsigned lbo = 128, sbo = (UM_KC / 4) * 128;
+
+    if (warp >= 4 && warp < 8) {
+        // ===== producers =====
+        const int pw = warp - 4;
+        unsigned it_count = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long row0 = (long long)tile * 128;
+            for (int j = 0; j < nchunk; j++, it_count++) {
+                const int stage = it_count % UM2_STAGES;
+                const unsigned use = it_count / UM2_STAGES;
+                um_mbar_wait(b_empty + 8 * stage, (use & 1u) ^ 1u);          // slot free (passes on first use)
+                const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
+                unsigned char *dh = pa + (size_t)stage * a_stage, *dl = dh + 128 * UM_KC * 4;
+                // 32 warp-instructions per chunk (16 row groups x 2 chunk quads), 8 per producer warp: loads first, stores after
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int it = pw + 4 * u;
+                    const int g = it % 16, cq = it / 16;
+                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kf < kc && row0 + row < n) v[u] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(row0 + row) * lda + k0 + kf));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int it = pw + 4 * u;
+                    const int g = it % 16, cq = it / 16;
+                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                    float4 h, l;
+                    um_split(v[u].x, h.x, l.x); um_split(v[u].y, h.y, l.y); um_split(v[u].z, h.z, l.z); um_split(v[u].w, h.w, l.w);
+                    const unsigned o = um_off(row, kf);
+                    *reinterpret_cast<float4 *>(dh + o) = h;
+                    *reinterpret_cast<float4 *>(dl + o) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) um_mbar_arrive(b_full + 8 * stage);
+            }
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            unsigned it_count = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+                const unsigned buf = tcount & 1u, tuse = tcount >> 1;
+                um_mbar_wait(b_tempty + 8 * buf, (tuse & 1u) ^ 1u);              // accumulator drained (passes on first use)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned acc = tmem + buf * (unsigned)N;
+                for (int j = 0; j < nchunk; j++, it_count++) {
+                    const int stage = it_count % UM2_STAGES;
+                    const unsigned use = it_count / UM2_STAGES;
+                    um_mbar_wait(b_full + 8 * stage, use & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int kc = min(UM_KC, K - j * UM_KC);
+                    const unsigned ah = sa + stage * a_stage, al = ah + 128 * UM_KC * 4;
+                    const unsigned bh = sw_hi + j * w_bytes, bl = sw_lo + j * w_bytes;
+                    for (int s = 0; s < kc / 8; s++) {
+                        const unsigned adv = (unsigned)s * 256;
+                        const unsigned long long dah = um_desc(ah + adv, lbo, sbo), dal = um_desc(al + adv, lbo, sbo);
+                        const unsigned long long dbh = um_desc(bh + adv, lbo, sbo), dbl = um_desc(bl + adv, lbo, sbo);
+                        um_mma_tf32(acc, dah, dbh, idesc, (j > 0 || s > 0) ? 1u : 0u);
+                        um_mma_tf32(acc, dal, dbh, idesc, 1u);
+                        um_mma_tf32(acc, dah, dbl, idesc, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_empty + 8 * stage) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_tfull + 8 * buf) : "memory");
+            }
+        }
+    } else {
+        // ===== epilogue (warps 0-3) =====
+        unsigned tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const unsigned buf = tcount & 1u, tuse = tcount >> 1;
+            um_mbar_wait(b_tfull + 8 * buf, tuse & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row = (long long)tile * 128 + warp * 32 + lane;
+            for (int col = 0; col < N; col += 16) {
+                unsigned r[16];
+                const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + buf * (unsigned)N + (unsigned)col;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < n) {
+                    float4 *dst = reinterpret_cast<float4 *>(Y + (size_t)row * ldy + n0 + col);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        float4 o = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                               __uint_as_float(r[4 * q + 3]));
+                        if (bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col) + q);
+                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        }
+                        dst[q] = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) um_mbar_arrive(b_tempty + 8 * buf);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
+}
+
+static int g_umma_v = 2;    // kernel version used by cb_umma_linear: 2 = persistent pipelined (default), 1 = simple one-tile CTAs
+extern "C" int cb_linear_set_umma_version(int v)
+{
+    if (v == 1 || v == 2) g_umma_v = v;
+    return g_umma_v;
+}
+
 static int g_umma = 1;      // 1: tcgen05 path for the shapes it takes (default) | 0: mma.sync kernels (tc_gemm.cu)
 extern "C" int cb_linear_set_umma(int on)
 {
@@ -206,6 +403,42 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
                    cudaStream_t st)
 {
     const int ldw = trans_b ? N : K;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    if (g_umma_v == 2) {
+        // column blocks such that W (hi + lo, all of K) + the A ring fit the 227 KB of one CTA; N of a block % 16 == 0, <= 256
+        const int nchunk = (K + UM_KC - 1) / UM_KC;
+        const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4;
+        int nb_max = (int)(((size_t)227 * 1024 - 2048 - a_ring) / ((size_t)2 * nchunk * UM_KC * 4));
+        nb_max = nb_max / 16 * 16;
+        if (nb_max > 256) nb_max = 256;
+        if (nb_max >= 16) {
+            const int nblocks = (N + nb_max - 1) / nb_max;
+            int nb_even = ((N + nblocks - 1) / nblocks + 15) / 16 * 16;           // balanced column blocks
+            const int ntiles = (n + 127) / 128;
+            for (int c0 = 0; c0 < N; c0 += nb_even) {
+                const int nb = N - c0 < nb_even ? N - c0 : nb_even;
+                int ncols = 32;
+                while (ncols < 2 * nb) ncols <<= 1;
+                const size_t smem = (size_t)2 * nchunk * nb * UM_KC * 4 + a_ring;
+                const int blocks = ntiles < sms ? ntiles : sms;
+                if (trans_b) {
+                    cudaFuncSetAttribute(k_umma_linear2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    k_umma_linear2<1><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
+                } else {
+                    cudaFuncSetAttribute(k_umma_linear2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    k_umma_linear2<0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
+                }
+                CB_COUNT(1);
+            }
+            return CB_OK;
+        }
+    }
     for (int c0 = 0; c0 < N; c0 += 256) {
         const int nb = N - c0 < 256 ? N - c0 : 256;
         int ncols = 32;

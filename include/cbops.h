@@ -308,6 +308,8 @@ int cb_linear_set_tensor_cores(int on);
 int cb_umma_linear_forward(int n, int ci, int co, const float *X, const float *W, const float *b, float *Y, void *stream);
 int cb_umma_linear_dgrad(int n, int ci, int co, const float *G, const float *W, float *dX, void *stream);
 int cb_linear_set_umma(int on);
+int cb_linear_set_umma_version(int v);   /* 2 (default): persistent warp-specialised pipeline (TMA-less producer warps, MMA
+                                            issuer, epilogue warps, double-buffered TMEM accumulators); 1: one tile per CTA */
 int cb_grid_set_fused(int mode);   /* 1 (default): the search-grid build is ONE cooperative kernel; 0: ten small kernels; 2: fused unless capturing */
 
 /* backward of cb_pt_layer_forward.  grad_xk / grad_xv (n,c) and grad_params must be ZERO-FILLED by the

@@ -8,12 +8,20 @@ from contrastboundary_b200 import _lib as L
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(1000, 32, 96), (40960, 64, 192), (163840, 32, 32), (5000, 128, 384), (777, 8, 16), (300, 40, 48), (129, 256, 256),
+SHAPES = [(1000, 32, 96), (150000, 32, 96), (60000, 72, 144), (40960, 64, 192), (163840, 32, 32), (5000, 128, 384), (777, 8, 16), (300, 40, 48), (129, 256, 256),
           (8192, 512, 512), (1, 16, 16)]
 
 
+@pytest.fixture(params=[2, 1], ids=["pipelined", "simple"])
+def version(request):
+    import ctypes as C
+    L.lib().cb_linear_set_umma_version(C.c_int(request.param))
+    yield request.param
+    L.lib().cb_linear_set_umma_version(C.c_int(2))
+
+
 @pytest.mark.parametrize("n,ci,co", SHAPES)
-def test_umma_forward_matches_float64(n, ci, co):
+def test_umma_forward_matches_float64(n, ci, co, version):
     g = torch.Generator(device="cuda").manual_seed(n + ci)
     x = torch.randn(n, ci, device="cuda", generator=g)
     w = torch.randn(co, ci, device="cuda", generator=g) / ci ** 0.5
@@ -29,7 +37,7 @@ def test_umma_forward_matches_float64(n, ci, co):
 
 
 @pytest.mark.parametrize("n,ci,co", SHAPES)
-def test_umma_dgrad_matches_float64(n, ci, co):
+def test_umma_dgrad_matches_float64(n, ci, co, version):
     if co % 8 or ci % 16:
         pytest.skip("dgrad needs co % 8 == 0 and ci % 16 == 0")
     g = torch.Generator(device="cuda").manual_seed(n + co)
