@@ -144,3 +144,37 @@ def test_trainer_metrics_scalars_and_sync_bn_option(tmp_path):
     assert any(isinstance(x, nn.SyncBatchNorm) for x in m.modules()) and not any(type(x) is nn.BatchNorm1d for x in m.modules())
     assert all(not x.fused for x in m.modules() if hasattr(x, "fused") and isinstance(x, (model.PointTransformerLayer, model.TransitionDown)))
     assert set(trainer.build_model().state_dict()) == set(m.state_dict())   # same checkpoint keys either way
+
+
+def test_reference_constructor_signatures():
+    """pointtransformer_seg_repro(c=, k=, config=) / Loss(config) / ContrastHead(head_cfg, config) take the reference's own
+    config node (pytorch/util/config.py CfgNode of the shipped yaml; pointtransformer_seg.py:15-66,139-143, heads.py:66)"""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    refpy = next((p for p in ("/root/reference/pytorch", os.path.join(root, "baseline", "_ref", "pytorch"))
+                  if os.path.exists(os.path.join(p, "util", "config.py"))), None)
+    cfg_dict = {"base_fdim": 32, "nsample": [36, 24, 24, 24, 24], "nstride": [4, 4, 4, 4], "ignore_label": 255, "voxel_size": 0.04,
+                "contrast": {"stage": "Ua", "contrast": "softnn", "ftype": "latent", "sample": "label", "pos": "cnt", "dist": "l2",
+                             "temperature": 1, "weight": "w.1"},
+                "multi": {"stage": "Ua", "ftype": "latent", "combine": "concat"}}
+    if refpy is not None:
+        sys.path.insert(0, refpy)
+        from util.config import CfgNode
+        cfg = CfgNode(json.loads(json.dumps(cfg_dict)), default="")
+    else:
+        cfg = cfg_dict
+    m = model.pointtransformer_seg_repro(c=6, k=13, config=cfg)
+    crit = model.Loss(cfg)
+    head = model.ContrastHead(cfg["contrast"] if isinstance(cfg, dict) else cfg.contrast, cfg)
+    assert m.cfg.nsample == [36, 24, 24, 24, 24] and m.cfg.contrast.weight == 0.1 and m.cfg.contrast.temperature == 1.0
+    assert head.stages == [("up", i) for i in range(5)] and crit.contrast_head is not None
+    assert len(m.state_dict()) == 960                                       # the reference network's parameter / buffer count
+    bad = dict(cfg_dict, contrast=dict(cfg_dict["contrast"], contrast="nce"))
+    import pytest
+    with pytest.raises(NotImplementedError):
+        model.Loss(bad)
+    plain = {k: v for k, v in cfg_dict.items() if k not in ("contrast", "multi")}
+    m2 = model.pointtransformer_seg_repro(c=6, k=13, config=plain)           # origin_4gpu.yaml: no heads, plain classifier
+    assert m2.head is None and m2.cls is not None and model.Loss(plain).contrast_head is None
