@@ -220,3 +220,30 @@ def test_calibrate_neighbors_and_batches():
         d = np.random.default_rng(1).choice(len(c), 100, replace=False)
         sizes += [int((((c - c[i]) ** 2).sum(1) < 1.0).sum()) for i in d]
     assert 2.5 * np.mean(sizes) < lim < 6.0 * np.mean(sizes), (lim, np.mean(sizes))
+
+
+def test_batch_neighbors_width_contract_and_wide_rows():
+    """tf_batch_neighbors: `limit` pads to exactly `limit` columns (no host read), exact_width=True reproduces the reference's
+    `neighbors[:, :limit]` shape min(max_count, limit) (datasets/base.py:762); rows wider than 256 (dense clouds during
+    neighbourhood calibration) take the exact scan"""
+    import oracle
+    from contrastboundary_b200 import synthetic, tf_ops
+    pts = synthetic.make_scene(3000, 41)[0]
+    lens = np.array([3000], np.int32)
+    ref = oracle.batch_neighbors(pts, pts, lens, lens, 0.1)
+    mx = ref.shape[1]
+    padded = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, 0.1, limit=mx + 7).cpu().numpy()
+    assert padded.shape == (3000, mx + 7) and (padded[:, mx:] == 3000).all()
+    exact = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, 0.1, limit=mx + 7, exact_width=True).cpu().numpy()
+    assert exact.shape == ref.shape
+    assert np.array_equal(np.sort(exact, 1), np.sort(ref, 1))               # same sets (order inside equal distances aside)
+    cropped = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, 0.1, limit=5, exact_width=True).cpu().numpy()
+    assert cropped.shape == (3000, 5)
+    wide_ref = oracle.batch_neighbors(pts, pts, lens, lens, 0.4)
+    assert wide_ref.shape[1] > 256
+    wide = tf_ops.tf_batch_neighbors(pts, pts, lens, lens, 0.4).cpu().numpy()
+    assert wide.shape == wide_ref.shape
+    assert np.array_equal((wide < 3000).sum(1), (wide_ref < 3000).sum(1))
+    rows = np.random.default_rng(0).choice(3000, 50, replace=False)
+    for r in rows:
+        assert np.array_equal(np.sort(wide[r]), np.sort(wide_ref[r]))
