@@ -189,14 +189,18 @@ __global__ void __launch_bounds__(UM_THREADS) k_umma_linear(int n, int K, int N,
 // ---------------------------------------------------------------------------------------------
 // v2: persistent, warp-specialised, pipelined.  One CTA per SM walks the 128-row tiles:
 //   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> + bias -> global      (warp w <-> TMEM lanes 32w..32w+31)
-//   warps 4-7  producers  global A rows -> TF32 hi / lo -> shared memory core-matrix layout, UM2_STAGES-deep ring
-//   warp  8    one lane issues every tcgen05.mma; tcgen05.commit releases ring slots / publishes accumulators
+//   warps 4-15 producers  global A rows -> TF32 hi / lo -> shared memory core-matrix layout; one group of 4 warps per slot of
+//                         the UM2_STAGES-deep ring, so UM2_STAGES chunks (48 KB of loads per SM) are in flight at once —
+//                         the kernel is an HBM stream and bytes in flight are what buys bandwidth (Little's law)
+//   warp  16   one lane issues every tcgen05.mma; tcgen05.commit releases ring slots / publishes accumulators
 // W (hi / lo, all of K) is staged ONCE per CTA.  Two accumulators in TMEM (2 x N columns): the MMAs of tile t+1 run while
 // the epilogue drains tile t.  Four mbarrier families: full[s] (4 producer warps -> MMA), empty[s] (commit -> producers),
 // tfull[b] (commit -> epilogue), tempty[b] (4 epilogue warps -> MMA).
 // ---------------------------------------------------------------------------------------------
-#define UM2_THREADS 288
 #define UM2_STAGES 3
+#define UM2_PWARPS (4 * UM2_STAGES)            // producer warps: one group of 4 per ring slot
+#define UM2_MMA_WARP (4 + UM2_PWARPS)
+#define UM2_THREADS (32 * (UM2_MMA_WARP + 1))
 
 __device__ __forceinline__ void um_mbar_arrive(unsigned bar)
 {
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     const unsigned a_stage = 2 * 128 * UM_KC * 4;
     const unsigned b_full = um_smem_u32(&bars[0]), b_empty = um_smem_u32(&bars[UM2_STAGES]), b_tfull = um_smem_u32(&bars[2 * UM2_STAGES]),
                    b_tempty = um_smem_u32(&bars[2 * UM2_STAGES + 2]);
-    if (warp == 8) {
+    if (warp == UM2_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(&tmem_slot)), "r"((unsigned)ncols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -247,16 +251,21 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
                 *reinterpret_cast<float4 *>(dh + o) = h;
                 *reinterpret_cast<float4 *>(dl + o) = l;
             }
-        } else {
-            for (int e = tid; e < N * UM_KC; e += UM2_THREADS) {
-                const int row = e % N, kf = e / N;
-                float v = 0.f;
-                if (kf < kc) v = __ldg(W + (size_t)(k0 + kf) * ldw + n0 + row);
-                float h, l;
-                um_split(v, h, l);
-                const unsigned o = um_off(row, kf);
-                *reinterpret_cast<float *>(dh + o) = h;
-                *reinterpret_cast<float *>(dl + o) = l;
+        } else {                                            // W is (K x N): 4 consecutive output columns per thread
+            const int nq = N / 4;
+            for (int e = tid; e < nq * UM_KC; e += UM2_THREADS) {
+                const int row = (e % nq) * 4, kf = e / nq;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kf < kc) v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(k0 + kf) * ldw + n0 + row));
+                const float va[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float h, l;
+                    um_split(va[q], h, l);
+                    const unsigned o = um_off(row + q, kf);
+                    *reinterpret_cast<float *>(dh + o) = h;
+                    *reinterpret_cast<float *>(dl + o) = l;
+                }
             }
         }
     }
@@ -268,45 +277,46 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
     const unsigned lbo = 128, sbo = (UM_KC / 4) * 128;
 
-    if (warp >= 4 && warp < 8) {
-        // ===== producers =====
-        const int pw = warp - 4;
-        unsigned it_count = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long long row0 = (long long)tile * 128;
-            for (int j = 0; j < nchunk; j++, it_count++) {
-                const int stage = it_count % UM2_STAGES;
-                const unsigned use = it_count / UM2_STAGES;
-                um_mbar_wait(b_empty + 8 * stage, (use & 1u) ^ 1u);          // slot free (passes on first use)
-                const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
-                unsigned char *dh = pa + (size_t)stage * a_stage, *dl = dh + 128 * UM_KC * 4;
-                // 32 warp-instructions per chunk (16 row groups x 2 chunk quads), 8 per producer warp: loads first, stores after
-                float4 v[8];
+    if (warp >= 4 && warp < UM2_MMA_WARP) {
+        // ===== producers: group `stage` (4 warps) fills ring slot `stage`, i.e. the chunks c = stage, stage + STAGES, ... of
+        //       this CTA's chunk sequence (tile-major) =====
+        const int stage = (warp - 4) / 4, pw = (warp - 4) % 4;
+        int my_tiles = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
+        const long long total_chunks = (long long)my_tiles * nchunk;
+        unsigned char *dh = pa + (size_t)stage * a_stage, *dl = dh + 128 * UM_KC * 4;
+        unsigned use = 0;
+        for (long long c = stage; c < total_chunks; c += UM2_STAGES, use++) {
+            const int tseq = (int)(c / nchunk), j = (int)(c % nchunk);
+            const long long row0 = ((long long)blockIdx.x + (long long)tseq * gridDim.x) * 128;
+            const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
+            // the loads do not depend on the slot: issue them before waiting for it
+            float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int it = pw + 4 * u;
-                    const int g = it % 16, cq = it / 16;
-                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (kf < kc && row0 + row < n) v[u] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(row0 + row) * lda + k0 + kf));
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int it = pw + 4 * u;
-                    const int g = it % 16, cq = it / 16;
-                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
-                    float4 h, l;
-                    um_split(v[u].x, h.x, l.x); um_split(v[u].y, h.y, l.y); um_split(v[u].z, h.z, l.z); um_split(v[u].w, h.w, l.w);
-                    const unsigned o = um_off(row, kf);
-                    *reinterpret_cast<float4 *>(dh + o) = h;
-                    *reinterpret_cast<float4 *>(dl + o) = l;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) um_mbar_arrive(b_full + 8 * stage);
+            for (int u = 0; u < 8; u++) {
+                const int it = pw + 4 * u;
+                const int g = it % 16, cq = it / 16;
+                const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kf < kc && row0 + row < n) v[u] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(row0 + row) * lda + k0 + kf));
             }
+            um_mbar_wait(b_empty + 8 * stage, (use & 1u) ^ 1u);              // slot free (passes on first use)
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int it = pw + 4 * u;
+                const int g = it % 16, cq = it / 16;
+                const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                float4 h, l;
+                um_split(v[u].x, h.x, l.x); um_split(v[u].y, h.y, l.y); um_split(v[u].z, h.z, l.z); um_split(v[u].w, h.w, l.w);
+                const unsigned o = um_off(row, kf);
+                *reinterpret_cast<float4 *>(dh + o) = h;
+                *reinterpret_cast<float4 *>(dl + o) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) um_mbar_arrive(b_full + 8 * stage);
         }
-    } else if (warp == 8) {
+    } else if (warp == UM2_MMA_WARP) {
         // ===== MMA issuer =====
         if (lane == 0) {
             unsigned it_count = 0, tcount = 0;
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
+    if (warp == UM2_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
 }
 
 static int g_umma_v = 2;    // kernel version used by cb_umma_linear: 2 = persistent pipelined (default), 1 = simple one-tile CTAs
@@ -393,8 +403,13 @@ int cb_umma_enabled() { return g_umma; }
 
 bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int lda, int ldy)
 {
+    // the whole of W (TF32 hi + lo) stays resident in shared memory next to the A ring: N * K <= ~33 K floats per column block;
+    // larger layers (c >= 256: levels 3-4, a few hundred rows) keep the mma.sync / cuBLAS path
+    const int nchunk = (K + UM_KC - 1) / UM_KC;
+    const size_t w_bytes = (size_t)2 * nchunk * (N < 256 ? N : 256) * UM_KC * 4;
+    const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4;
     return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && lda % 4 == 0 && ldy % 4 == 0 &&
-           (((uintptr_t)A | (uintptr_t)Y) & 15) == 0;
+           (((uintptr_t)A | (uintptr_t)Y) & 15) == 0 && w_bytes + a_ring + 2048 <= (size_t)227 * 1024;
 }
 
 // Y (n x N) = A (n x K) . B^T (+ bias); trans_b = 0: W is (N x K) (forward), 1: W is (K x N) (dgrad).  N is processed in
