@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(UM_THREADS) k_umma_linear(int n, int K, int N,
 #define UM2_PWARPS (4 * UM2_STAGES)            // producer warps: one group of 4 per ring slot
 #define UM2_MMA_WARP (4 + UM2_PWARPS)
 #define UM2_THREADS (32 * (UM2_MMA_WARP + 1))
+#define UM2_EPI_PITCH 36                      // floats per staged epilogue row (32 + 4: conflict-free float4 rows)
+#define UM2_EPI_BYTES (4 * 32 * UM2_EPI_PITCH * 4)
 
 __device__ __forceinline__ void um_mbar_arrive(unsigned bar)
 {
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     // layout: [W hi chunks][W lo chunks][stage 0: A hi, A lo][stage 1 ...]
     unsigned char *pw_hi = um_smem, *pw_lo = pw_hi + (size_t)nchunk * w_bytes;
     unsigned char *pa = pw_lo + (size_t)nchunk * w_bytes;
+    unsigned char *pstage = pa + (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4;        // epilogue transposition buffers (4 warps)
     const unsigned sw_hi = um_smem_u32(pw_hi), sw_lo = um_smem_u32(pw_lo), sa = um_smem_u32(pa);
     const unsigned a_stage = 2 * 128 * UM_KC * 4;
     const unsigned b_full = um_smem_u32(&bars[0]), b_empty = um_smem_u32(&bars[UM2_STAGES]), b_tfull = um_smem_u32(&bars[2 * UM2_STAGES]),
@@ -353,28 +356,43 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
             const unsigned buf = tcount & 1u, tuse = tcount >> 1;
             um_mbar_wait(b_tfull + 8 * buf, tuse & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long row = (long long)tile * 128 + warp * 32 + lane;
-            for (int col = 0; col < N; col += 16) {
-                unsigned r[16];
-                const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + buf * (unsigned)N + (unsigned)col;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                             : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < n) {
-                    float4 *dst = reinterpret_cast<float4 *>(Y + (size_t)row * ldy + n0 + col);
+            // 32-column panels: TMEM -> registers (lane = row) -> shared (row-major, 144-byte row pitch: conflict free) ->
+            // registers (8 lanes = one 128-byte row segment) -> global: every store instruction writes 4 full 128-byte lines
+            // instead of 32 scattered 16-byte pieces
+            float *stg = reinterpret_cast<float *>(pstage) + warp * (32 * UM2_EPI_PITCH);
+            const long long trow0 = (long long)tile * 128 + warp * 32;
+            for (int col = 0; col < N; col += 32) {
+                const int pw_cols = min(32, N - col);                 // 32 or 16
+                for (int half = 0; half < pw_cols; half += 16) {
+                    unsigned r[16];
+                    const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + buf * (unsigned)N + (unsigned)(col + half);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                                 : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float4 *d4 = reinterpret_cast<float4 *>(stg + lane * UM2_EPI_PITCH + half);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        float4 o = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                               __uint_as_float(r[4 * q + 3]));
-                        if (bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col) + q);
+                    for (int q = 0; q < 4; q++)
+                        d4[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                            __uint_as_float(r[4 * q + 3]));
+                }
+                __syncwarp();
+                const int q = lane & 7;                               // float4 within the 128-byte row segment
+                if (4 * q < pw_cols) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col) + q);
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int rr = it * 4 + (lane >> 3);
+                        if (trow0 + rr < n) {
+                            float4 o = *reinterpret_cast<const float4 *>(stg + rr * UM2_EPI_PITCH + 4 * q);
                             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            *reinterpret_cast<float4 *>(Y + (size_t)(trow0 + rr) * ldy + n0 + col + 4 * q) = o;
                         }
-                        dst[q] = o;
                     }
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -407,7 +425,7 @@ bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int l
     // larger layers (c >= 256: levels 3-4, a few hundred rows) keep the mma.sync / cuBLAS path
     const int nchunk = (K + UM_KC - 1) / UM_KC;
     const size_t w_bytes = (size_t)2 * nchunk * (N < 256 ? N : 256) * UM_KC * 4;
-    const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4;
+    const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES;
     return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && lda % 4 == 0 && ldy % 4 == 0 &&
            (((uintptr_t)A | (uintptr_t)Y) & 15) == 0 && w_bytes + a_ring + 2048 <= (size_t)227 * 1024;
 }
@@ -428,7 +446,7 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
     if (g_umma_v == 2) {
         // column blocks such that W (hi + lo, all of K) + the A ring fit the 227 KB of one CTA; N of a block % 16 == 0, <= 256
         const int nchunk = (K + UM_KC - 1) / UM_KC;
-        const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4;
+        const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES;
         int nb_max = (int)(((size_t)227 * 1024 - 2048 - a_ring) / ((size_t)2 * nchunk * UM_KC * 4));
         nb_max = nb_max / 16 * 16;
         if (nb_max > 256) nb_max = 256;
