@@ -426,7 +426,9 @@ bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int l
     const int nchunk = (K + UM_KC - 1) / UM_KC;
     const size_t w_bytes = (size_t)2 * nchunk * (N < 256 ? N : 256) * UM_KC * 4;
     const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES;
-    return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && lda % 4 == 0 && ldy % 4 == 0 &&
+    // 32 -> 32 layers: 12 MMAs of N = 32 per 32 KB tile are issue-latency bound (26.7 us vs 20.4 us for the mma.sync kernel at
+    // n = 163840, tools/bench_linear.py); from 64 columns or 64 reduction elements on, the tcgen05 kernel is 1.1-1.6x faster
+    return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && (K >= 64 || N >= 64) && lda % 4 == 0 && ldy % 4 == 0 &&
            (((uintptr_t)A | (uintptr_t)Y) & 15) == 0 && w_bytes + a_ring + 2048 <= (size_t)227 * 1024;
 }
 

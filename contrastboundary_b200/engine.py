@@ -126,7 +126,7 @@ class GraphTrainStep(TrainStep):
     """TrainStep whose step() replays captured CUDA graphs.  Same numerics (the captured work IS TrainStep's
     work); falls back to TrainStep's stream mode for batch signatures it could not capture."""
 
-    def __init__(self, cfg: CBLConfig = None, device="cuda", ddp=False, eager_warmup=2, max_signatures=2, net_priority=False, **kw):
+    def __init__(self, cfg: CBLConfig = None, device="cuda", ddp=False, eager_warmup=2, max_signatures=4, net_priority=False, **kw):
         # data parallel here = one all-reduce of the packed gradient after the graph; no DDP wrapper
         super().__init__(cfg, device, ddp=False, **kw)
         import torch.distributed as dist
@@ -136,7 +136,13 @@ class GraphTrainStep(TrainStep):
                 dist.broadcast(t.data, 0)
         self.eager_warmup = max(1, eager_warmup)
         self.max_signatures = max_signatures
-        self._sigs = {}            # signature -> [slot0, slot1] | None (capture failed)
+        # signature (tuple of scene sizes) -> [slot0, slot1] | None (capture failed); least-recently-used first.  A captured
+        # signature pins ~5 GB of activations for 4 x 40960 points, so the cache is small and evicts (the reference's loader
+        # crops every cloud larger than voxel_max to exactly voxel_max points, data_util.py:64-67: batches of equal-size scenes
+        # recur; anything else runs in stream mode)
+        import collections
+        self._sigs = collections.OrderedDict()
+        self._seen = {}
         self._eager_done = 0
         self._net_pool = None      # net[0] / net[1] replay back to back on one stream: they may share temporaries
         self.flat = None
@@ -289,8 +295,19 @@ class GraphTrainStep(TrainStep):
             if self._eager_done < self.eager_warmup or not update:
                 self._eager_done += 1
                 return self._eager_step(batch, update)
+            # a capture costs ~1 s: only signatures that come back are worth it (first sighting runs in stream mode)
+            self._seen[sig] = self._seen.get(sig, 0) + 1
+            if len(self._seen) > 4096:
+                self._seen.clear()
+            if self._seen[sig] < 2 and any(v is not None for v in self._sigs.values()):
+                return self._eager_step(batch, update)
             slots = None
-            if len(self._sigs) < self.max_signatures:
+            while sum(v is not None for v in self._sigs.values()) >= self.max_signatures:
+                old = next(k for k, v in self._sigs.items() if v is not None)       # evict the least recently used capture
+                torch.cuda.synchronize(self.device)                                 # its graphs may still be replaying
+                del self._sigs[old]
+                torch.cuda.empty_cache()
+            if True:
                 try:
                     slots = self._capture(batch, sig)
                 except Exception as e:                                  # keep training in stream mode
@@ -305,6 +322,7 @@ class GraphTrainStep(TrainStep):
             self._sigs[sig] = slots
         if slots is None or not update:
             return self._eager_step(batch, update)
+        self._sigs.move_to_end(sig)
         self._set_packed(True)                                          # the optimiser reads the packed gradient
         cur = next((s for s in slots if s.holds is batch), None)
         if cur is None:

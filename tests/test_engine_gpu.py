@@ -57,7 +57,11 @@ def test_graph_step_other_signature_falls_back_or_captures():
     for s in range(4):
         l = gts.step(a[s % 2])
         assert torch.isfinite(l).all()
-    l = gts.step(c[0])            # second signature: over the cap -> stream mode, still trains
+    l = gts.step(c[0])            # a new signature: first sighting runs in stream mode (a capture costs ~1 s)
+    assert torch.isfinite(l).all() and tuple(c[0]["offset_host"]) not in gts._sigs
+    l = gts.step(c[0])            # it came back: with max_signatures=1 the first capture is evicted (LRU) and this one captured
     assert torch.isfinite(l).all()
-    l = gts.step(a[0])            # back to the captured signature
+    assert tuple(c[0]["offset_host"]) in gts._sigs and tuple(a[0]["offset_host"]) not in gts._sigs
+    l = gts.step(a[0])            # back to the first signature: captured again
     assert torch.isfinite(l).all() and gts.graph_error is None
+    assert len([v for v in gts._sigs.values() if v is not None]) == 1
