@@ -33,6 +33,10 @@ def lib():
         for name in ("cb_cbl_workspace_bytes",):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t
+        if os.environ.get("CB_UMMA"):            # developer knob: CB_UMMA=0 -> mma.sync kernels instead of tcgen05 for the linear layers
+            _lib.cb_linear_set_umma(C.c_int(int(os.environ["CB_UMMA"])))
+        if os.environ.get("CB_GRID_FUSED"):      # developer knob: 0 -> the multi-kernel grid build
+            _lib.cb_grid_set_fused(C.c_int(int(os.environ["CB_GRID_FUSED"])))
         if os.environ.get("CB_FPS_MODE"):        # developer knob (profilers that cannot launch cluster kernels): see cbops.h
             _lib.cb_fps_set_mode(C.c_int(int(os.environ["CB_FPS_MODE"])), C.c_int(8192))
     return _lib

@@ -445,6 +445,16 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
+    static bool attr_set = false;
+    if (!attr_set) {
+        // ONE opt-in to the full 227 KB for every instance: the dynamic size differs from layer to layer, and a CUDA graph
+        // replays a node with ITS size against whatever the attribute is at replay time
+        cudaFuncSetAttribute(k_umma_linear2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_umma_linear2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_umma_linear<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
     if (g_umma_v == 2) {
         // column blocks such that W (hi + lo, all of K) + the A ring fit the 227 KB of one CTA; N of a block % 16 == 0, <= 256
         const int nchunk = (K + UM_KC - 1) / UM_KC;
@@ -463,10 +473,8 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
                 const size_t smem = (size_t)2 * nchunk * nb * UM_KC * 4 + a_ring;
                 const int blocks = ntiles < sms ? ntiles : sms;
                 if (trans_b) {
-                    cudaFuncSetAttribute(k_umma_linear2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     k_umma_linear2<1><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
                 } else {
-                    cudaFuncSetAttribute(k_umma_linear2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     k_umma_linear2<0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
                 }
                 CB_COUNT(1);
@@ -481,10 +489,8 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
         const size_t smem = (size_t)(2 * 128 + 2 * nb) * UM_KC * 4;
         const int blocks = (n + 127) / 128;
         if (trans_b) {
-            cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_umma_linear<1><<<blocks, UM_THREADS, smem, st>>>(n, K, nb, ncols, A, lda, W, bias, Y, ldy, c0, ldw);
         } else {
-            cudaFuncSetAttribute(k_umma_linear<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_umma_linear<0><<<blocks, UM_THREADS, smem, st>>>(n, K, nb, ncols, A, lda, W, bias, Y, ldy, c0, ldw);
         }
         CB_COUNT(1);

@@ -42,6 +42,7 @@ def test_graph_step_matches_stream_step():
             # by BatchNorm over the 28 points of the deepest level); the replayed gradient must sit at that floor
             floor = float((g_ref2 - g_ref).norm() / g_ref.norm().clamp(min=1e-20))
             rel = float((snap["g"] - g_ref).norm() / g_ref.norm().clamp(min=1e-20))
+            print(f"step {s}: graph-vs-stream gradient {rel:.3e}, stream-vs-stream floor {floor:.3e}")
             assert rel < max(3e-3, 8.0 * floor), (s, rel, floor)     # a wrong gradient is off by O(1)
     assert gts.graph_error is None, gts.graph_error
     assert gts.launches_per_step and gts.launches_per_step > 100
