@@ -288,7 +288,7 @@ def roofline_knn_gather(torch, dev):
     return {"bound": "hbm", "kernel": "k_knn_gather (fused grid-KNN + TMA neighbour-row gather), N=40960 K=16 C=256, grid prebuilt",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "alg_bytes": alg, "us_per_launch": t_kernel * 1e6,
-            "whole_operator": {"what": "cb_knn_gather incl. grid build (11 small kernels)", "us": t_call * 1e6,
+            "whole_operator": {"what": "cb_knn_gather incl. the grid build (one cooperative kernel) and the tie-replay / re-gather followers", "us": t_call * 1e6,
                                "achieved": alg / t_call / 1e9, "frac": alg / t_call / 1e9 / peak},
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)" if peaks else "fallback 6650 (B200_PROFILING.md)",
             "l2": "between timed iterations a 256 MiB buffer is zeroed and another 256 MiB buffer is read (L2 left full of clean foreign lines)"}

@@ -473,7 +473,9 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
     typename CbTopKSel<KPL>::type tk;
     tk.init(K, lane, sc.start);
     bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane, dist_mode);
-    if (ok && dist_mode == 0 && tk.has_tie()) ok = false;
+    // sqrt_dist bit 1 = "set semantics": the caller only uses the SET of neighbours (label histograms), so ties INSIDE the set
+    // need no replay of the reference heap; only a tie across the K-th boundary does
+    if (ok && dist_mode == 0 && ((sqrt_dist & 2) ? tk.has_boundary_tie() : tk.has_tie())) ok = false;
     if (!ok) {
         if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
         return;
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
         if (e < K) {
             if (dist_mode == 0) {
                 idx[(size_t)q * K + e] = tk.out_i(j);
-                dist2[(size_t)q * K + e] = sqrt_dist ? __fsqrt_rn(tk.out_d(j)) : tk.out_d(j);
+                dist2[(size_t)q * K + e] = (sqrt_dist & 1) ? __fsqrt_rn(tk.out_d(j)) : tk.out_d(j);
             } else {
                 idx[(size_t)q * K + e] = tk.out_d(j) < r2 ? tk.out_i(j) : pad_idx;
             }
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
         for (int k = t; k < K; k += CB_REPLAY_THREADS) {
             if (dist_mode == 0) {
                 idx[(size_t)q * K + k] = hi[k];
-                dist2[(size_t)q * K + k] = sqrt_dist ? __fsqrt_rn(hd[k]) : hd[k];
+                dist2[(size_t)q * K + k] = (sqrt_dist & 1) ? __fsqrt_rn(hd[k]) : hd[k];
             } else {
                 idx[(size_t)q * K + k] = hd[k] < r2 ? hi[k] : pad_idx;
             }

@@ -131,6 +131,8 @@ struct CbTopK {
     __device__ __forceinline__ float out_d(int j) const { return d[j]; }
     __device__ __forceinline__ int out_i(int j) const { return i[j]; }
 
+    // true if the SET of the K nearest is ambiguous: a candidate outside the list ties with the K-th entry
+    __device__ __forceinline__ bool has_boundary_tie() const { return (tie_val == kth) && (kth < 1e10f); }
     // true if the reference's result for this query may depend on its heap mechanics
     __device__ __forceinline__ bool has_tie() const
     {
@@ -318,6 +320,13 @@ struct CbTopKB {
             }
         }
         refresh_thresholds();
+    }
+    // the SET of the K nearest is ambiguous: full list -> a dropped / evicted value equal to the last entry;
+    // list with a spare entry -> entries K-1 and K (the best candidate outside the set) tie
+    __device__ __forceinline__ bool has_boundary_tie() const
+    {
+        if (K == 32 * KPL) return (tie_val == thr) && (thr < 1e10f);
+        return (kth == thr) && (kth < 1e10f);
     }
     __device__ __forceinline__ bool has_tie() const
     {

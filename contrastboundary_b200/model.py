@@ -230,7 +230,7 @@ def _searches(levels, cfg, with_contrast, ready, knn_stream):
             if l > 0:
                 kr *= cfg.nstride[l - 1]
                 # sub-scene labels: kr nearest full-resolution points (basic_operators.py:20-30)
-                lv.label_idx, _ = knn(grids[0], kr, levels[0].p, lv.p, levels[0].o, lv.o)
+                lv.label_idx, _ = knn(grids[0], kr, levels[0].p, lv.p, levels[0].o, lv.o, set_only=True)
             lv.cbl_idx, _ = knn(grids[l], cfg.nsample[l], lv.p, lv.p, lv.o, lv.o)        # heads.py:192
 
 

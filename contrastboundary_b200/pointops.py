@@ -117,15 +117,18 @@ def grid_for(xyz, offset, nsample_hint, m_max):
     return ws
 
 
-def knn_on_grid(grid, nsample, xyz, new_xyz, offset, new_offset, sqrt_dist=True):
-    """same result as knn_raw, on a grid prebuilt by grid_for (one build, many query sets / K)"""
+def knn_on_grid(grid, nsample, xyz, new_xyz, offset, new_offset, sqrt_dist=True, set_only=False):
+    """same result as knn_raw, on a grid prebuilt by grid_for (one build, many query sets / K).
+    set_only=True: the caller uses the neighbours as a SET (e.g. the label histogram of get_subscene_label,
+    basic_operators.py:20-30): equal distances inside the set may come out in any order, which spares the exact heap replay
+    for them (K = 64 / 256 replays cost ~1.4 ms per step); the set itself is still the reference's."""
     n, m, b = xyz.shape[0], new_xyz.shape[0], offset.shape[0]
     dev = xyz.device
     idx = torch.empty((m, nsample), dtype=torch.int32, device=dev)
     dist = torch.empty((m, nsample), dtype=torch.float32, device=dev)
     rc = L.lib().cb_knn_query_grid(C.c_int(m), C.c_int(int(nsample)), L.ptr(xyz), C.c_int(n), L.ptr(new_xyz), L.ptr(offset),
-                                   L.ptr(new_offset), C.c_int(b), L.ptr(idx), L.ptr(dist), C.c_int(1 if sqrt_dist else 0),
-                                   L.ptr(grid), C.c_size_t(grid.numel()), L.stream())
+                                   L.ptr(new_offset), C.c_int(b), L.ptr(idx), L.ptr(dist),
+                                   C.c_int((1 if sqrt_dist else 0) | (2 if set_only else 0)), L.ptr(grid), C.c_size_t(grid.numel()), L.stream())
     L.check(rc, "cb_knn_query_grid")
     return idx, dist
 

@@ -51,7 +51,8 @@ unsigned long long cb_launch_count(void); /* kernels launched by this library so
  * through an exact replay of that heap.
  *   n, b            number of support points / scenes (the reference launcher infers them)
  *   new_xyz         may equal xyz (self query)
- *   sqrt_dist       non-zero: write sqrtf(dist2) instead (what pointops.py:43 returns)
+ *   sqrt_dist       bit 0: write sqrtf(dist2) instead (what pointops.py:43 returns); bit 1 ("set semantics"): the caller
+ *                   uses the result as a SET — ties inside it may come out in any order (no heap replay for them)
  *   workspace       >= cb_knn_workspace_bytes(n, m, b) bytes, 256-byte aligned
  * ---------------------------------------------------------------------------------------------- */
 size_t cb_knn_workspace_bytes(int n, int m, int b);
