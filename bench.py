@@ -294,6 +294,39 @@ def roofline_knn_gather(torch, dev):
             "l2": "between timed iterations a 256 MiB buffer is zeroed and another 256 MiB buffer is read (L2 left full of clean foreign lines)"}
 
 
+def roofline_linear(torch, dev):
+    """a kernel that IS in the timed step: the fused q/k/v projection of the level-1 PointTransformer blocks
+    (40960 x 64 -> 192) and the level-0 one (163840 x 32 -> 96) through cb_linear_forward = k_umma_linear2
+    (tcgen05.mma kind::tf32, TMEM accumulators).  Algorithmic bytes 4 n (ci + co)."""
+    from contrastboundary_b200 import _lib as L
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    out = []
+    for n, ci, co in ((40960, 64, 192), (163840, 32, 96)):
+        x, w, b = torch.randn(n, ci, device=dev), torch.randn(co, ci, device=dev), torch.randn(co, device=dev)
+        y = torch.empty(n, co, device=dev)
+        for _ in range(3):
+            L.call("cb_linear_forward", n, ci, co, x, w, b, y, L.stream())
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            L.call("cb_linear_forward", n, ci, co, x, w, b, y, L.stream())
+            e.record(st)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e) * 1e-3)
+        t = float(np.mean(ts))
+        alg = 4 * n * (ci + co)
+        out.append({"kernel": f"k_umma_linear2 (tcgen05 kind::tf32 3xTF32, TMEM), n={n} ci={ci} co={co}", "bound": "hbm", "alg_bytes": alg,
+                    "us_per_launch": t * 1e6, "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak})
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -451,6 +484,7 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_roofline:
         line["roofline"] = roofline_knn_gather(torch, dev)
+        line["roofline_step_kernels"] = roofline_linear(torch, dev)
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         # B1: the reference's stock pointops CUDA build on this same GPU, after the timed regions, in a child process
         del ts

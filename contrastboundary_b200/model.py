@@ -273,7 +273,9 @@ class PointTransformerLayer(nn.Module):
 
     def forward(self, lv, x):
         p, idx = lv.p, lv.knn
-        if self.fused:
+        # the fused kernels cover the widths / neighbourhood sizes of the shipped networks; anything else takes the
+        # op-by-op path below on the stand-alone operators (same results, more kernels)
+        if self.fused and self.out_planes in (32, 64, 128, 256, 512) and idx.shape[1] <= 32 and lv.rel is not None:
             # one (c -> 3c) projection instead of three (the parameters stay linear_q / linear_k / linear_v)
             from . import ptlayer
             from .linear_ops import fast_linear
