@@ -449,10 +449,12 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
     if (!attr_set) {
         // ONE opt-in to the full 227 KB for every instance: the dynamic size differs from layer to layer, and a CUDA graph
         // replays a node with ITS size against whatever the attribute is at replay time
-        cudaFuncSetAttribute(k_umma_linear2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_umma_linear2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_umma_linear<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const int dyn_max = 227 * 1024 - 2048;        // 227 KB per CTA minus the kernels' static shared memory (1 KB) and slack
+        cudaFuncSetAttribute(k_umma_linear2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        (void)cudaGetLastError();
         attr_set = true;
     }
     if (g_umma_v == 2) {
