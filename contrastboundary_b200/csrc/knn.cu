@@ -499,14 +499,68 @@ __global__ void __launch_bounds__(128) k_knn_query(int m, int K, const float *__
 // block evaluates distances in index order, thread 0 runs the reference's heap
 // (knnquery_cuda_kernel.cu:21-48,91-110) in shared memory.
 // ---------------------------------------------------------------------------------------------
+// The reference's reheap (knnquery_cuda_kernel.cu:21-36) with the value on its way down kept in registers: place (vd, vi)
+// at the root of the max-heap and sift it down; returns the new root distance.  Same comparisons in the same order as the
+// reference's swap loop (dist[root] there IS the moving value), so the same arrangement results.  The heap is stored as
+// packed (distance, index) pairs, node j at hp[j + 1]: the two children of a node are one aligned 16-byte shared-memory
+// load, and while the larger child is being chosen the child pairs of BOTH children are already on their way (the
+// storage holds 2 * K + 8 entries so that these speculative loads stay inside it) — the shared-memory latency of a level
+// overlaps with the compare-and-branch of the level above.  This loop is the serial critical path of a replay.
+// (explicit shared-space accesses on a 32-bit address: the generic-pointer form re-derives the shared window from
+// SR_CgaCtaId inside the loop)
+__device__ __forceinline__ int4 cb_lds128(unsigned a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 cb_lds64(unsigned a)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cb_sts64(unsigned a, int x, int y)
+{
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ float cb_replay_sift(unsigned hp_s, int len, float vd, int vi)
+{
+    int r = 0, child = 1;
+    float new_root = vd;
+    int4 c = cb_lds128(hp_s + 16);                                          // nodes 1, 2
+    while (child < len) {
+        const int4 na = cb_lds128(hp_s + 16 * child + 16);                  // children of node child
+        const int4 nb = cb_lds128(hp_s + 16 * child + 32);                  // children of node child + 1
+        const bool right = child + 1 < len && __int_as_float(c.z) > __int_as_float(c.x);
+        const float cdv = __int_as_float(right ? c.z : c.x);
+        const int cvi = right ? c.w : c.y;
+        if (vd > cdv) break;
+        cb_sts64(hp_s + 8 * r + 8, __float_as_int(cdv), cvi);
+        if (r == 0) new_root = cdv;
+        r = child + (right ? 1 : 0);
+        child = r * 2 + 1;
+        c.x = right ? nb.x : na.x; c.y = right ? nb.y : na.y; c.z = right ? nb.z : na.z; c.w = right ? nb.w : na.w;
+    }
+    cb_sts64(hp_s + 8 * r + 8, __float_as_int(vd), vi);
+    return new_root;
+}
+
 #define CB_REPLAY_THREADS 1024
-#define CB_REPLAY_PER_THREAD 4
-#define CB_REPLAY_BATCH (CB_REPLAY_THREADS * CB_REPLAY_PER_THREAD)
+#define CB_REPLAY_BATCH 4096                  /* capacity of the survivor list of one batch */
+#define CB_REPLAY_ROWS 8                      /* rows of 32 candidates a warp keeps in flight */
+static size_t cb_replay_smem(int K);
 // The heap replay itself is serial (the reference's result under ties is defined by its heap
 // history), but only candidates with d2 < root are ever inserted and the root never grows.  So the
-// block filters a batch of 4096 candidates in parallel against the root at the start of the batch
+// block filters a batch of candidates in parallel against the root at the start of the batch
 // (an upper bound for every later root), compacts the survivors IN INDEX ORDER, and thread 0
-// replays just those — a handful per batch once the heap has warmed up.
+// replays just those.  Batches DOUBLE (256, 512, ... ): a batch of s candidates after p scanned ones
+// leaves about s * K / p survivors, so s = p keeps the serial pass at ~K entries per batch while the
+// number of block-wide synchronisation rounds is log2(n / 256) instead of n / 4096.  Warp w owns a contiguous
+// segment of the batch and walks it in coalesced rows of 32, CB_REPLAY_ROWS rows of loads in flight:
+// (warp, row, lane) order is index order.  Pass 1 counts survivors, pass 2 (same arithmetic, L1/L2 hits) stores them
+// behind the scanned offsets; if a batch leaves more than CB_REPLAY_BATCH survivors (an adversarial point order), it
+// is retried at a quarter of the size, down to CB_REPLAY_BATCH candidates — which always fit.
 __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const float *__restrict__ xyz,
                                                                  const float *__restrict__ new_xyz,
                                                                  const int *__restrict__ offset,
@@ -516,54 +570,50 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
                                                                  const int *__restrict__ flagged, int dist_mode, float r2,
                                                                  int pad_idx)
 {
-    extern __shared__ unsigned char smem_raw[];
-    float *hd = (float *)smem_raw;                     // K
-    int *hi = (int *)(hd + K);                         // K
-    float *cd = (float *)(hi + K);                     // CB_REPLAY_BATCH survivors (distance)
-    int *ci = (int *)(cd + CB_REPLAY_BATCH);           // CB_REPLAY_BATCH survivors (index)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2 *hp = (int2 *)smem_raw;                                           // 2K + 8 packed heap entries, node j at hp[j + 1]
+    int2 *cand = hp + 2 * K + 8;                                           // CB_REPLAY_BATCH survivors (distance, index)
     __shared__ int warp_cnt[CB_REPLAY_THREADS / 32];
-    __shared__ int s_total;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int count = hdr->flagged_count;
     for (int f = blockIdx.x; f < count; f += gridDim.x) {
         const int q = flagged[f];
         const int s = cb_scene_of(q, new_offset, b);
         const int start = s == 0 ? 0 : offset[s - 1], end = offset[s];
         const float qx = new_xyz[3 * q], qy = new_xyz[3 * q + 1], qz = new_xyz[3 * q + 2];
-        for (int k = t; k < K; k += CB_REPLAY_THREADS) { hd[k] = 1e10f; hi[k] = start; }
+        for (int k = t; k < 2 * K + 8; k += CB_REPLAY_THREADS) hp[k] = make_int2(__float_as_int(1e10f), start);
         __syncthreads();
-        // Graded batches (256, 512, ... 4096 candidates): a batch is pre-filtered against the heap root at its start,
-        // which is 1e10 for the first one — keeping that one small keeps the serial pass of thread 0 short
-        // (expected survivors of a batch of s candidates after p scanned ones: s * K / p).
-        int bs = 256;                       // batch size: 256, 512, ... CB_REPLAY_BATCH
+        int bs = 256;
         for (int base = start; base < end;) {
-            const float root = hd[0];
-            const int pt = bs >= CB_REPLAY_THREADS ? bs / CB_REPLAY_THREADS : 1;
-            const int i0 = base + t * pt;
-            const int lim = min(end, base + bs);
-            float d[CB_REPLAY_PER_THREAD];
-            int npass = 0;
+            const float root = __int_as_float(hp[1].x);
+            const int cur = min(bs, end - base);
+            const int rows_total = (cur + 31) >> 5;
+            const int rows_per_warp = (rows_total + CB_REPLAY_THREADS / 32 - 1) / (CB_REPLAY_THREADS / 32);
+            const int r0 = w * rows_per_warp, r1 = min(rows_total, r0 + rows_per_warp);
+            const int lim = base + cur;
+            int cnt = 0;                                                    // pass 1: survivors of this warp's segment
+            for (int r = r0; r < r1; r += CB_REPLAY_ROWS) {
+                float px[CB_REPLAY_ROWS], py[CB_REPLAY_ROWS], pz[CB_REPLAY_ROWS];
 #pragma unroll
-            for (int u = 0; u < CB_REPLAY_PER_THREAD; u++) {
-                const int i = i0 + u;
-                d[u] = 3.0e38f;
-                if (u < pt && i < lim)
-                    d[u] = cb_sqdist_mode(dist_mode, qx, qy, qz, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
-                npass += d[u] < root;
-            }
-            base += bs;
-            if (bs < CB_REPLAY_BATCH) bs <<= 1;
-            // block exclusive scan of npass (thread order == index order)
-            int inc = npass;
+                for (int u = 0; u < CB_REPLAY_ROWS; u++) {
+                    const int i = base + ((r + u) << 5) + lane;
+                    const bool in = r + u < r1 && i < lim;
+                    px[u] = in ? __ldg(xyz + 3 * i) : 0.f;
+                    py[u] = in ? __ldg(xyz + 3 * i + 1) : 0.f;
+                    pz[u] = in ? __ldg(xyz + 3 * i + 2) : 0.f;
+                }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(CB_FULL_MASK, inc, o);
-                if (lane >= o) inc += v;
+                for (int u = 0; u < CB_REPLAY_ROWS; u++) {
+                    const int i = base + ((r + u) << 5) + lane;
+                    const bool in = r + u < r1 && i < lim;
+                    const float d = in ? cb_sqdist_mode(dist_mode, qx, qy, qz, px[u], py[u], pz[u]) : 3.0e38f;
+                    cnt += __popc(__ballot_sync(CB_FULL_MASK, d < root));
+                }
             }
-            if (lane == 31) warp_cnt[w] = inc;
+            if (lane == 0) warp_cnt[w] = cnt;
             __syncthreads();
-            // exclusive offset of this warp = sum of the counts of the warps before it (second-level warp scan)
-            int woff;
+            int woff, total;                                                // exclusive scan over the warps' counts
             {
                 const int wc = lane < CB_REPLAY_THREADS / 32 ? warp_cnt[lane] : 0;
                 int winc = wc;
@@ -573,57 +623,82 @@ __global__ void __launch_bounds__(CB_REPLAY_THREADS) k_knn_replay(int K, const f
                     if (lane >= o) winc += v;
                 }
                 woff = __shfl_sync(CB_FULL_MASK, winc - wc, w);
+                total = __shfl_sync(CB_FULL_MASK, winc, 31);
             }
-            if (t == CB_REPLAY_THREADS - 1) s_total = woff + inc;
-            int pos = woff + inc - npass;
+            if (total > CB_REPLAY_BATCH) {                                  // does not fit: retry this batch smaller
+                bs = max(bs >> 2, CB_REPLAY_BATCH);
+                __syncthreads();
+                continue;
+            }
+            if (cnt > 0) {                                                  // pass 2: store in (warp, row, lane) = index order
+                int pos = woff;
+                for (int r = r0; r < r1; r += CB_REPLAY_ROWS) {
+                    float px[CB_REPLAY_ROWS], py[CB_REPLAY_ROWS], pz[CB_REPLAY_ROWS];
 #pragma unroll
-            for (int u = 0; u < CB_REPLAY_PER_THREAD; u++)
-                if (d[u] < root) { cd[pos] = d[u]; ci[pos] = i0 + u; pos++; }
-            __syncthreads();
-            if (t == 0) {
-                const int total = s_total;
-                for (int u = 0; u < total; u++) {
-                    const float d2 = cd[u];
-                    if (d2 < hd[0]) {
-                        hd[0] = d2; hi[0] = ci[u];
-                        int r = 0, child = 1;                              // reheap (knnquery_cuda_kernel.cu:21-36)
-                        while (child < K) {
-                            if (child + 1 < K && hd[child + 1] > hd[child]) child++;
-                            if (hd[r] > hd[child]) break;
-                            float td = hd[r]; hd[r] = hd[child]; hd[child] = td;
-                            int ti = hi[r]; hi[r] = hi[child]; hi[child] = ti;
-                            r = child; child = r * 2 + 1;
-                        }
+                    for (int u = 0; u < CB_REPLAY_ROWS; u++) {
+                        const int i = base + ((r + u) << 5) + lane;
+                        const bool in = r + u < r1 && i < lim;
+                        px[u] = in ? __ldg(xyz + 3 * i) : 0.f;
+                        py[u] = in ? __ldg(xyz + 3 * i + 1) : 0.f;
+                        pz[u] = in ? __ldg(xyz + 3 * i + 2) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < CB_REPLAY_ROWS; u++) {
+                        const int i = base + ((r + u) << 5) + lane;
+                        const bool in = r + u < r1 && i < lim;
+                        const float d = in ? cb_sqdist_mode(dist_mode, qx, qy, qz, px[u], py[u], pz[u]) : 3.0e38f;
+                        const unsigned bal = __ballot_sync(CB_FULL_MASK, d < root);
+                        if (d < root) cand[pos + __popc(bal & lt_mask)] = make_int2(__float_as_int(d), i);
+                        pos += __popc(bal);
                     }
                 }
             }
             __syncthreads();
+            if (t == 0 && total > 0) {
+                const unsigned hp_s = (unsigned)__cvta_generic_to_shared(hp), cand_s = (unsigned)__cvta_generic_to_shared(cand);
+                float rootv = __int_as_float(cb_lds64(hp_s + 8).x);
+                int2 e = cb_lds64(cand_s);
+                for (int u = 0; u < total; u++) {
+                    const int2 nxt = cb_lds64(cand_s + 8 * (u + 1 < total ? u + 1 : u));   // next survivor on its way during the sift
+                    if (__int_as_float(e.x) < rootv) rootv = cb_replay_sift(hp_s, K, __int_as_float(e.x), e.y);
+                    e = nxt;
+                }
+            }
+            __syncthreads();
+            base += cur;
+            if (bs < (1 << 28)) bs <<= 1;
         }
         if (t == 0) {                                                       // heap_sort (:39-48)
             for (int i = K - 1; i > 0; i--) {
-                float td = hd[0]; hd[0] = hd[i]; hd[i] = td;
-                int ti = hi[0]; hi[0] = hi[i]; hi[i] = ti;
-                int r = 0, child = 1;
-                while (child < i) {
-                    if (child + 1 < i && hd[child + 1] > hd[child]) child++;
-                    if (hd[r] > hd[child]) break;
-                    float t2 = hd[r]; hd[r] = hd[child]; hd[child] = t2;
-                    int t3 = hi[r]; hi[r] = hi[child]; hi[child] = t3;
-                    r = child; child = r * 2 + 1;
-                }
+                const unsigned hp_s = (unsigned)__cvta_generic_to_shared(hp);
+                const int2 v = cb_lds64(hp_s + 8 * i + 8), top = cb_lds64(hp_s + 8);
+                cb_sts64(hp_s + 8 * i + 8, top.x, top.y);
+                (void)cb_replay_sift(hp_s, i, __int_as_float(v.x), v.y);
             }
         }
         __syncthreads();
         for (int k = t; k < K; k += CB_REPLAY_THREADS) {
+            const int2 e = hp[k + 1];
+            const float dk = __int_as_float(e.x);
             if (dist_mode == 0) {
-                idx[(size_t)q * K + k] = hi[k];
-                dist2[(size_t)q * K + k] = (sqrt_dist & 1) ? __fsqrt_rn(hd[k]) : hd[k];
+                idx[(size_t)q * K + k] = e.y;
+                dist2[(size_t)q * K + k] = (sqrt_dist & 1) ? __fsqrt_rn(dk) : dk;
             } else {
-                idx[(size_t)q * K + k] = hd[k] < r2 ? hi[k] : pad_idx;
+                idx[(size_t)q * K + k] = dk < r2 ? e.y : pad_idx;
             }
         }
         __syncthreads();
     }
+}
+
+static size_t cb_replay_smem(int K)
+{
+    static bool opted_in = false;                  // rows wider than ~2040 entries need more than the default 48 KB
+    if (!opted_in) {
+        cudaFuncSetAttribute(k_knn_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        opted_in = true;
+    }
+    return (2 * (size_t)K + 8) * 8 + (size_t)CB_REPLAY_BATCH * 8;
 }
 
 // brute-force for every query (K > 256): flag all, then replay
@@ -735,7 +810,7 @@ void cb_knn_replay_launch(int K, int m, const float *xyz, const float *new_xyz, 
                           const int *new_offset, int b, int *idx, float *dist2, int sqrt_dist, const CbGridView &v,
                           cudaStream_t st)
 {
-    const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
+    const size_t smem = cb_replay_smem(K);
     const int rblocks = K <= 256 ? 148 : (m < 148 * 8 ? (m > 0 ? m : 1) : 148 * 8);
     k_knn_replay<<<rblocks, CB_REPLAY_THREADS, smem, st>>>(K, xyz, new_xyz, offset, new_offset, b, idx, dist2,
                                                            sqrt_dist, v.hdr, v.flagged, 0, 0.f, 0);
@@ -749,7 +824,7 @@ int cb_knn_query_radius_impl(int m, int K, const float *xyz, int n, const float 
     CB_REQUIRE(K <= 2048, CB_EUNSUPPORTED, "radius neighbours: row width %d > 2048 unsupported", K);
     const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
     const int blocks = (m + 3) / 4;
-    const size_t smem = (size_t)K * 8 + (size_t)CB_REPLAY_BATCH * 8;
+    const size_t smem = cb_replay_smem(K);
     if (K > 256) {
         // rows wider than the register top-K of k_knn_query (dense clouds during neighbourhood-limit calibration,
         // datasets/base.py:199-294): every query takes the exact scene scan

@@ -15,7 +15,8 @@
 #define KG_WARPS 8
 static int g_kg_chunk_bytes = 8192;
 static int g_kg_spin_ns = 0;          // back-off of a search warp that finds the hand-off queue full (0 = busy spin)
-static int g_kg_ws = 3;              // 0 one-warp TMA | 1,2,3 warp-specialised TMA rings (8/4, 12/8, 6/4) | 4 direct register copy    // bytes per TMA chunk (two chunks are in flight per warp)
+static int g_kg_mode = -1;           // -1 by row width (knn_gather_launch) | 0 one-warp TMA | 1,2,3 warp-specialised TMA rings (8/4, 12/8, 6/4)
+                                     // | 4 direct register copy | 5 loader + storer warps | 6,7 one / two load-store-unit copy warps
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -40,15 +41,41 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
             : "memory");
     } while (!ok);
 }
+// L2 residency hints (bit 0: chunk stores evict_first, bit 1: row loads evict_last).  The output stream (4*N*K*C bytes) is
+// written once and never read by this kernel; without a hint it pushes feature rows out of L2 before the queries of the
+// next grid slab need them again once the feature table no longer fits beside it (N*C*4 > ~60 MB).
+__constant__ int c_kg_l2_hint = 3;
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+    if (c_kg_l2_hint & 2)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                     "l"(src), "r"(bytes), "r"(bar), "l"(l2_policy_evict_last())
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    if (c_kg_l2_hint & 1)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes),
+                     "l"(l2_policy_evict_first())
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -310,6 +337,128 @@ __global__ void __launch_bounds__(256, 4) k_knn_gather_ws(int m, int K, int c, i
             }
         }
         if (lane == 0) bulk_wait_all();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSU-copy variant (modes 6 / 7).  The TMA variants above move every 1 KB feature row with its own bulk copy: 655 360 row
+// loads + 81 920 chunk stores per call = one bulk operation per ~65 cycles and SM — the rate at which the kernel saturates
+// whatever the ring depth (Little's law on the ring gives the same 4.7 TB/s).  Here the copy warps use the load/store
+// units instead: a queue item is one contiguous (K x c) destination block; the warp walks it as float4 vectors, KGL_U
+// independent ld.global.nc (L2 hits: the feature table is resident) in flight per lane, then KGL_U streaming stores
+// (st.global.cs: the 671 MB output must not evict the 42 MB table from L2).  No staging shared memory at all.
+// Queue: ticket t -> slot t % KGW_QN; the slot is free for generation t / KGW_QN once q_done[slot] says so; copy warp cw
+// takes the tickets t = cw (mod NCOPY).
+// ---------------------------------------------------------------------------------------------
+#define KGL_U 8
+
+template <int KPL, int NCOPY>
+__global__ void __launch_bounds__(256, 4) k_knn_gather_lsu(int m, int K, int c, const float *__restrict__ new_xyz,
+                                                           const float *__restrict__ feat, const int *__restrict__ new_offset, int b,
+                                                           int self_query, const CbScene *__restrict__ scenes,
+                                                           const int *__restrict__ cells, const float4 *__restrict__ sorted,
+                                                           int *__restrict__ idx, float *__restrict__ dist2,
+                                                           float *__restrict__ grouped, CbGridHeader *hdr, int *flagged)
+{
+    constexpr int NSEARCH = 8 - NCOPY;
+    __shared__ CbWarpScratch scratch[NSEARCH];
+    __shared__ int q_entry[KGW_QN][1 + 32 * KPL];
+    __shared__ volatile int q_seq[KGW_QN];
+    __shared__ volatile int q_done[KGW_QN];
+    __shared__ int q_tail;
+    __shared__ volatile int producers_done;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x < KGW_QN) { q_seq[threadIdx.x] = 0; q_done[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { q_tail = 0; producers_done = 0; }
+    __syncthreads();
+    if (wib < NSEARCH) {
+        // ------------------------------ search warps ------------------------------
+        const int stride = gridDim.x * NSEARCH;
+        for (int w = blockIdx.x * NSEARCH + wib; w < m; w += stride) {
+            int q = w;
+            float qx, qy, qz;
+            if (self_query) {
+                const float4 p = __ldg(sorted + w);
+                q = __float_as_int(p.w); qx = p.x; qy = p.y; qz = p.z;
+            } else {
+                qx = __ldg(new_xyz + 3 * q); qy = __ldg(new_xyz + 3 * q + 1); qz = __ldg(new_xyz + 3 * q + 2);
+            }
+            const int s = cb_scene_of(q, new_offset, b);
+            const CbScene sc = scenes[s];
+            typename CbTopKSel<KPL>::type tk;
+            tk.init(K, lane, sc.start);
+            bool ok = cb_grid_search(tk, sc, qx, qy, qz, cells, sorted, &scratch[wib], lane);
+            if (ok && tk.has_tie()) ok = false;
+            if (!ok) {
+                if (lane == 0) flagged[atomicAdd(&hdr->flagged_count, 1)] = q;
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const int e = j * 32 + lane;
+                if (e < K) {
+                    idx[(size_t)q * K + e] = tk.out_i(j);
+                    dist2[(size_t)q * K + e] = tk.out_d(j);
+                }
+            }
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(&q_tail, 1);
+                while (q_done[t % KGW_QN] != t / KGW_QN) { }              // slot still holds ticket t - KGW_QN
+            }
+            t = __shfl_sync(CB_FULL_MASK, t, 0);
+            const int slot = t % KGW_QN;
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                const int e = j * 32 + lane;
+                if (e < K) q_entry[slot][1 + e] = tk.out_i(j);
+            }
+            if (lane == 0) q_entry[slot][0] = q;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) q_seq[slot] = t + 1;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd((int *)&producers_done, 1); }
+    } else {
+        // ------------------------------ copy warps ------------------------------
+        const int cw = wib - NSEARCH;
+        const int c4 = c >> 2;
+        const int V = K * c4;                                              // float4 vectors per item
+        const float4 *feat4 = reinterpret_cast<const float4 *>(feat);
+        for (int t = cw;; t += NCOPY) {
+            const int slot = t % KGW_QN;
+            bool finished = false;
+            while (q_seq[slot] != t + 1) {
+                if (producers_done == NSEARCH) {
+                    __threadfence_block();
+                    if (t >= *((volatile int *)&q_tail) ) { finished = true; break; }
+                }
+            }
+            if (finished) break;
+            __threadfence_block();
+            const int q = q_entry[slot][0];
+            float4 *dst = reinterpret_cast<float4 *>(grouped + (size_t)q * K * c);
+            for (int v0 = 0; v0 < V; v0 += 32 * KGL_U) {
+                float4 r[KGL_U];
+#pragma unroll
+                for (int u = 0; u < KGL_U; u++) {
+                    const int v = v0 + u * 32 + lane;
+                    if (v < V) {
+                        const int row = v / c4, col = v - row * c4;
+                        const int j = q_entry[slot][1 + row];
+                        r[u] = __ldg(feat4 + (size_t)j * c4 + col);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < KGL_U; u++) {
+                    const int v = v0 + u * 32 + lane;
+                    if (v < V) __stcs(dst + v, r[u]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) q_done[slot] = t / KGW_QN + 1;                   // the slot may take ticket t + KGW_QN
+        }
     }
 }
 
@@ -577,6 +726,9 @@ static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const 
                              const int *offset, const int *new_offset, int b, int n, int *idx, float *dist2, float *grouped,
                              const CbGridView &v, cudaStream_t st, bool fresh_grid = false)
 {
+    // copy path by row width (tools/gather_mode_probe.py, B200): rows up to 256 B go through two load/store-unit copy
+    // warps per CTA (a TMA bulk copy per 128-256 B row costs more than it moves), wider rows through the TMA ring
+    const int g_kg_ws = g_kg_mode >= 0 ? g_kg_mode : (c <= 64 ? 7 : 3);
     if (m == 0) return CB_OK;
     if (!fresh_grid) cb_knn_reset_flagged(v, st);      // a grid built a moment ago already has flagged_count = 0
     const int self_query = (new_xyz == xyz && m == n) ? 1 : 0;
@@ -603,6 +755,22 @@ static int knn_gather_launch(int m, int nsample, int c, const float *xyz, const 
         cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
         k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
         CB_COUNT(4);
+        CB_CUDA_CHECK("cb_knn_gather");
+        return CB_OK;
+    }
+    if (nsample <= 64 && (g_kg_ws == 6 || g_kg_ws == 7)) {
+        int blocks_l = 148 * 4;
+        const int ns_w = g_kg_ws == 6 ? 7 : 6;
+        if (blocks_l > (m + ns_w - 1) / ns_w) blocks_l = (m + ns_w - 1) / ns_w;
+#define KGL_LAUNCH(KPL, NC)                                                                                          \
+    k_knn_gather_lsu<KPL, NC><<<blocks_l, 256, 0, st>>>(m, nsample, c, new_xyz, feat, new_offset, b, self_query, v.scenes, \
+                                                        v.cells, v.sorted, idx, dist2, grouped, v.hdr, v.flagged)
+        if (nsample <= 32) { if (g_kg_ws == 6) KGL_LAUNCH(1, 1); else KGL_LAUNCH(1, 2); }
+        else { if (g_kg_ws == 6) KGL_LAUNCH(2, 1); else KGL_LAUNCH(2, 2); }
+#undef KGL_LAUNCH
+        cb_knn_replay_launch(nsample, m, xyz, new_xyz, offset, new_offset, b, idx, dist2, 0, v, st);
+        k_regather_flagged<<<148, 256, 0, st>>>(nsample, c, feat, idx, grouped, v.hdr, v.flagged);
+        CB_COUNT(3);
         CB_CUDA_CHECK("cb_knn_gather");
         return CB_OK;
     }
@@ -683,7 +851,12 @@ static bool kg_tma_ok(int c, int nsample, const float *feat, const float *groupe
 
 extern "C" int cb_knn_gather_set_spin_ns(int ns) { if (ns >= 0 && ns <= 4096) g_kg_spin_ns = ns; return g_kg_spin_ns; }
 
-extern "C" int cb_knn_gather_set_mode(int mode) { g_kg_ws = (mode >= 0 && mode <= 5) ? mode : 3; return g_kg_ws; }
+extern "C" int cb_knn_gather_set_l2_hint(int bits)
+{
+    bits &= 3;
+    return cudaMemcpyToSymbol(c_kg_l2_hint, &bits, sizeof(int)) == cudaSuccess ? bits : -1;
+}
+extern "C" int cb_knn_gather_set_mode(int mode) { g_kg_mode = (mode >= -1 && mode <= 7) ? mode : -1; return g_kg_mode; }
 
 extern "C" int cb_knn_gather_set_chunk_bytes(int bytes)
 {

@@ -84,9 +84,13 @@ int cb_knn_gather_grid(int m, int nsample, int c, const float *xyz, int n, const
 float cb_knn_set_occupancy(float factor);       /* tuning knob: target points per occupied grid cell = factor * K (default 0.45) */
 int cb_knn_gather_set_spin_ns(int ns);          /* tuning knob: nanosleep back-off of search warps on a full hand-off queue (default 0) */
 int cb_knn_gather_set_chunk_bytes(int bytes);   /* tuning knob: bytes per TMA chunk (default 8192); returns the value in use */
-int cb_knn_gather_set_mode(int mode);   /* tuning knob: 3 (default) = 7 search warps + 1 TMA copy warp per CTA (6-slab ring);
+int cb_knn_gather_set_mode(int mode);   /* tuning knob: -1 (default) = 7 for rows up to 256 B, else 3;
+                                           3 = 7 search warps + 1 TMA copy warp per CTA (6-slab ring);
                                            0 = every warp searches and copies (TMA); 1,2 = other ring depths; 4 = register copy;
-                                           5 = 6 search warps + a loader warp + a storer warp (same speed as 3) */
+                                           5 = 6 search warps + a loader warp + a storer warp (same speed as 3);
+                                           6,7 = 7 / 6 search warps + 1 / 2 load-store-unit copy warps (no TMA, no staging) */
+int cb_knn_gather_set_l2_hint(int bits); /* tuning knob: L2 policy of the TMA copies; bit 0 = output stores evict_first,
+                                           bit 1 = feature-row loads evict_last (default 3) */
 
 /* ------------------------------------------------------------------------------------------------
  * a2  farthest point sampling             replaces furthestsampling_cuda_launcher

@@ -96,6 +96,29 @@ def test_knn_large_k_bruteforce_path():
     assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
 
 
+@pytest.mark.parametrize("k", [4, 16, 300])
+def test_knn_replay_adversarial_point_order(k):
+    """Tie replay (knn.cu k_knn_replay) on a support set stored FARTHEST FIRST from the queries at the near end: every
+    candidate beats the running K-th distance, so a doubled batch overflows the survivor list and is retried smaller.
+    Every point is duplicated, so every query sees exact ties and goes through the replay."""
+    n = 30000
+    rng = np.random.default_rng(11)
+    x = np.sort(rng.random(n // 2).astype(np.float32) * 50)[::-1]
+    xyz = np.zeros((n, 3), np.float32)
+    xyz[0::2, 0] = x
+    xyz[1::2, 0] = x
+    xyz[:, 1] = np.repeat(rng.random(n // 2).astype(np.float32) * 0.01, 2)
+    off = cases.cumsum_i32([n])
+    qsel = np.concatenate([np.arange(0, 64), np.arange(n // 2, n // 2 + 64), np.arange(n - 128, n)])
+    q = xyz[qsel] + np.float32(0.0)
+    q[1::2, 2] += np.float32(0.5)                      # off-support queries as well
+    qoff = cases.cumsum_i32([len(q)])
+    idx, d2 = run_knn(k, xyz, q, off, qoff)
+    oi, od = oracle.knnquery(k, xyz, q, off, qoff)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
 def test_knn_properties_at_microbench_size():
     """size-independent properties at N = 2^18 (no oracle): self first, ascending, in-scene, distances consistent"""
     n, k = 1 << 18, 16
@@ -227,11 +250,11 @@ def test_queryandgroup_and_interpolation_api():
         assert np.allclose(out, ref, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 3, 4, 5])
+@pytest.mark.parametrize("mode", [-1, 0, 1, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("k,c", [(16, 256), (16, 64), (8, 32), (36, 32), (64, 64), (3, 6)])
 def test_fused_knn_gather(k, c, mode):
     from contrastboundary_b200 import fused, _lib
-    _lib.lib().cb_knn_gather_set_mode(mode)          # 0 one-warp TMA, 1/3 warp-specialised TMA rings, 4 direct register copy, 5 loader + storer warps
+    _lib.lib().cb_knn_gather_set_mode(mode)          # 0 one-warp TMA, 1/3 warp-specialised TMA rings, 4 direct register copy, 5 loader + storer warps, 6/7 LSU copy warps
     xyz, off = cases.scene_multi()
     rng = np.random.default_rng(4)
     feat = rng.standard_normal((len(xyz), c)).astype(np.float32)
@@ -240,7 +263,7 @@ def test_fused_knn_gather(k, c, mode):
     assert np.array_equal(idx.cpu().numpy(), oi)
     assert np.array_equal(d2.cpu().numpy().view(np.uint32), od.view(np.uint32))
     assert np.array_equal(grouped.cpu().numpy(), feat[oi])
-    _lib.lib().cb_knn_gather_set_mode(3)
+    _lib.lib().cb_knn_gather_set_mode(-1)
 
 
 def test_fused_knn_gather_ties_and_cross():

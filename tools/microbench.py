@@ -103,12 +103,12 @@ def main():
             medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb), iters=20)
             print(f"      kernel only, ws=3, queue-full back-off {ns:3d} ns: {medk:8.1f} us (min {mnk:.1f})")
         L.lib().cb_knn_gather_set_spin_ns(0)
-        for cb, ws in ((8192, 3), (16384, 3), (8192, 5), (8192, 1)):     # measured: 150-158 / 159 / 155 / 160 us
+        for cb, ws in ((8192, 3), (16384, 3), (8192, 5), (8192, 1), (8192, 6), (8192, 7)):     # measured: 150-158 / 159 / 155 / 160 us
             L.lib().cb_knn_gather_set_chunk_bytes(cb)
             L.lib().cb_knn_gather_set_mode(ws)
             medk, mnk = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz, feat, off, off, outb))
             print(f"      kernel only (grid prebuilt), ws={ws} chunk {cb:5d} B: {medk:8.1f} us (min {mnk:.1f}) -> {by / medk / 1e3:.0f} GB/s ({by / medk / 1e3 / 6569.6 * 100:.0f}%)")
-        L.lib().cb_knn_gather_set_chunk_bytes(8192); L.lib().cb_knn_gather_set_mode(3)
+        L.lib().cb_knn_gather_set_chunk_bytes(8192); L.lib().cb_knn_gather_set_mode(-1)
         xyz2 = xyz.clone()          # a distinct query tensor: queries are processed in ORIGINAL order (linear output addresses)
         medq, mnq = timeit(lambda: fused.knn_gather_grid(grid, k, xyz, xyz2, feat, off, off, outb))
         print(f"      kernel only, queries in original order (streamed output):  {medq:8.1f} us (min {mnq:.1f}) -> {by / medq / 1e3:.0f} GB/s ({by / medq / 1e3 / 6569.6 * 100:.0f}%)")
