@@ -197,10 +197,12 @@ __global__ void __launch_bounds__(UM_THREADS) k_umma_linear(int n, int K, int N,
 // the epilogue drains tile t.  Four mbarrier families: full[s] (4 producer warps -> MMA), empty[s] (commit -> producers),
 // tfull[b] (commit -> epilogue), tempty[b] (4 epilogue warps -> MMA).
 // ---------------------------------------------------------------------------------------------
-#define UM2_STAGES 3
-#define UM2_PWARPS (4 * UM2_STAGES)            // producer warps: one group of 4 per ring slot
-#define UM2_MMA_WARP (4 + UM2_PWARPS)
-#define UM2_THREADS (32 * (UM2_MMA_WARP + 1))
+#define UM2_STAGES 3                           // v2: three producer groups, loads held in registers
+#define UM3_STAGES 2                           // v3: two producer groups ...
+#define UM3_DEPTH 3                            //     ... each with a 3-deep cp.async ring of raw FP32 chunks (96 KB in flight per SM)
+#define UM_THREADS_OF(STAGES) (32 * (4 + 4 * (STAGES) + 1))
+#define UM2_THREADS UM_THREADS_OF(UM2_STAGES)
+#define UM3_THREADS UM_THREADS_OF(UM3_STAGES)
 #define UM2_EPI_PITCH 36                      // floats per staged epilogue row (32 + 4: conflict-free float4 rows)
 #define UM2_EPI_BYTES (4 * 32 * UM2_EPI_PITCH * 4)
 
@@ -209,13 +211,24 @@ __device__ __forceinline__ void um_mbar_arrive(unsigned bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int TRANS_B>
-__global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, int N, int ncols, int ntiles, const float *__restrict__ A,
+// v3 = the same pipeline with DEPTH > 0: the producer threads do not hold their loads in registers (3 groups x 128 threads x 8
+// float4 = 48 KB per SM, the measured limit of v2: HBM-latency bound at 35 % DRAM utilisation) but stream them with
+// cp.async.cg into a private DEPTH-deep ring of raw FP32 chunks in shared memory; every thread later reads back exactly the 16-byte
+// pieces it copied itself (no barrier between copy and use, only cp.async.wait_group), splits them into TF32 hi / lo and
+// writes the core-matrix tiles as before.  STAGES x DEPTH x 16 KB are in flight per SM.
+__device__ __forceinline__ void um_cp_async16(unsigned dst, const void *src, unsigned src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int TRANS_B, int STAGES, int DEPTH>
+__global__ void __launch_bounds__(UM_THREADS_OF(STAGES), 1) k_umma_linear2(int n, int K, int N, int ncols, int ntiles, const float *__restrict__ A,
                                                                  int lda, const float *__restrict__ W, const float *__restrict__ bias,
                                                                  float *__restrict__ Y, int ldy, int n0, int ldw)
 {
     extern __shared__ __align__(1024) unsigned char um_smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * UM2_STAGES + 4];
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
+    constexpr int MMA_WARP = 4 + 4 * STAGES, NTHREADS = UM_THREADS_OF(STAGES);
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunk = (K + UM_KC - 1) / UM_KC;
@@ -223,17 +236,18 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     // layout: [W hi chunks][W lo chunks][stage 0: A hi, A lo][stage 1 ...]
     unsigned char *pw_hi = um_smem, *pw_lo = pw_hi + (size_t)nchunk * w_bytes;
     unsigned char *pa = pw_lo + (size_t)nchunk * w_bytes;
-    unsigned char *pstage = pa + (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4;        // epilogue transposition buffers (4 warps)
+    unsigned char *pstage = pa + (size_t)STAGES * 2 * 128 * UM_KC * 4;        // epilogue transposition buffers (4 warps)
+    unsigned char *praw = pstage + UM2_EPI_BYTES;                                 // DEPTH > 0: raw FP32 chunk rings of the producer groups
     const unsigned sw_hi = um_smem_u32(pw_hi), sw_lo = um_smem_u32(pw_lo), sa = um_smem_u32(pa);
     const unsigned a_stage = 2 * 128 * UM_KC * 4;
-    const unsigned b_full = um_smem_u32(&bars[0]), b_empty = um_smem_u32(&bars[UM2_STAGES]), b_tfull = um_smem_u32(&bars[2 * UM2_STAGES]),
-                   b_tempty = um_smem_u32(&bars[2 * UM2_STAGES + 2]);
-    if (warp == UM2_MMA_WARP) {
+    const unsigned b_full = um_smem_u32(&bars[0]), b_empty = um_smem_u32(&bars[STAGES]), b_tfull = um_smem_u32(&bars[2 * STAGES]),
+                   b_tempty = um_smem_u32(&bars[2 * STAGES + 2]);
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(&tmem_slot)), "r"((unsigned)ncols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        for (int s = 0; s < UM2_STAGES; s++) { um_mbar_init(b_full + 8 * s, 4); um_mbar_init(b_empty + 8 * s, 1); }
+        for (int s = 0; s < STAGES; s++) { um_mbar_init(b_full + 8 * s, 4); um_mbar_init(b_empty + 8 * s, 1); }
         for (int b = 0; b < 2; b++) { um_mbar_init(b_tfull + 8 * b, 1); um_mbar_init(b_tempty + 8 * b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -243,7 +257,7 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
         unsigned char *dh = pw_hi + (size_t)j * w_bytes, *dl = pw_lo + (size_t)j * w_bytes;
         if (!TRANS_B) {
             const int groups = N / 8;
-            for (int it = warp; it < groups * (UM_KC / 16); it += UM2_THREADS / 32) {
+            for (int it = warp; it < groups * (UM_KC / 16); it += NTHREADS / 32) {
                 const int g = it % groups, cq = it / groups;
                 const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
             }
         } else {                                            // W is (K x N): 4 consecutive output columns per thread
             const int nq = N / 4;
-            for (int e = tid; e < nq * UM_KC; e += UM2_THREADS) {
+            for (int e = tid; e < nq * UM_KC; e += NTHREADS) {
                 const int row = (e % nq) * 4, kf = e / nq;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (kf < kc) v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(k0 + kf) * ldw + n0 + row));
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
     const unsigned lbo = 128, sbo = (UM_KC / 4) * 128;
 
-    if (warp >= 4 && warp < UM2_MMA_WARP) {
+    if (warp >= 4 && warp < MMA_WARP) {
         // ===== producers: group `stage` (4 warps) fills ring slot `stage`, i.e. the chunks c = stage, stage + STAGES, ... of
         //       this CTA's chunk sequence (tile-major) =====
         const int stage = (warp - 4) / 4, pw = (warp - 4) % 4;
@@ -289,37 +303,89 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
         const long long total_chunks = (long long)my_tiles * nchunk;
         unsigned char *dh = pa + (size_t)stage * a_stage, *dl = dh + 128 * UM_KC * 4;
         unsigned use = 0;
-        for (long long c = stage; c < total_chunks; c += UM2_STAGES, use++) {
-            const int tseq = (int)(c / nchunk), j = (int)(c % nchunk);
-            const long long row0 = ((long long)blockIdx.x + (long long)tseq * gridDim.x) * 128;
-            const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
-            // the loads do not depend on the slot: issue them before waiting for it
-            float4 v[8];
+        if (DEPTH == 0) {
+            for (long long c = stage; c < total_chunks; c += STAGES, use++) {
+                const int tseq = (int)(c / nchunk), j = (int)(c % nchunk);
+                const long long row0 = ((long long)blockIdx.x + (long long)tseq * gridDim.x) * 128;
+                const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
+                // the loads do not depend on the slot: issue them before waiting for it
+                float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int it = pw + 4 * u;
-                const int g = it % 16, cq = it / 16;
-                const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kf < kc && row0 + row < n) v[u] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(row0 + row) * lda + k0 + kf));
-            }
-            um_mbar_wait(b_empty + 8 * stage, (use & 1u) ^ 1u);              // slot free (passes on first use)
+                for (int u = 0; u < 8; u++) {
+                    const int it = pw + 4 * u;
+                    const int g = it % 16, cq = it / 16;
+                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kf < kc && row0 + row < n) v[u] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(row0 + row) * lda + k0 + kf));
+                }
+                um_mbar_wait(b_empty + 8 * stage, (use & 1u) ^ 1u);              // slot free (passes on first use)
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int it = pw + 4 * u;
-                const int g = it % 16, cq = it / 16;
-                const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
-                float4 h, l;
-                um_split(v[u].x, h.x, l.x); um_split(v[u].y, h.y, l.y); um_split(v[u].z, h.z, l.z); um_split(v[u].w, h.w, l.w);
-                const unsigned o = um_off(row, kf);
-                *reinterpret_cast<float4 *>(dh + o) = h;
-                *reinterpret_cast<float4 *>(dl + o) = l;
+                for (int u = 0; u < 8; u++) {
+                    const int it = pw + 4 * u;
+                    const int g = it % 16, cq = it / 16;
+                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                    float4 h, l;
+                    um_split(v[u].x, h.x, l.x); um_split(v[u].y, h.y, l.y); um_split(v[u].z, h.z, l.z); um_split(v[u].w, h.w, l.w);
+                    const unsigned o = um_off(row, kf);
+                    *reinterpret_cast<float4 *>(dh + o) = h;
+                    *reinterpret_cast<float4 *>(dl + o) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) um_mbar_arrive(b_full + 8 * stage);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) um_mbar_arrive(b_full + 8 * stage);
+        } else {
+            // private ring: slab d of this group, piece u of this thread at ((d * 8 + u) * 128 + thread-in-group) * 16 bytes
+            constexpr int DD = DEPTH > 0 ? DEPTH : 1;
+            const int tig = pw * 32 + lane;
+            unsigned char *myraw = praw + ((size_t)stage * DD * 8 * 128 + tig) * 16;
+            const unsigned myraw_s = um_smem_u32(myraw);
+            auto issue = [&](long long c, int slab) {
+                if (c < total_chunks) {
+                    const int tseq = (int)(c / nchunk), j = (int)(c % nchunk);
+                    const long long row0 = ((long long)blockIdx.x + (long long)tseq * gridDim.x) * 128;
+                    const int k0 = j * UM_KC, kc = min(UM_KC, K - k0);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int it = pw + 4 * u;
+                        const int g = it % 16, cq = it / 16;
+                        const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                        const bool in = kf < kc && row0 + row < n;
+                        const float *src = in ? A + (size_t)(row0 + row) * lda + k0 + kf : A;
+                        um_cp_async16(myraw_s + (unsigned)((slab * 8 + u) * 128 * 16), src, in ? 16u : 0u);   // src-size 0: zero fill
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");           // always: keeps the group count uniform
+            };
+#pragma unroll
+            for (int d = 0; d < DD; d++) issue((long long)stage + (long long)d * STAGES, d);
+            int slab = 0;
+            for (long long c = stage; c < total_chunks; c += STAGES, use++) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(DD - 1) : "memory");
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = *reinterpret_cast<const float4 *>(myraw + (size_t)((slab * 8 + u) * 128 * 16));
+                um_mbar_wait(b_empty + 8 * stage, (use & 1u) ^ 1u);              // slot free (passes on first use)
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int it = pw + 4 * u;
+                    const int g = it % 16, cq = it / 16;
+                    const int row = g * 8 + (lane & 7), kf = (cq * 4 + (lane >> 3)) * 4;
+                    float4 h, l;
+                    um_split(v[u].x, h.x, l.x); um_split(v[u].y, h.y, l.y); um_split(v[u].z, h.z, l.z); um_split(v[u].w, h.w, l.w);
+                    const unsigned o = um_off(row, kf);
+                    *reinterpret_cast<float4 *>(dh + o) = h;
+                    *reinterpret_cast<float4 *>(dl + o) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) um_mbar_arrive(b_full + 8 * stage);
+                issue(c + (long long)DD * STAGES, slab);                          // refill the slab just consumed
+                slab = slab + 1 == DD ? 0 : slab + 1;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-    } else if (warp == UM2_MMA_WARP) {
+    } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
         if (lane == 0) {
             unsigned it_count = 0, tcount = 0;
@@ -329,8 +395,8 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned acc = tmem + buf * (unsigned)N;
                 for (int j = 0; j < nchunk; j++, it_count++) {
-                    const int stage = it_count % UM2_STAGES;
-                    const unsigned use = it_count / UM2_STAGES;
+                    const int stage = it_count % STAGES;
+                    const unsigned use = it_count / STAGES;
                     um_mbar_wait(b_full + 8 * stage, use & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int kc = min(UM_KC, K - j * UM_KC);
@@ -401,14 +467,20 @@ __global__ void __launch_bounds__(UM2_THREADS, 1) k_umma_linear2(int n, int K, i
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == UM2_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)ncols));
 }
 
-static int g_umma_v = 2;    // kernel version used by cb_umma_linear: 2 = persistent pipelined (default), 1 = simple one-tile CTAs
+static int g_umma_v = 3;    // kernel version used by cb_umma_linear: 3 = persistent pipelined, cp.async raw ring (default),
+                            // 2 = persistent pipelined, loads held in registers, 1 = simple one-tile CTAs
 extern "C" int cb_linear_set_umma_version(int v)
 {
-    if (v == 1 || v == 2) g_umma_v = v;
+    if (v >= 1 && v <= 3) g_umma_v = v;
     return g_umma_v;
+}
+static size_t um_ring_bytes(int v)
+{
+    return v == 3 ? (size_t)UM3_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES + (size_t)UM3_STAGES * UM3_DEPTH * 128 * UM_KC * 4
+                  : (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES;
 }
 
 static int g_umma = 1;      // 1: tcgen05 path for the shapes it takes (default) | 0: mma.sync kernels (tc_gemm.cu)
@@ -425,7 +497,7 @@ bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int l
     // larger layers (c >= 256: levels 3-4, a few hundred rows) keep the mma.sync / cuBLAS path
     const int nchunk = (K + UM_KC - 1) / UM_KC;
     const size_t w_bytes = (size_t)2 * nchunk * (N < 256 ? N : 256) * UM_KC * 4;
-    const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES;
+    const size_t a_ring = um_ring_bytes(2);     // v3 falls back to the v2 ring when W does not fit beside its raw ring
     // 32 -> 32 layers: 12 MMAs of N = 32 per 32 KB tile are issue-latency bound (26.7 us vs 20.4 us for the mma.sync kernel at
     // n = 163840, tools/bench_linear.py); from 64 columns or 64 reduction elements on, the tcgen05 kernel is 1.1-1.6x faster
     return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && (K >= 64 || N >= 64) && lda % 4 == 0 && ldy % 4 == 0 &&
@@ -450,17 +522,24 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
         // ONE opt-in to the full 227 KB for every instance: the dynamic size differs from layer to layer, and a CUDA graph
         // replays a node with ITS size against whatever the attribute is at replay time
         const int dyn_max = 227 * 1024 - 2048;        // 227 KB per CTA minus the kernels' static shared memory (1 KB) and slack
-        cudaFuncSetAttribute(k_umma_linear2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
-        cudaFuncSetAttribute(k_umma_linear2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear2<0, UM2_STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear2<1, UM2_STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear2<0, UM3_STAGES, UM3_DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+        cudaFuncSetAttribute(k_umma_linear2<1, UM3_STAGES, UM3_DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
         cudaFuncSetAttribute(k_umma_linear<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
         cudaFuncSetAttribute(k_umma_linear<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
         (void)cudaGetLastError();
         attr_set = true;
     }
-    if (g_umma_v == 2) {
+    if (g_umma_v >= 2) {
         // column blocks such that W (hi + lo, all of K) + the A ring fit the 227 KB of one CTA; N of a block % 16 == 0, <= 256
         const int nchunk = (K + UM_KC - 1) / UM_KC;
-        const size_t a_ring = (size_t)UM2_STAGES * 2 * 128 * UM_KC * 4 + UM2_EPI_BYTES;
+        int ver = g_umma_v;
+        if (ver == 3) {                      // the raw ring costs 96 KB: only where all of W still fits in ONE column block
+            const size_t room = (size_t)227 * 1024 - 2048 - um_ring_bytes(3);
+            if ((size_t)2 * nchunk * N * UM_KC * 4 > room || N > 256) ver = 2;
+        }
+        const size_t a_ring = um_ring_bytes(ver);
         int nb_max = (int)(((size_t)227 * 1024 - 2048 - a_ring) / ((size_t)2 * nchunk * UM_KC * 4));
         nb_max = nb_max / 16 * 16;
         if (nb_max > 256) nb_max = 256;
@@ -474,10 +553,15 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
                 while (ncols < 2 * nb) ncols <<= 1;
                 const size_t smem = (size_t)2 * nchunk * nb * UM_KC * 4 + a_ring;
                 const int blocks = ntiles < sms ? ntiles : sms;
-                if (trans_b) {
-                    k_umma_linear2<1><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
+                if (ver == 3) {
+                    if (trans_b)
+                        k_umma_linear2<1, UM3_STAGES, UM3_DEPTH><<<blocks, UM3_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
+                    else
+                        k_umma_linear2<0, UM3_STAGES, UM3_DEPTH><<<blocks, UM3_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
+                } else if (trans_b) {
+                    k_umma_linear2<1, UM2_STAGES, 0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
                 } else {
-                    k_umma_linear2<0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
+                    k_umma_linear2<0, UM2_STAGES, 0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
                 }
                 CB_COUNT(1);
             }

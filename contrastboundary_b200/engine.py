@@ -8,6 +8,20 @@ import torch
 from .model import CBLConfig, Loss, PointTransformerSeg, build_geometry
 
 
+WGRAD_FORK = True      # weight gradients of the linear layers on a side stream during the backward (linear_ops.wgrad_fork)
+
+
+def _backward(loss):
+    """loss.sum().backward() as the reference's iteration does it (pytorch/tool/train.py:322-324), with the weight-gradient
+    kernels of the linear layers forked to a side stream and joined before anyone reads the gradients."""
+    if WGRAD_FORK and loss.is_cuda:
+        from .linear_ops import wgrad_fork
+        with wgrad_fork():
+            loss.sum().backward()
+    else:
+        loss.sum().backward()
+
+
 class TrainStep:
     def __init__(self, cfg: CBLConfig = None, device="cuda", ddp=False, lr=0.5, momentum=0.9, weight_decay=1e-4, seed=0):
         self.cfg = cfg or CBLConfig()
@@ -69,7 +83,7 @@ class TrainStep:
             self.prefetch_geometry(next_batch)
         out, stages = self.net(batch, levels)
         loss = self.criterion(out, batch["point_labels"], stages)
-        loss.sum().backward()
+        _backward(loss)
         if update:
             self.opt.step()
         return loss.detach()
@@ -174,7 +188,7 @@ class GraphTrainStep(TrainStep):
         self._geo.clear()
         out, stages = self.model(batch, None)
         loss = self.criterion(out, batch["point_labels"], stages)
-        loss.sum().backward()
+        _backward(loss)
         if self._gparams is None:
             # parameters that receive a gradient (the rest keep grad None, as in stream mode)
             self._gparams = [p for p in self.model.parameters() if p.grad is not None]
@@ -200,7 +214,7 @@ class GraphTrainStep(TrainStep):
         self.opt.zero_grad(set_to_none=True)
         out, stages = self.model(batch, None)
         loss = self.criterion(out, batch["point_labels"], stages)
-        loss.sum().backward()
+        _backward(loss)
         ps = self._gparams if self._gparams is not None else [p for p in self.model.parameters() if p.grad is not None]
         flat = torch.cat([p.grad.reshape(-1) for p in ps])
         for p in self.model.parameters():
@@ -257,7 +271,7 @@ class GraphTrainStep(TrainStep):
                 with torch.cuda.graph(g, pool=self._net_pool, **({"stream": self.hp} if self.hp is not None else {})):
                     out, stages = self.model(sl.inputs, sl.levels)
                     loss = self.criterion(out, sl.inputs["point_labels"], stages)
-                    loss.sum().backward()
+                    _backward(loss)
                     torch.cat([p.grad.reshape(-1) for p in self._gparams], out=self.flat)
                     sl.loss = loss.detach()
                 sl.net = g

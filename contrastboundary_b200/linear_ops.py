@@ -23,15 +23,62 @@ def set_tensor_cores(flag):
     L.lib().cb_linear_set_tensor_cores(C.c_int(1 if flag else 0))
 
 
+# ------------------------------------------------------------------------------------------------
+# Weight gradients on a side stream.  In the backward of y = x W^T + b, dW = g^T x / db = sum(g) feed nothing but the
+# optimizer, while dx = g W is on the critical path of everything upstream.  engine.TrainStep wraps its backward in
+# `wgrad_fork()`: every linear layer then launches its weight-gradient kernels on ONE side stream (forked after g is ready),
+# and the engine joins that stream once, after the backward and before the gradients are packed.  Inside a CUDA-graph capture
+# the fork / join become graph edges: ~70 small kernels per step leave the serial chain of the network graph and overlap with
+# it.  Off by default: a caller who runs loss.backward() without the join must not see gradients that are still in flight.
+# ------------------------------------------------------------------------------------------------
+_fork = {"on": False, "streams": {}, "used": set()}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _fork["streams"].get(key)
+    if st is None:
+        st = _fork["streams"][key] = torch.cuda.Stream(device=key)
+    return st
+
+
+class wgrad_fork:
+    """with wgrad_fork(): loss.backward()   -- weight gradients of the linear layers run on a side stream; the exit joins it."""
+
+    def __enter__(self):
+        self.prev = _fork["on"]
+        _fork["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _fork["on"] = self.prev
+        join_wgrad()
+        return False
+
+
+def join_wgrad():
+    """The current stream waits for every weight-gradient kernel forked since the last join."""
+    for key in list(_fork["used"]):
+        torch.cuda.current_stream(key).wait_stream(_fork["streams"][key])
+    _fork["used"].clear()
+
+
 class _SkinnyLinearFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         n, ci = x.shape
         co = weight.shape[0]
-        y = torch.empty((n, co), dtype=torch.float32, device=x.device)
-        L.call("cb_linear_forward", n, ci, co, x, weight, bias, y, L.stream())
+        ctx.custom = n >= MIN_ROWS and co <= MAX_CO
+        if ctx.custom:
+            y = torch.empty((n, co), dtype=torch.float32, device=x.device)
+            L.call("cb_linear_forward", n, ci, co, x, weight, bias, y, L.stream())
+        else:
+            y = F.linear(x, weight, bias)              # few rows: cuBLAS (see MIN_ROWS)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        # the fork is only safe when dW / db go straight to AccumulateGrad (which adopts the tensor without launching a kernel
+        # while p.grad is None); a weight that is itself computed (e.g. a slice of a parameter) has more backward ahead of it
+        ctx.leaf_params = weight.is_leaf and (bias is None or bias.is_leaf)
         return y
 
     @staticmethod
@@ -42,24 +89,37 @@ class _SkinnyLinearFn(Function):
         co = weight.shape[0]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            L.call("cb_linear_dgrad", n, ci, co, g, weight, gx, L.stream())
-        if ctx.needs_input_grad[1]:
-            if n >= MIN_ROWS_WGRAD and (TENSOR_CORES or (ci * co <= MAX_WGRAD and co <= 256)):
-                gw = torch.empty_like(weight)
-                gb = torch.empty(co, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-                L.call("cb_linear_wgrad", n, ci, co, x, g, gw, gb, L.stream())
+            if ctx.custom:
+                gx = torch.empty_like(x)
+                L.call("cb_linear_dgrad", n, ci, co, g, weight, gx, L.stream())
             else:
-                gw = g.t().mm(x)
-                gb = g.sum(0) if ctx.has_bias else None
-        elif ctx.has_bias:
-            gb = g.sum(0)
+                gx = g.mm(weight)
+        want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            side = None
+            if _fork["on"] and g.is_cuda and ctx.leaf_params and weight.grad is None:
+                side = _side_stream(g.device)
+                side.wait_stream(torch.cuda.current_stream(g.device))          # g is ready; x, weight long since
+            import contextlib
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                if want_w and n >= MIN_ROWS_WGRAD and co <= MAX_CO and (TENSOR_CORES or (ci * co <= MAX_WGRAD and co <= 256)):
+                    gw = torch.empty_like(weight)
+                    gb = torch.empty(co, dtype=torch.float32, device=x.device) if want_b else None
+                    L.call("cb_linear_wgrad", n, ci, co, x, g, gw, gb, L.stream())
+                else:
+                    if want_w:
+                        gw = g.t().mm(x)
+                    if want_b:
+                        gb = g.sum(0)
+            if side is not None:
+                x.record_stream(side)
+                g.record_stream(side)
+                _fork["used"].add(side.device.index)
         return gx, gw, gb
 
 
 def fast_linear(x, weight, bias=None):
-    if (x.is_cuda and x.dtype == torch.float32 and weight.shape[0] <= MAX_CO and x.numel() // x.shape[-1] >= MIN_ROWS
-            and weight.is_contiguous()):
+    if x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.is_contiguous() and x.dim() >= 2:
         shp = x.shape
         y = _SkinnyLinearFn.apply(x.reshape(-1, shp[-1]).contiguous(), weight, bias)
         return y.view(*shp[:-1], weight.shape[0])

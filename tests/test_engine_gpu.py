@@ -55,6 +55,47 @@ def test_graph_step_matches_stream_step():
     assert all(sl.net is not None for sl in gts._sigs[tuple(host[0]["offset_host"])])
 
 
+def test_forked_weight_gradients_match_serial_backward():
+    """engine._backward runs the weight-gradient kernels of the linear layers on a side stream (linear_ops.wgrad_fork) and
+    joins it before the gradients are read: same gradients as the serial backward, down to the float-atomic noise floor —
+    a gradient read before its kernel has finished is off by O(1)."""
+    dev = torch.device("cuda", 0)
+    b = engine.to_device(_batches(1, [4096, 3072], 900)[0], dev)
+    ts = engine.TrainStep(model.CBLConfig(), dev, seed=5)
+
+    def grads(fork):
+        engine.WGRAD_FORK = fork
+        ts.opt.zero_grad(set_to_none=True)
+        out, stages = ts.net(b, None)
+        loss = ts.criterion(out, b["point_labels"], stages)
+        engine._backward(loss)
+        named = {n: p.grad.clone() for n, p in ts.model.named_parameters() if p.grad is not None}
+        torch.cuda.synchronize()
+        return named
+    try:
+        serial, serial2, forked = grads(False), grads(False), grads(True)
+    finally:
+        engine.WGRAD_FORK = True
+    assert set(serial) == set(forked) and len(serial) > 100
+    worst_floor = worst = 0.0
+    for n in serial:
+        den = float(serial[n].norm().clamp(min=1e-12))
+        floor = float((serial2[n] - serial[n]).norm()) / den
+        rel = float((forked[n] - serial[n]).norm()) / den
+        if floor > 0.02:
+            # pure-noise gradients: e.g. the q / k biases feed a BatchNorm (linear_w[0], blocks.py:24), which removes any
+            # per-channel shift — their true gradient is 0 and two serial runs already differ by O(1)
+            continue
+        worst_floor, worst = max(worst_floor, floor), max(worst, rel)
+        assert rel < 0.2, (n, rel, floor)
+    cat = lambda d: torch.cat([d[n].reshape(-1) for n in sorted(d)])
+    g0, g1, g2 = cat(serial), cat(serial2), cat(forked)
+    tot_floor, tot = float((g1 - g0).norm() / g0.norm()), float((g2 - g0).norm() / g0.norm())
+    print(f"forked-vs-serial: worst tensor {worst:.3e} (floor {worst_floor:.3e}), whole gradient {tot:.3e} (floor {tot_floor:.3e})")
+    assert worst < 4.0 * worst_floor + 2e-3, (worst, worst_floor)
+    assert tot < 4.0 * tot_floor + 1e-3, (tot, tot_floor)
+
+
 def test_graph_step_other_signature_falls_back_or_captures():
     dev = torch.device("cuda", 0)
     kw = dict(lr=0.01, seed=5)

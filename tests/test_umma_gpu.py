@@ -12,12 +12,12 @@ SHAPES = [(1000, 32, 96), (150000, 32, 96), (60000, 72, 144), (40960, 64, 192), 
           (8192, 512, 512), (1, 16, 16)]
 
 
-@pytest.fixture(params=[2, 1], ids=["pipelined", "simple"])
+@pytest.fixture(params=[3, 2, 1], ids=["pipelined_cp_async", "pipelined", "simple"])
 def version(request):
     import ctypes as C
     L.lib().cb_linear_set_umma_version(C.c_int(request.param))
     yield request.param
-    L.lib().cb_linear_set_umma_version(C.c_int(2))
+    L.lib().cb_linear_set_umma_version(C.c_int(3))
 
 
 @pytest.mark.parametrize("n,ci,co", SHAPES)

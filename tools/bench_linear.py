@@ -35,7 +35,7 @@ def main():
     lib = L.lib()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    print("      n    ci    co |  fwd umma us (frac)   fwd mma.sync us (frac) | dgrad umma us (frac)  dgrad mma.sync us (frac)")
+    print("      n    ci    co |  fwd: umma v3 us (frac)  umma v2  mma.sync | dgrad: umma v3 us (frac)  umma v2  mma.sync")
     for n, ci, co in SHAPES:
         x = torch.randn(n, ci, device="cuda")
         w = torch.randn(co, ci, device="cuda")
@@ -45,15 +45,16 @@ def main():
         dx = torch.empty(n, ci, device="cuda")
         by = 4 * n * (ci + co)
         res = []
-        for umma in (1, 0):
-            lib.cb_linear_set_umma(C.c_int(umma))
-            res.append(timed(lambda: L.call("cb_linear_forward", n, ci, co, x, w, b, y, L.stream()), flush))
-        for umma in (1, 0):
-            lib.cb_linear_set_umma(C.c_int(umma))
-            res.append(timed(lambda: L.call("cb_linear_dgrad", n, ci, co, g, w, dx, L.stream()), flush))
+        for call, args in (("cb_linear_forward", (n, ci, co, x, w, b, y)), ("cb_linear_dgrad", (n, ci, co, g, w, dx))):
+            for umma, ver in ((1, 3), (1, 2), (0, 3)):
+                lib.cb_linear_set_umma(C.c_int(umma))
+                lib.cb_linear_set_umma_version(C.c_int(ver))
+                res.append(timed(lambda: L.call(call, *args, L.stream()), flush))
         lib.cb_linear_set_umma(C.c_int(1))
+        lib.cb_linear_set_umma_version(C.c_int(3))
         fr = [by / t / 1e3 / peak for t in res]
-        print("%7d %5d %5d | %9.1f (%.2f) %14.1f (%.2f)      | %9.1f (%.2f) %14.1f (%.2f)" % (n, ci, co, res[0], fr[0], res[1], fr[1], res[2], fr[2], res[3], fr[3]))
+        print("%7d %5d %5d | %9.1f (%.2f) %8.1f (%.2f) %8.1f (%.2f) | %9.1f (%.2f) %8.1f (%.2f) %8.1f (%.2f)"
+              % (n, ci, co, res[0], fr[0], res[1], fr[1], res[2], fr[2], res[3], fr[3], res[4], fr[4], res[5], fr[5]))
 
 
 if __name__ == "__main__":
