@@ -62,11 +62,30 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_colsums(long long n, int C, c
 }
 
 // forward apply: every block derives scale / shift from the statistics; block 0 also writes bnbuf and the running stats
+// Self-cleaning accumulators (ticket != NULL): the statistics buffer is PERSISTENT and zero between uses — the column-sum
+// kernel accumulates into it, every block of the apply kernel reads it in its prologue and then takes a ticket; the block
+// that takes the last ticket knows everyone has read, and zeroes buffer and ticket for the next use.  This removes the
+// cudaMemsetAsync in front of every BatchNorm (2 per layer and step: 138 graph nodes of this network).
+__device__ __forceinline__ void bn_self_clean(double *acc, int count, int *ticket)
+{
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        for (int c = threadIdx.x; c < count; c += blockDim.x) acc[c] = 0.0;
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
 __global__ void __launch_bounds__(BN_THREADS) k_bn_apply(long long n, int C, const float *__restrict__ x,
-                                                         const float *__restrict__ residual, const double *__restrict__ stats,
+                                                         const float *__restrict__ residual, double *stats,
                                                          const float *__restrict__ gamma, const float *__restrict__ beta,
                                                          float *running_mean, float *running_var, float momentum, float eps,
-                                                         int training, int relu, float *__restrict__ y, float *__restrict__ bnbuf)
+                                                         int training, int relu, float *__restrict__ y, float *__restrict__ bnbuf,
+                                                         int *ticket)
 {
     extern __shared__ float ba_sm[];            // [2][C]: scale, shift
     const double count = (double)n;
@@ -94,6 +113,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_apply(long long n, int C, con
         }
     }
     __syncthreads();
+    if (ticket && training) bn_self_clean(stats, 2 * C, ticket);
     const int cq = C >> 2;
     const long long total = n * cq;
     for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BN_THREADS) {
@@ -114,9 +134,9 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_apply(long long n, int C, con
 __global__ void __launch_bounds__(BN_THREADS) k_bn_bwd_apply(long long n, int C, const float *__restrict__ x,
                                                              const float *__restrict__ gy, const float *__restrict__ y,
                                                              const float *__restrict__ gamma, const float *__restrict__ bnbuf,
-                                                             const double *__restrict__ sums, int training, int relu,
+                                                             double *sums, int training, int relu,
                                                              float *__restrict__ gx, float *__restrict__ gres,
-                                                             float *__restrict__ dgamma, float *__restrict__ dbeta)
+                                                             float *__restrict__ dgamma, float *__restrict__ dbeta, int *ticket)
 {
     extern __shared__ float bb_sm[];            // [5][C]: kk, ma, mb, mean, invstd
     const double count = (double)n;
@@ -131,6 +151,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_bwd_apply(long long n, int C,
         if (blockIdx.x == 0) { dgamma[c] = (float)sb; dbeta[c] = (float)sa; }
     }
     __syncthreads();
+    if (ticket) bn_self_clean(sums, 2 * C, ticket);
     const int cq = C >> 2;
     const long long total = n * cq;
     for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BN_THREADS) {
@@ -174,14 +195,17 @@ extern "C" int cb_bn_act_forward(long long n, int c, const float *x, const float
     CB_REQUIRE(((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual)) & 15) == 0, CB_EINVAL, "cb_bn_act_forward: 16-byte alignment");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return CB_OK;
+    const bool persistent = (training & 2) != 0;       // stats: 2c doubles + an int ticket, zero on entry, zero again on exit
+    training &= 1;
+    int *ticket = persistent ? reinterpret_cast<int *>(stats + 2 * c) : nullptr;
     if (training) {
-        cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c, st);
+        if (!persistent) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c, st);
         const int lanes = BN_THREADS / (c / 4) > 0 ? BN_THREADS / (c / 4) : 1;
         k_bn_colsums<0><<<bn_grid(n, lanes * 8), BN_THREADS, 2 * c * sizeof(float), st>>>(n, c, x, nullptr, nullptr, nullptr, 0, stats);
     }
     k_bn_apply<<<bn_grid(n * (c / 4), BN_THREADS * 4), BN_THREADS, 2 * c * sizeof(float), st>>>(n, c, x, residual, stats, gamma, beta,
                                                                                              running_mean, running_var, momentum,
-                                                                                             eps, training, relu, y, bnbuf);
+                                                                                             eps, training, relu, y, bnbuf, ticket);
     CB_COUNT(training ? 2 : 1);
     CB_CUDA_CHECK("cb_bn_act_forward");
     return CB_OK;
@@ -195,7 +219,10 @@ extern "C" int cb_bn_act_backward(long long n, int c, const float *x, const floa
     CB_REQUIRE(x && gamma && bnbuf && grad_y && grad_x && grad_gamma && grad_beta && sums && (y || !relu), CB_EINVAL,
                "cb_bn_act_backward: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, st);
+    const bool persistent = (training & 2) != 0;       // sums: 2c doubles + an int ticket, zero on entry, zero again on exit
+    training &= 1;
+    int *ticket = persistent ? reinterpret_cast<int *>(sums + 2 * c) : nullptr;
+    if (!persistent) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, st);
     if (n == 0) {
         cudaMemsetAsync(grad_gamma, 0, sizeof(float) * c, st);
         cudaMemsetAsync(grad_beta, 0, sizeof(float) * c, st);
@@ -205,7 +232,7 @@ extern "C" int cb_bn_act_backward(long long n, int c, const float *x, const floa
     k_bn_colsums<1><<<bn_grid(n, lanes * 8), BN_THREADS, 2 * c * sizeof(float), st>>>(n, c, x, grad_y, y, bnbuf, relu, sums);
     k_bn_bwd_apply<<<bn_grid(n * (c / 4), BN_THREADS * 4), BN_THREADS, 5 * c * sizeof(float), st>>>(n, c, x, grad_y, y, gamma, bnbuf, sums,
                                                                                                  training, relu, grad_x,
-                                                                                                 grad_residual, grad_gamma, grad_beta);
+                                                                                                 grad_residual, grad_gamma, grad_beta, ticket);
     CB_COUNT(2);
     CB_CUDA_CHECK("cb_bn_act_backward");
     return CB_OK;

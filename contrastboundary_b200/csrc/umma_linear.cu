@@ -222,10 +222,13 @@ __device__ __forceinline__ void um_cp_async16(unsigned dst, const void *src, uns
 }
 
 template <int TRANS_B, int STAGES, int DEPTH>
-__global__ void __launch_bounds__(UM_THREADS_OF(STAGES), 1) k_umma_linear2(int n, int K, int N, int ncols, int ntiles, const float *__restrict__ A,
+__global__ void __launch_bounds__(UM_THREADS_OF(STAGES), 1) k_umma_linear2(int n, int K, int nb, int ncols, int ntiles, const float *__restrict__ A,
                                                                  int lda, const float *__restrict__ W, const float *__restrict__ bias,
-                                                                 float *__restrict__ Y, int ldy, int n0, int ldw)
+                                                                 float *__restrict__ Y, int ldy, int Ntot, int ldw)
 {
+    // blockIdx.y = column block of nb output columns (the last one may be narrower, still a multiple of 16)
+    const int n0 = blockIdx.y * nb;
+    const int N = min(nb, Ntot - n0);
     extern __shared__ __align__(1024) unsigned char um_smem[];
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
     constexpr int MMA_WARP = 4 + 4 * STAGES, NTHREADS = UM_THREADS_OF(STAGES);
@@ -493,15 +496,15 @@ int cb_umma_enabled() { return g_umma; }
 
 bool cb_umma_shape_ok(int n, int K, int N, const float *A, const float *Y, int lda, int ldy)
 {
-    // the whole of W (TF32 hi + lo) stays resident in shared memory next to the A ring: N * K <= ~33 K floats per column block;
-    // larger layers (c >= 256: levels 3-4, a few hundred rows) keep the mma.sync / cuBLAS path
+    // W (TF32 hi + lo, all of K) of one COLUMN BLOCK stays resident in shared memory next to the A ring; the blocks are
+    // gridDim.y of one launch.  Needs at least 16 columns per block: K <= 864.
     const int nchunk = (K + UM_KC - 1) / UM_KC;
-    const size_t w_bytes = (size_t)2 * nchunk * (N < 256 ? N : 256) * UM_KC * 4;
+    const size_t per_col = (size_t)2 * nchunk * UM_KC * 4;
     const size_t a_ring = um_ring_bytes(2);     // v3 falls back to the v2 ring when W does not fit beside its raw ring
     // 32 -> 32 layers: 12 MMAs of N = 32 per 32 KB tile are issue-latency bound (26.7 us vs 20.4 us for the mma.sync kernel at
     // n = 163840, tools/bench_linear.py); from 64 columns or 64 reduction elements on, the tcgen05 kernel is 1.1-1.6x faster
     return g_umma && n > 0 && K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && (K >= 64 || N >= 64) && lda % 4 == 0 && ldy % 4 == 0 &&
-           (((uintptr_t)A | (uintptr_t)Y) & 15) == 0 && w_bytes + a_ring + 2048 <= (size_t)227 * 1024;
+           (((uintptr_t)A | (uintptr_t)Y) & 15) == 0 && 16 * per_col + a_ring + 2048 <= (size_t)227 * 1024;
 }
 
 // Y (n x N) = A (n x K) . B^T (+ bias); trans_b = 0: W is (N x K) (forward), 1: W is (K x N) (dgrad).  N is processed in
@@ -545,26 +548,26 @@ int cb_umma_linear(int n, int K, int N, const float *A, int lda, const float *W,
         if (nb_max > 256) nb_max = 256;
         if (nb_max >= 16) {
             const int nblocks = (N + nb_max - 1) / nb_max;
-            int nb_even = ((N + nblocks - 1) / nblocks + 15) / 16 * 16;           // balanced column blocks
+            const int nb = ((N + nblocks - 1) / nblocks + 15) / 16 * 16;               // balanced column blocks
             const int ntiles = (n + 127) / 128;
-            for (int c0 = 0; c0 < N; c0 += nb_even) {
-                const int nb = N - c0 < nb_even ? N - c0 : nb_even;
-                int ncols = 32;
-                while (ncols < 2 * nb) ncols <<= 1;
-                const size_t smem = (size_t)2 * nchunk * nb * UM_KC * 4 + a_ring;
-                const int blocks = ntiles < sms ? ntiles : sms;
-                if (ver == 3) {
-                    if (trans_b)
-                        k_umma_linear2<1, UM3_STAGES, UM3_DEPTH><<<blocks, UM3_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
-                    else
-                        k_umma_linear2<0, UM3_STAGES, UM3_DEPTH><<<blocks, UM3_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
-                } else if (trans_b) {
-                    k_umma_linear2<1, UM2_STAGES, 0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
-                } else {
-                    k_umma_linear2<0, UM2_STAGES, 0><<<blocks, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, c0, ldw);
-                }
-                CB_COUNT(1);
+            int ncols = 32;
+            while (ncols < 2 * nb) ncols <<= 1;
+            const size_t smem = (size_t)2 * nchunk * nb * UM_KC * 4 + a_ring;
+            int bx = sms / nblocks;                                                    // persistent over row tiles, one wave
+            if (bx < 1) bx = 1;
+            if (bx > ntiles) bx = ntiles;
+            const dim3 grid(bx, nblocks);
+            if (ver == 3) {
+                if (trans_b)
+                    k_umma_linear2<1, UM3_STAGES, UM3_DEPTH><<<grid, UM3_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, N, ldw);
+                else
+                    k_umma_linear2<0, UM3_STAGES, UM3_DEPTH><<<grid, UM3_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, N, ldw);
+            } else if (trans_b) {
+                k_umma_linear2<1, UM2_STAGES, 0><<<grid, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, N, ldw);
+            } else {
+                k_umma_linear2<0, UM2_STAGES, 0><<<grid, UM2_THREADS, smem, st>>>(n, K, nb, ncols, ntiles, A, lda, W, bias, Y, ldy, N, ldw);
             }
+            CB_COUNT(1);
             return CB_OK;
         }
     }

@@ -160,6 +160,8 @@ class GraphTrainStep(TrainStep):
         self._eager_done = 0
         self._net_pool = None      # net[0] / net[1] replay back to back on one stream: they may share temporaries
         self.flat = None
+        self.pflat = None                   # device table of the one-launch optimiser step (see _pack_params)
+        self._opt_refs = None
         self._gparams = None
         self.launches_per_step = None
         self.graph_error = None
@@ -222,6 +224,59 @@ class GraphTrainStep(TrainStep):
         self._set_packed(was)
         return loss.detach(), flat
 
+    # -- one-launch optimiser ---------------------------------------------------------------------------
+    def _pack_params(self):
+        """Once, before the first capture: a device table (offsets into self.flat, parameter pointers, momentum-buffer
+        pointers) so that the optimiser step after a graph replay is ONE kernel (cb_sgd_momentum_step) instead of torch's 39
+        multi-tensor launches.  Nothing is re-allocated: parameters and torch.optim.SGD's momentum buffers stay where they
+        are (stream-mode steps, state_dict / checkpoints keep working on the same tensors)."""
+        if self.pflat is not None or self.device.type != "cuda":
+            return
+        g = self.opt.param_groups
+        ok = (len(g) == 1 and g[0].get("momentum", 0) > 0 and g[0].get("dampening", 0) == 0 and not g[0].get("nesterov", False)
+              and not g[0].get("maximize", False)
+              and all(p.dtype == torch.float32 and p.is_contiguous() for p in self._gparams)
+              and all(self.opt.state.get(p, {}).get("momentum_buffer") is not None for p in self._gparams))
+        if not ok:
+            self.pflat = False          # unusual optimiser configuration (or no step taken yet): keep torch's step
+            return
+        self._bind_opt_table()
+        if hasattr(self.opt, "register_load_state_dict_post_hook"):
+            self.opt.register_load_state_dict_post_hook(lambda opt: setattr(self, "_opt_refs", None))
+
+    def _bind_opt_table(self):
+        offs, o = [0], 0
+        for p in self._gparams:
+            o += p.numel()
+            offs.append(o)
+        mbs = [self.opt.state[p]["momentum_buffer"] for p in self._gparams]
+        assert all(m.is_contiguous() and m.dtype == torch.float32 for m in mbs)
+        self._opt_refs = (list(self._gparams), mbs, [p.data_ptr() for p in self._gparams])
+        self.pflat = (torch.tensor(offs, dtype=torch.int64, device=self.device),
+                      torch.tensor([p.data_ptr() for p in self._gparams], dtype=torch.int64, device=self.device),
+                      torch.tensor([m.data_ptr() for m in mbs], dtype=torch.int64, device=self.device), o)
+
+    def _opt_step(self):
+        """optimiser step on the packed gradient (self.flat holds this step's gradient, every p.grad is a view of it)"""
+        if not isinstance(self.pflat, tuple):
+            self.opt.step()
+            return
+        # someone may have re-bound the storage since (optimizer.load_state_dict replaces the momentum tensors, module.to() the
+        # parameters): rebuild the table instead of updating stale memory
+        refs = self._opt_refs
+        if (refs is None or refs[0][0].data_ptr() != refs[2][0] or refs[0][-1].data_ptr() != refs[2][-1]
+                or self.opt.state[refs[0][0]]["momentum_buffer"] is not refs[1][0]
+                or self.opt.state[refs[0][-1]]["momentum_buffer"] is not refs[1][-1]):
+            self._bind_opt_table()
+        import ctypes as C
+        from . import _lib as L
+        g = self.opt.param_groups[0]
+        off, pp, mp, total = self.pflat
+        rc = L.lib().cb_sgd_momentum_step(C.c_longlong(total), C.c_int(len(self._gparams)), L.ptr(off), L.ptr(pp), L.ptr(mp),
+                                          L.ptr(self.flat), C.c_float(float(g["lr"])), C.c_float(float(g["momentum"])),
+                                          C.c_float(float(g["weight_decay"])), C.c_int(0), L.stream())
+        L.check(rc, "cb_sgd_momentum_step")
+
     # -- capture ------------------------------------------------------------------------------------------
     def _static_inputs(self, batch, sig):
         n, b = sig[-1], len(sig)
@@ -240,6 +295,7 @@ class GraphTrainStep(TrainStep):
         if self.flat is None:
             assert self._gparams, "GraphTrainStep needs at least one stream-mode step before the capture"
             self.flat = torch.zeros(sum(p.numel() for p in self._gparams), dtype=torch.float32, device=dev)
+        self._pack_params()
         ohs = level_offsets_host(list(sig), self.cfg)
         slots = [_Slot(), _Slot()]
         for sl in slots:
@@ -283,7 +339,7 @@ class GraphTrainStep(TrainStep):
         for p in params:
             p.grad = None
         self._packed = False
-        self.launches_per_step = (lc1 - lc0) // 2 + (lc2 - lc1) // 2
+        self.launches_per_step = (lc1 - lc0) // 2 + (lc2 - lc1) // 2 + (1 if isinstance(self.pflat, tuple) else 0)
         return slots
 
     # -- replay -------------------------------------------------------------------------------------------
@@ -360,5 +416,5 @@ class GraphTrainStep(TrainStep):
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
-        self.opt.step()
+        self._opt_step()
         return cur.loss.clone()

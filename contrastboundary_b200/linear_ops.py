@@ -168,32 +168,35 @@ class BatchNorm1d(nn.BatchNorm1d):
 # fused BatchNorm (+ residual) (+ ReLU): libcbops' cb_bn_act_forward / cb_bn_act_backward (bn_ops.cu)
 # ------------------------------------------------------------------------------------------------
 FUSED_BN = True
+PERSISTENT_BN_ACC = True      # per-module self-cleaning statistics accumulator instead of a memset per BatchNorm call (bn_ops.cu)
 
 
 class _BnActFn(Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, momentum, eps, training, relu):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, momentum, eps, training, relu, acc=None):
         import ctypes as C
         x = x.contiguous()
         n, c = x.shape
         y = torch.empty_like(x)
         bnbuf = torch.empty(4 * c, dtype=torch.float32, device=x.device)
-        stats = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        # acc: the module's persistent, self-cleaning accumulator (2c doubles + ticket; zero between uses) -> no memset
+        persistent = acc is not None
+        stats = acc if persistent else torch.empty(2 * c, dtype=torch.float64, device=x.device)
         res = residual.contiguous() if residual is not None else None
         rc = L.lib().cb_bn_act_forward(C.c_longlong(n), C.c_int(c), L.ptr(x), L.ptr(res), L.ptr(gamma), L.ptr(beta),
                                        L.ptr(running_mean), L.ptr(running_var), C.c_float(momentum), C.c_float(eps),
-                                       C.c_int(1 if training else 0), C.c_int(1 if relu else 0), L.ptr(y), L.ptr(bnbuf),
-                                       L.ptr(stats), L.stream())
+                                       C.c_int((1 if training else 0) | (2 if persistent else 0)), C.c_int(1 if relu else 0),
+                                       L.ptr(y), L.ptr(bnbuf), L.ptr(stats), L.stream())
         L.check(rc, "cb_bn_act_forward")
         ctx.save_for_backward(x, y, gamma, bnbuf)
-        ctx.cfg = (bool(training), bool(relu), residual is not None, stats)
+        ctx.cfg = (bool(training), bool(relu), residual is not None, stats, persistent)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         import ctypes as C
         x, y, gamma, bnbuf = ctx.saved_tensors
-        training, relu, has_res, stats = ctx.cfg
+        training, relu, has_res, stats, persistent = ctx.cfg
         n, c = x.shape
         gy = gy.contiguous()
         gx = torch.empty_like(x)
@@ -201,10 +204,10 @@ class _BnActFn(Function):
         gg = torch.empty(c, dtype=torch.float32, device=x.device)
         gb = torch.empty(c, dtype=torch.float32, device=x.device)
         rc = L.lib().cb_bn_act_backward(C.c_longlong(n), C.c_int(c), L.ptr(x), L.ptr(y), L.ptr(gamma), L.ptr(bnbuf),
-                                        C.c_int(1 if training else 0), C.c_int(1 if relu else 0), L.ptr(gy), L.ptr(gx),
-                                        L.ptr(gres), L.ptr(gg), L.ptr(gb), L.ptr(stats), L.stream())
+                                        C.c_int((1 if training else 0) | (2 if persistent else 0)), C.c_int(1 if relu else 0),
+                                        L.ptr(gy), L.ptr(gx), L.ptr(gres), L.ptr(gg), L.ptr(gb), L.ptr(stats), L.stream())
         L.check(rc, "cb_bn_act_backward")
-        return gx, gres, gg, gb, None, None, None, None, None, None
+        return gx, gres, gg, gb, None, None, None, None, None, None, None
 
 
 def bn_act(bn, x, residual=None, relu=True):
@@ -215,8 +218,13 @@ def bn_act(bn, x, residual=None, relu=True):
             and not isinstance(bn, nn.SyncBatchNorm)):
         if bn.training:
             bump_bn_counter(bn)
+        acc = None
+        if PERSISTENT_BN_ACC:
+            acc = bn.__dict__.get("_cb_acc")           # plain attribute: not a registered buffer, not in the state_dict
+            if acc is None or acc.device != x.device:
+                acc = bn.__dict__["_cb_acc"] = torch.zeros(2 * x.shape[1] + 2, dtype=torch.float64, device=x.device)
         return _BnActFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum),
-                              float(bn.eps), bn.training, relu)
+                              float(bn.eps), bn.training, relu, acc)
     y = bn(x)
     if residual is not None:
         y = y + residual

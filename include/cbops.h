@@ -292,7 +292,10 @@ int cb_linear_wgrad(int n, int ci, int co, const float *X, const float *G, float
  * forward: y = act((x - mean) * invstd * gamma + beta [+ residual]); training: batch statistics (biased variance), running
  * statistics updated with the unbiased one (nn.BatchNorm1d semantics); bnbuf (4c floats: scale, shift, mean, invstd) and
  * stats (2c doubles, scratch) are caller-allocated; bnbuf is kept for the backward.
- * backward: grad_x, grad_residual (optional, = grad_y masked by the ReLU), grad_gamma, grad_beta; sums: 2c doubles scratch. */
+ * backward: grad_x, grad_residual (optional, = grad_y masked by the ReLU), grad_gamma, grad_beta; sums: 2c doubles scratch.
+ * training: bit 0 = batch statistics; bit 1 = stats / sums is a PERSISTENT accumulator of 2c + 1 doubles (the last one holds
+ * an int ticket) that is all-zero on entry and left all-zero on exit (the last block of the apply kernel clears it): no
+ * memset is issued.  Without bit 1 the buffer is plain scratch and is cleared by a cudaMemsetAsync first. */
 int cb_bn_act_forward(long long n, int c, const float *x, const float *residual, const float *gamma, const float *beta,
                       float *running_mean, float *running_var, float momentum, float eps, int training, int relu, float *y,
                       float *bnbuf, double *stats, void *stream);
@@ -407,6 +410,15 @@ void aggregation_forward_cuda_launcher(int n, int nsample, int c, int w_c, const
 void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, const float *input, const float *position,
                                         const float *weight, const int *idx, const float *grad_output,
                                         float *grad_input, float *grad_position, float *grad_weight);
+
+/* ------------------------------------------------------------------------------------------------
+ * optimiser step, all tensors in one launch    replaces torch.optim.SGD(...).step() of pytorch/tool/train.py:154,324
+ * d = g + weight_decay * p;  m = first_step ? d : momentum * m + d;  p -= lr * m
+ * g: the packed gradient (total floats); off: ntensors + 1 prefix offsets into g (device, int64);
+ * pp / mp: device arrays of ntensors device pointers (parameter / momentum buffer of tensor t, off[t+1] - off[t] floats)
+ * ------------------------------------------------------------------------------------------------ */
+int cb_sgd_momentum_step(long long total, int ntensors, const long long *off, float *const *pp, float *const *mp,
+                         const float *g, float lr, float momentum, float weight_decay, int first_step, void *stream);
 
 #ifdef __cplusplus
 }

@@ -22,12 +22,12 @@ def test_graph_step_matches_stream_step():
     devb = [engine.to_device(h, dev) for h in host]
     gts = engine.GraphTrainStep(model.CBLConfig(), dev, eager_warmup=2, lr=0.01, momentum=0.9, weight_decay=1e-4, seed=3)
     snap = {}
-    opt_step = gts.opt.step
+    opt_step = gts._opt_step
 
-    def spy(*a, **k):       # the packed gradient exactly as the optimiser receives it
+    def spy(*a, **k):       # the packed gradient exactly as the optimiser step receives it
         snap["g"] = gts.flat.clone() if gts._packed else None
         return opt_step(*a, **k)
-    gts.opt.step = spy
+    gts._opt_step = spy
     rels, floors = [], []
     for s in range(8):
         # steps 0-1 eager, step 2 captures; steps 4-5 with look-ahead; step 6 feeds a pinned HOST batch
@@ -53,6 +53,38 @@ def test_graph_step_matches_stream_step():
     assert gts.graph_error is None, gts.graph_error
     assert gts.launches_per_step and gts.launches_per_step > 100
     assert all(sl.net is not None for sl in gts._sigs[tuple(host[0]["offset_host"])])
+
+
+def test_one_launch_sgd_step_matches_torch_sgd():
+    """cb_sgd_momentum_step (one kernel for all tensors, through a device table of parameter / momentum pointers and the packed
+    gradient) against torch.optim.SGD, the reference's optimiser (pytorch/tool/train.py:154), over several steps including
+    the first (momentum buffer = d) and a learning-rate drop."""
+    import ctypes as C
+    from contrastboundary_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(1)
+    sizes = [7, 1, 300_001, 32 * 32, 5, 96, 1_000_003, 2]
+    refs = [torch.nn.Parameter(torch.randn(n, device="cuda", generator=g)) for n in sizes]
+    opt = torch.optim.SGD(refs, lr=0.5, momentum=0.9, weight_decay=1e-4)
+    ps = [r.detach().clone() for r in refs]
+    ms = [torch.empty_like(p) for p in ps]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    off = torch.tensor(offs, dtype=torch.int64, device="cuda")
+    pp = torch.tensor([p.data_ptr() for p in ps], dtype=torch.int64, device="cuda")
+    mp = torch.tensor([m.data_ptr() for m in ms], dtype=torch.int64, device="cuda")
+    for step in range(4):
+        flat = torch.randn(int(offs[-1]), device="cuda", generator=g)
+        for r, a, b in zip(refs, offs[:-1], offs[1:]):
+            r.grad = flat[a:b].clone()
+        opt.step()
+        lr = opt.param_groups[0]["lr"]              # the rate torch just used
+        if step == 1:
+            opt.param_groups[0]["lr"] = 0.05        # a MultiStepLR drop before step 2
+        rc = L.lib().cb_sgd_momentum_step(C.c_longlong(int(offs[-1])), C.c_int(len(sizes)), L.ptr(off), L.ptr(pp), L.ptr(mp), L.ptr(flat),
+                                          C.c_float(lr), C.c_float(0.9), C.c_float(1e-4), C.c_int(1 if step == 0 else 0), L.stream())
+        L.check(rc, "cb_sgd_momentum_step")
+        for r, p, m in zip(refs, ps, ms):
+            torch.testing.assert_close(p, r.data, rtol=2e-6, atol=2e-6)
+            torch.testing.assert_close(m, opt.state[r]["momentum_buffer"], rtol=2e-6, atol=2e-6)
 
 
 def test_forked_weight_gradients_match_serial_backward():

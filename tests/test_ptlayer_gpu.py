@@ -203,3 +203,54 @@ def test_fused_bn_act(n, c, training, residual, relu):
         assert torch.equal(b[2], a[2])
     assert rel_err(b[3], a[3]) < 2e-4 and rel_err(b[4], a[4]) < 2e-4
     assert rel_err(b[5], a[5]) < 1e-5 and rel_err(b[6], a[6]) < 1e-5
+
+
+@pytest.mark.parametrize("n,c", [(40960, 64), (300, 512), (5, 32)])
+def test_fused_bn_act_self_cleaning_accumulator(n, c):
+    """The module's persistent statistics accumulator (bn_ops.cu: the last block of the apply kernel zeroes it) must be all-zero
+    after every forward and every backward, so that repeated calls — eager or as CUDA-graph replays — give what the
+    memset-per-call path gives."""
+    from contrastboundary_b200 import linear_ops
+    torch.manual_seed(n)
+    x0 = torch.randn(n, c, device="cuda") * 2 + 1
+    g = torch.randn(n, c, device="cuda")
+    outs = {}
+    for persistent in (False, True):
+        linear_ops.PERSISTENT_BN_ACC = persistent
+        try:
+            bn = linear_ops.BatchNorm1d(c).cuda().train()
+            runs = []
+            for it in range(3):
+                x = x0.clone().requires_grad_(True)
+                y = linear_ops.bn_act(bn, x, relu=True)
+                if persistent:
+                    assert float(bn.__dict__["_cb_acc"].abs().max()) == 0.0 and int(bn.__dict__["_cb_acc"][2 * c:].view(torch.int32)[0]) == 0
+                y.backward(g)
+                if persistent:
+                    assert float(bn.__dict__["_cb_acc"].abs().max()) == 0.0
+                runs.append((y.detach().clone(), x.grad.clone(), bn.weight.grad.clone()))
+                bn.weight.grad = None
+                bn.bias.grad = None
+            for r in runs[1:]:
+                assert rel_err(r[0], runs[0][0]) < 1e-6 and rel_err(r[1], runs[0][1]) < 1e-5 and rel_err(r[2], runs[0][2]) < 1e-5
+            outs[persistent] = runs[0]
+        finally:
+            linear_ops.PERSISTENT_BN_ACC = True
+    assert rel_err(outs[True][0], outs[False][0]) < 1e-6 and rel_err(outs[True][1], outs[False][1]) < 1e-5
+    # the same through a CUDA graph: capture once, replay three times
+    bn = linear_ops.BatchNorm1d(c).cuda().train()
+    xs = x0.clone().requires_grad_(True)
+    linear_ops.bn_act(bn, xs, relu=True).backward(g)          # warm-up outside the capture (allocates the accumulator)
+    xs.grad = None
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(gr):
+            ys = linear_ops.bn_act(bn, xs, relu=True)
+            ys.backward(g)
+    for _ in range(3):
+        gr.replay()
+    torch.cuda.synchronize()
+    assert rel_err(ys, outs[False][0]) < 1e-6 and rel_err(xs.grad, outs[False][1]) < 1e-5
+    assert float(bn.__dict__["_cb_acc"].abs().max()) == 0.0

@@ -13,7 +13,9 @@ sys.path.insert(0, ROOT)
 from contrastboundary_b200 import _lib as L  # noqa: E402
 
 SHAPES = [(163840, 32, 32), (163840, 32, 96), (40960, 64, 64), (40960, 64, 192), (40960, 32, 64), (10240, 128, 128), (10240, 128, 384),
-          (10240, 64, 128), (163840, 32, 64), (1310720, 32, 8 * 4), (655360, 64, 8 * 8)]
+          (10240, 64, 128), (163840, 32, 64), (1310720, 32, 8 * 4), (655360, 64, 8 * 8),
+          # the deep levels (n = 2560 / 640 rows): cuBLAS territory so far (linear_ops.MIN_ROWS)
+          (2560, 256, 256), (2560, 256, 768), (2560, 128, 256), (640, 512, 512), (640, 512, 1536), (640, 256, 512), (2560, 512, 256)]
 
 
 def timed(fn, flush, iters=10):
@@ -52,9 +54,12 @@ def main():
                 res.append(timed(lambda: L.call(call, *args, L.stream()), flush))
         lib.cb_linear_set_umma(C.c_int(1))
         lib.cb_linear_set_umma_version(C.c_int(3))
+        t_fwd = timed(lambda: torch.nn.functional.linear(x, w, b), flush)
+        t_dg = timed(lambda: g.mm(w), flush)
         fr = [by / t / 1e3 / peak for t in res]
         print("%7d %5d %5d | %9.1f (%.2f) %8.1f (%.2f) %8.1f (%.2f) | %9.1f (%.2f) %8.1f (%.2f) %8.1f (%.2f)"
-              % (n, ci, co, res[0], fr[0], res[1], fr[1], res[2], fr[2], res[3], fr[3], res[4], fr[4], res[5], fr[5]))
+              % (n, ci, co, res[0], fr[0], res[1], fr[1], res[2], fr[2], res[3], fr[3], res[4], fr[4], res[5], fr[5])
+              + "   | cuBLAS fwd %6.1f dgrad %6.1f" % (t_fwd, t_dg))
 
 
 if __name__ == "__main__":
