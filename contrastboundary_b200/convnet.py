@@ -345,7 +345,8 @@ class ConvNetLoss(nn.Module):
 
     def forward(self, logits, labels, stage_list):
         cfg = self.cfg
-        losses = [F.cross_entropy(logits, labels)]                              # calc_loss 'xen', mean over points
+        from .model import cross_entropy
+        losses = [cross_entropy(logits, labels)]                                # calc_loss 'xen', mean over points
         if cfg.contrast:
             inputs, geo = stage_list["inputs"], stage_list["geometry"]
             t = cfg.contrast_temperature if cfg.contrast_temperature is not None else 1.0

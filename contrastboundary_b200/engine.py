@@ -276,6 +276,7 @@ class GraphTrainStep(TrainStep):
                                           L.ptr(self.flat), C.c_float(float(g["lr"])), C.c_float(float(g["momentum"])),
                                           C.c_float(float(g["weight_decay"])), C.c_int(0), L.stream())
         L.check(rc, "cb_sgd_momentum_step")
+        self.opt._opt_called = True         # what lr_scheduler.step() looks at to tell that the optimiser has stepped
 
     # -- capture ------------------------------------------------------------------------------------------
     def _static_inputs(self, batch, sig):

@@ -594,6 +594,45 @@ class ContrastHead(nn.Module):
         return [self.stage_loss(i, levels, stage_list[n][i][self.ftype], target) for n, i in self.stages]
 
 
+class _CrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss(ignore_index)(logits, target), mean over the counted rows: cb_cross_entropy_forward / _backward"""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        import ctypes as C
+        from . import _lib as L
+        logits = logits.contiguous()
+        target = target.contiguous()
+        n, c = logits.shape
+        acc = torch.empty(3, dtype=torch.float64, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        L.check(L.lib().cb_cross_entropy_forward(C.c_int(n), C.c_int(c), L.ptr(logits), L.ptr(target), C.c_longlong(int(ignore_index)),
+                                                 L.ptr(acc), L.ptr(loss), L.stream()), "cb_cross_entropy_forward")
+        ctx.save_for_backward(logits, target, acc)
+        ctx.ignore_index = int(ignore_index)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from . import _lib as L
+        logits, target, acc = ctx.saved_tensors
+        n, c = logits.shape
+        d = torch.empty_like(logits)
+        g = g.contiguous().to(torch.float32)
+        L.check(L.lib().cb_cross_entropy_backward(C.c_int(n), C.c_int(c), L.ptr(logits), L.ptr(target), C.c_longlong(ctx.ignore_index),
+                                                  L.ptr(acc), L.ptr(g), L.ptr(d), L.stream()), "cb_cross_entropy_backward")
+        return d, None, None
+
+
+def cross_entropy(logits, target, ignore_index=-100):
+    """the reference's criterion (pointtransformer_seg.py:19) — one kernel per direction on CUDA float32 (n, c) logits"""
+    if (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and target.dtype == torch.int64 and target.dim() == 1
+            and 0 < logits.shape[1] <= 1024 and logits.shape[0] > 0 and logits.shape[0] < 2 ** 31):
+        return _CrossEntropyFn.apply(logits, target, ignore_index)
+    return F.cross_entropy(logits, target, ignore_index=ignore_index)
+
+
 class Loss(nn.Module):
     """pointtransformer_seg.py:15-25: `Loss(config).forward(output, target, stage_list)` -> stacked
     [cross-entropy, cbl_0 .. cbl_4]; `config` = the reference's config node or a CBLConfig."""
@@ -606,7 +645,7 @@ class Loss(nn.Module):
         self.xen = nn.CrossEntropyLoss(ignore_index=cfg.ignore_label)
 
     def forward(self, output, target, stage_list):
-        loss_list = [self.xen(output, target)]
+        loss_list = [cross_entropy(output, target, self.xen.ignore_index)]
         if self.contrast_head is not None:
             loss_list += self.contrast_head(output, target, stage_list)
         return torch.stack(loss_list)

@@ -412,6 +412,17 @@ void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, cons
                                         float *grad_input, float *grad_position, float *grad_weight);
 
 /* ------------------------------------------------------------------------------------------------
+ * segmentation cross-entropy      replaces nn.CrossEntropyLoss(ignore_index)(output, target) of
+ *                                 pytorch/model/pointtransformer_seg.py:15-25 (mean over the rows whose target != ignore_index)
+ * logits (n, c) float32 row-major, target (n) int64; acc: 3 doubles of scratch kept for the backward (sum, count, ticket);
+ * loss: 1 float.  backward: grad_logits = (softmax - onehot) * grad_loss[0] / count, zero rows for ignored targets.
+ * ------------------------------------------------------------------------------------------------ */
+int cb_cross_entropy_forward(int n, int c, const float *logits, const long long *target, long long ignore_index, double *acc,
+                             float *loss, void *stream);
+int cb_cross_entropy_backward(int n, int c, const float *logits, const long long *target, long long ignore_index,
+                              const double *acc, const float *grad_loss, float *grad_logits, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * optimiser step, all tensors in one launch    replaces torch.optim.SGD(...).step() of pytorch/tool/train.py:154,324
  * d = g + weight_decay * p;  m = first_step ? d : momentum * m + d;  p -= lr * m
  * g: the packed gradient (total floats); off: ntensors + 1 prefix offsets into g (device, int64);

@@ -154,3 +154,22 @@ def test_benchmark_config_stream_mode_matches_reference(golden_dir):
     loss.sum().backward()
     torch.cuda.synchronize()
     check_against_golden(gts.model, out, loss, stages, g, 1e-4)
+
+
+@pytest.mark.parametrize("n,c", [(163840, 13), (1000, 13), (257, 40), (1, 5)])
+def test_cross_entropy_kernel_matches_torch(n, c):
+    """model.cross_entropy (cb_cross_entropy_forward / _backward) against nn.CrossEntropyLoss(ignore_index) — the reference's
+    criterion (pointtransformer_seg.py:19) — including ignored rows and the upstream gradient of loss.sum()."""
+    from contrastboundary_b200 import model as M
+    g = torch.Generator(device="cuda").manual_seed(n + c)
+    logits = (torch.randn(n, c, device="cuda", generator=g) * 3).requires_grad_(True)
+    target = torch.randint(0, c, (n,), device="cuda", generator=g)
+    if n > 10:
+        target[torch.rand(n, device="cuda", generator=g) < 0.1] = 255
+    ref_in = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, target, ignore_index=255)
+    (ref * 1.7).backward()
+    got = M.cross_entropy(logits, target, 255)
+    (got * 1.7).backward()
+    torch.testing.assert_close(got, ref, rtol=2e-6, atol=1e-7)
+    torch.testing.assert_close(logits.grad, ref_in.grad, rtol=1e-5, atol=1e-9)

@@ -47,7 +47,7 @@ def main():
     for e in ev:
         if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e:
             st = e.get("args", {}).get("stream", -1)
-            nm = e["name"].split("(")[0].replace("void ", "")[:60]
+            nm = e["name"].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0].replace("void ", "").replace("at::native::", "")[:90]
             per_stream[st][nm][0] += e["dur"]
             per_stream[st][nm][1] += 1
             span[st][0] = min(span[st][0], e["ts"])
