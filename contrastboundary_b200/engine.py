@@ -8,7 +8,9 @@ import torch
 from .model import CBLConfig, Loss, PointTransformerSeg, build_geometry
 
 
-WGRAD_FORK = True      # weight gradients of the linear layers on a side stream during the backward (linear_ops.wgrad_fork)
+import os as _os
+WGRAD_FORK = _os.environ.get("CB_WGRAD_FORK", "1") != "0"   # weight gradients of the linear layers on a side stream during the
+                                                            # backward (linear_ops.wgrad_fork); CB_WGRAD_FORK=0 keeps them in line
 
 
 def _backward(loss):
