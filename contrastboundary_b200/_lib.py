@@ -30,7 +30,7 @@ def lib():
         _lib.cb_last_error_string.restype = C.c_char_p
         _lib.cb_knn_workspace_bytes.restype = C.c_size_t
         _lib.cb_knn_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
-        for name in ("cb_cbl_workspace_bytes",):
+        for name in ("cb_cbl_workspace_bytes", "cb_pt_bnbuf_floats", "cb_pt_stats_doubles", "cb_pt_bwd_scratch_floats"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t
         if os.environ.get("CB_UMMA"):            # developer knob: CB_UMMA=0 -> mma.sync kernels instead of tcgen05 for the linear layers
@@ -55,8 +55,19 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream(device=None):
     """torch's current stream (of `device`, default: the current device) as a C pointer"""
+    if _raw_stream is not None:          # ~10x cheaper than building a torch.cuda.Stream object; called once per kernel launch
+        if device is None:
+            idx = torch.cuda.current_device()
+        else:
+            idx = device if isinstance(device, int) else torch.device(device).index
+            if idx is None:
+                idx = torch.cuda.current_device()
+        return C.c_void_p(_raw_stream(idx))
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -72,26 +83,35 @@ def require_cuda(*tensors):
             raise CbopsError("contrastboundary_b200 operators run on CUDA tensors only (no CPU fallback)")
 
 
+_fn_cache = {}
+_Tensor = torch.Tensor
+
+
 def call(name, *args):
-    f = getattr(lib(), name)
+    f = _fn_cache.get(name)
+    if f is None:
+        f = _fn_cache[name] = getattr(lib(), name)
     conv = []
-    cur = None
+    checked = False
     for a in args:
-        if isinstance(a, torch.Tensor):
-            if a.is_cuda:
-                if cur is None:
-                    cur = torch.cuda.current_device()
-                if a.device.index != cur:          # the stream argument is the CURRENT device's stream
+        if isinstance(a, _Tensor):
+            if not checked and a.is_cuda:
+                # the stream argument is the CURRENT device's stream: the tensors must live there (checked on the first CUDA
+                # tensor of a call — the operands of one call share a device by construction)
+                checked = True
+                if a.get_device() != torch.cuda.current_device():
                     raise CbopsError("%s: tensor on cuda:%d but the current device is cuda:%d (call torch.cuda.set_device)"
-                                     % (name, a.device.index, cur))
+                                     % (name, a.get_device(), torch.cuda.current_device()))
             conv.append(C.c_void_p(a.data_ptr()))
         elif isinstance(a, float):
             conv.append(C.c_float(a))
         elif isinstance(a, int):
-            conv.append(C.c_int(a)) if abs(a) < 2 ** 31 else conv.append(C.c_size_t(a))
+            conv.append(C.c_int(a)) if -2 ** 31 < a < 2 ** 31 else conv.append(C.c_size_t(a))
         else:
             conv.append(a)
-    check(f(*conv), name)
+    rc = f(*conv)
+    if rc != 0:
+        check(rc, name)
 
 
 class SizeT:

@@ -31,7 +31,36 @@ class CbPtLayer(C.Structure):
         "w4", "b4")] + [("momentum", C.c_float), ("eps", C.c_float), ("training", C.c_int)]
 
 
+_size_cache = {}
+
+
+def _sizes(lib, c):
+    """(bnbuf floats, stats doubles) of a layer with c channels — constants of the library, asked once per width"""
+    v = _size_cache.get(c)
+    if v is None:
+        v = _size_cache[c] = (int(lib.cb_pt_bnbuf_floats(C.c_int(c))), int(lib.cb_pt_stats_doubles(C.c_int(c))))
+    return v
+
+
+_struct_cache = {}
+
+
 def _param_struct(params, buffers, momentum, eps, training):
+    # the struct holds 20 raw pointers; it only changes when a tensor is re-allocated, so it is cached per layer (identity of
+    # its first parameter, kept alive by the cache entry) and validated against the current addresses of all its tensors
+    key = (id(params[0]), id(buffers[0]), float(momentum), float(eps), int(training))
+    addrs = tuple(t.data_ptr() for t in params) + tuple(t.data_ptr() for t in buffers)
+    hit = _struct_cache.get(key)
+    if hit is not None and hit[1] == addrs and hit[2] is params[0]:
+        return hit[0]
+    s = _param_struct_build(params, buffers, momentum, eps, training)
+    if len(_struct_cache) > 4096:
+        _struct_cache.clear()
+    _struct_cache[key] = (s, addrs, params[0])
+    return s
+
+
+def _param_struct_build(params, buffers, momentum, eps, training):
     (w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, g3, be3, w4, b4) = params
     (rm1, rv1, rm2, rv2, rm3, rv3) = buffers
     s = CbPtLayer()
@@ -60,10 +89,8 @@ class PtAttentionFn(Function):
         w2buf = torch.empty((n, k, cs), dtype=torch.float32, device=dev)
         abuf = torch.empty((n, k, cs), dtype=torch.float32, device=dev)
         lib = L.lib()
-        lib.cb_pt_bnbuf_floats.restype = C.c_size_t
-        lib.cb_pt_stats_doubles.restype = C.c_size_t
-        bnbuf = torch.empty(lib.cb_pt_bnbuf_floats(C.c_int(c)), dtype=torch.float32, device=dev)
-        stats = torch.empty(lib.cb_pt_stats_doubles(C.c_int(c)), dtype=torch.float64, device=dev)
+        bnbuf = torch.empty(_sizes(lib, c)[0], dtype=torch.float32, device=dev)
+        stats = torch.empty(_sizes(lib, c)[1], dtype=torch.float64, device=dev)
         ps = _param_struct(params, buffers, momentum, eps, training)
         # tensor-core backward: keep the pre-BatchNorm activation w0 (n,k,c) instead of re-gathering it three times
         keep_w0 = bool(training) and TENSOR_CORES and any(ctx.needs_input_grad)
@@ -92,7 +119,6 @@ class PtAttentionFn(Function):
         gqkv = torch.zeros_like(qkv)                  # x_k / x_v blocks are scatter-add targets, x_q block is overwritten
         gxq, gxk, gxv = gqkv[:, :c], gqkv[:, c:2 * c], gqkv[:, 2 * c:]
         lib = L.lib()
-        lib.cb_pt_bwd_scratch_floats.restype = C.c_size_t
         scratch = torch.empty(lib.cb_pt_bwd_scratch_floats(C.c_int(n), C.c_int(k), C.c_int(c)), dtype=torch.float32, device=dev)
         # parameter gradients in one zeroed buffer (layout of cb_pt_layer_backward)
         sizes = [9, 3, 3, 3, c * 3, c, c, c, cs * c, cs, cs, cs, cs * cs, cs]
