@@ -387,6 +387,8 @@ class ConvNetTrainStep:
         self.pcfg = PyramidConfig(self.cfg.num_layers, self.cfg.first_subsampling_dl, self.cfg.density_parameter,
                                   list(self.cfg.neighborhood_limits))
         self.model.train()
+        self._side = None
+        self._pending = None
 
     def build_inputs(self, batch):
         """batch: dict(points (n,3), colors (n,3), point_labels (n) int64, lens (b) int32) of device tensors"""
@@ -394,8 +396,67 @@ class ConvNetTrainStep:
         feats = input_features(batch["points"], batch["colors"], self.cfg.in_features_dim)
         return segmentation_inputs_radius(batch["points"], feats, batch["point_labels"], batch["lens"], self.pcfg)
 
-    def step(self, batch, inputs=None, update=True):
-        inputs = inputs if inputs is not None else self.build_inputs(batch)
+    # ------------------------------------------------------------------------------------------
+    # Pyramid look-ahead.  The reference builds the neighbour pyramid of the NEXT batches on tf.data CPU workers while the
+    # GPU trains on the current one (tensorflow/datasets/base.py:75-118,767-842).  Here the pyramid of batch t+1 is built by
+    # a worker thread on a side stream during step t: its host round trips (data-dependent sizes, the unordered_map order
+    # replay) release the GIL while they wait, so they overlap with the main thread issuing the network's kernels.  Every
+    # batch's pyramid is still built exactly once.
+    # ------------------------------------------------------------------------------------------
+    def prefetch_inputs(self, batch):
+        import threading
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        ev_in = torch.cuda.Event()
+        ev_in.record(main)                                   # the batch's H2D copies were enqueued on `main`
+        box = {}
+
+        def work():
+            try:
+                torch.cuda.set_device(self.device)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(ev_in)
+                    inputs = self.build_inputs(batch)
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                box["inputs"], box["ev"] = inputs, ev
+            except BaseException as e:                       # re-raised by the consumer
+                box["error"] = e
+        th = threading.Thread(target=work, name="cb-pyramid-prefetch", daemon=True)
+        th.start()
+        self._pending = (batch, th, box)
+
+    def drain_prefetch(self):
+        """wait for (and drop) a pyramid that was prefetched but never consumed"""
+        pend, self._pending = self._pending, None
+        if pend is not None:
+            pend[1].join()
+
+    def _take_inputs(self, batch):
+        pend, self._pending = self._pending, None
+        if pend is None or pend[0] is not batch:
+            if pend is not None:
+                pend[1].join()                               # a prefetch nobody asked for: let it finish, drop it
+            return self.build_inputs(batch)
+        _, th, box = pend
+        th.join()
+        if "error" in box:
+            raise box["error"]
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(box["ev"])
+        for v in box["inputs"].values():                     # allocated on the side stream, consumed on `main`
+            for t in (v if isinstance(v, (list, tuple)) else [v]):
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(main)
+        return box["inputs"]
+
+    def step(self, batch, inputs=None, update=True, next_batch=None):
+        """next_batch: optional batch whose pyramid is built on a worker thread / side stream during this step"""
+        if inputs is None:
+            inputs = self._take_inputs(batch)
+        if next_batch is not None:
+            self.prefetch_inputs(next_batch)
         self.opt.zero_grad(set_to_none=True)
         logits, stage_list = self.model(inputs)
         loss = self.criterion(logits, inputs["point_labels"], stage_list)

@@ -119,3 +119,44 @@ def test_train_step_learns(setup):
     losses = [ts2.step(batch, inputs).cpu().numpy() for _ in range(6)]
     assert np.isfinite(losses).all()
     assert losses[-1][0] < losses[0][0]                                     # cross entropy goes down on a repeated batch
+
+
+def test_pyramid_lookahead_matches_inline_build(setup):
+    """ConvNetTrainStep.step(batch, next_batch=...) builds the pyramid of the next batch on a worker thread / side stream
+    (the reference's tf.data workers, datasets/base.py:75-118): same pyramid, same losses as building it inside the step."""
+    convnet, ts, batch, inputs = setup
+    dev = torch.device("cuda", 0)
+    batches = [_batch([4000, 3500], 300 + i, dev) for i in range(3)]
+    # the prefetched pyramid is the inline pyramid
+    ts.prefetch_inputs(batches[1])
+    got = ts._take_inputs(batches[1])
+    ref = ts.build_inputs(batches[1])
+    torch.cuda.synchronize()
+    for key in ("points", "batches_len"):
+        for a, b in zip(got[key], ref[key]):
+            assert torch.equal(a, b), key
+    for key in ("neighbors", "pools", "upsamples"):
+        # rows are equal as SETS: the order of exactly equidistant neighbours inside a row depends on the atomic order of the
+        # grid build (two inline builds differ in the same way; the reference leaves that order to nanoflann)
+        for a, b in zip(got[key], ref[key]):
+            assert a.shape == b.shape and torch.equal(torch.sort(a, 1)[0], torch.sort(b, 1)[0]), key
+    assert torch.equal(got["features"], ref["features"]) and torch.equal(got["point_labels"], ref["point_labels"])
+    # a prefetch for another batch is dropped, not consumed
+    ts.prefetch_inputs(batches[2])
+    other = ts._take_inputs(batches[0])
+    assert torch.equal(other["points"][0], ts.build_inputs(batches[0])["points"][0]) and ts._pending is None
+    # training with and without the look-ahead: same loss trajectory (same kernels in the same order on the same data)
+    runs = {}
+    for look in (False, True):
+        t2 = convnet.ConvNetTrainStep(convnet.ConvNetConfig(), dev, seed=4)
+        out = []
+        for s in range(5):
+            out.append(t2.step(batches[s % 3], next_batch=batches[(s + 1) % 3] if look else None).cpu().numpy())
+        t2.drain_prefetch()
+        runs[look] = np.stack(out)
+    assert np.isfinite(runs[True]).all()
+    # the first steps agree closely; after that the float-atomic / tie-order noise of the two runs is amplified by the SGD
+    # trajectory itself (two runs WITHOUT the look-ahead drift apart the same way), so later steps are only loosely compared
+    print("with look-ahead:\n", runs[True], "\nwithout:\n", runs[False])
+    np.testing.assert_allclose(runs[True][:2], runs[False][:2], rtol=5e-3, atol=1e-4)
+    assert np.isfinite(runs[False]).all() and runs[True][-1][0] < runs[True][0][0] and runs[False][-1][0] < runs[False][0][0]
