@@ -37,6 +37,8 @@ def lib():
             _lib.cb_linear_set_umma(C.c_int(int(os.environ["CB_UMMA"])))
         if os.environ.get("CB_GRID_FUSED"):      # developer knob: 0 -> the multi-kernel grid build
             _lib.cb_grid_set_fused(C.c_int(int(os.environ["CB_GRID_FUSED"])))
+        if os.environ.get("CB_PDL"):             # developer knob: 0 -> no programmatic dependent launches
+            _lib.cb_set_pdl(C.c_int(int(os.environ["CB_PDL"])))
         if os.environ.get("CB_FPS_MODE"):        # developer knob (profilers that cannot launch cluster kernels): see cbops.h
             _lib.cb_fps_set_mode(C.c_int(int(os.environ["CB_FPS_MODE"])), C.c_int(8192))
     return _lib

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_colsums(long long n, int C, c
                                                            double *__restrict__ sums)
 {
     extern __shared__ float bs_sm[];            // [2][C]
+    cb_pdl_wait();
     for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) bs_sm[i] = 0.f;
     __syncthreads();
     // thread -> 4 consecutive columns (C % 4 == 0), row lanes = BN_THREADS / (C / 4) (>= 1 for C <= 1024)
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_apply(long long n, int C, con
                                                          int *ticket)
 {
     extern __shared__ float ba_sm[];            // [2][C]: scale, shift
+    cb_pdl_wait();
     const double count = (double)n;
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
         float mean, var;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_bwd_apply(long long n, int C,
                                                              float *__restrict__ dgamma, float *__restrict__ dbeta, int *ticket)
 {
     extern __shared__ float bb_sm[];            // [5][C]: kk, ma, mb, mean, invstd
+    cb_pdl_wait();
     const double count = (double)n;
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
         const double sa = sums[c], sb = sums[C + c];
@@ -201,11 +204,11 @@ extern "C" int cb_bn_act_forward(long long n, int c, const float *x, const float
     if (training) {
         if (!persistent) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c, st);
         const int lanes = BN_THREADS / (c / 4) > 0 ? BN_THREADS / (c / 4) : 1;
-        k_bn_colsums<0><<<bn_grid(n, lanes * 8), BN_THREADS, 2 * c * sizeof(float), st>>>(n, c, x, nullptr, nullptr, nullptr, 0, stats);
+        cb_launch_pdl(k_bn_colsums<0>, dim3(bn_grid(n, lanes * 8)), dim3(BN_THREADS), 2 * c * sizeof(float), st, n, c, x, nullptr, nullptr,
+                      nullptr, 0, stats);
     }
-    k_bn_apply<<<bn_grid(n * (c / 4), BN_THREADS * 4), BN_THREADS, 2 * c * sizeof(float), st>>>(n, c, x, residual, stats, gamma, beta,
-                                                                                             running_mean, running_var, momentum,
-                                                                                             eps, training, relu, y, bnbuf, ticket);
+    cb_launch_pdl(k_bn_apply, dim3(bn_grid(n * (c / 4), BN_THREADS * 4)), dim3(BN_THREADS), 2 * c * sizeof(float), st, n, c, x, residual,
+                  stats, gamma, beta, running_mean, running_var, momentum, eps, training, relu, y, bnbuf, ticket);
     CB_COUNT(training ? 2 : 1);
     CB_CUDA_CHECK("cb_bn_act_forward");
     return CB_OK;
@@ -229,10 +232,10 @@ extern "C" int cb_bn_act_backward(long long n, int c, const float *x, const floa
         return CB_OK;
     }
     const int lanes = BN_THREADS / (c / 4) > 0 ? BN_THREADS / (c / 4) : 1;
-    k_bn_colsums<1><<<bn_grid(n, lanes * 8), BN_THREADS, 2 * c * sizeof(float), st>>>(n, c, x, grad_y, y, bnbuf, relu, sums);
-    k_bn_bwd_apply<<<bn_grid(n * (c / 4), BN_THREADS * 4), BN_THREADS, 5 * c * sizeof(float), st>>>(n, c, x, grad_y, y, gamma, bnbuf, sums,
-                                                                                                 training, relu, grad_x,
-                                                                                                 grad_residual, grad_gamma, grad_beta, ticket);
+    cb_launch_pdl(k_bn_colsums<1>, dim3(bn_grid(n, lanes * 8)), dim3(BN_THREADS), 2 * c * sizeof(float), st, n, c, x, grad_y, y, bnbuf, relu,
+                  sums);
+    cb_launch_pdl(k_bn_bwd_apply, dim3(bn_grid(n * (c / 4), BN_THREADS * 4)), dim3(BN_THREADS), 5 * c * sizeof(float), st, n, c, x, grad_y, y,
+                  gamma, bnbuf, sums, training, relu, grad_x, grad_residual, grad_gamma, grad_beta, ticket);
     CB_COUNT(2);
     CB_CUDA_CHECK("cb_bn_act_backward");
     return CB_OK;

@@ -31,6 +31,33 @@ extern unsigned long long g_cb_launches;   // kernels launched by this library (
 
 static inline size_t cb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A step of this network is a chain of ~1 300 short kernels; between two dependent kernels
+// of a stream (or of a captured graph) the GPU idles ~2.5 us while the next grid is set up.  A kernel launched through
+// cb_launch_pdl may be SET UP while its predecessor still runs; its first statement, cb_pdl_wait(), blocks until every
+// grid it depends on has completed and flushed its memory, so the semantics are those of an ordinary in-order launch.
+// Only kernels that start with cb_pdl_wait() may be launched this way.  cb_set_pdl(0) / CB_PDL=0 = ordinary launches.
+// ---------------------------------------------------------------------------------------------
+extern int g_cb_pdl;
+__device__ __forceinline__ void cb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cb_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_cb_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Squared distance exactly as the reference's SASS computes it (nvcc -fmad=true on
 // (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f)):  t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)
 // (knnquery_cuda_kernel.cu:99, sampling_cuda_kernel.cu:54; order read off the reference's sm_100a SASS

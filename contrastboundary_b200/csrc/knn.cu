@@ -24,6 +24,12 @@ void cb_set_error(const char *fmt, ...)
 extern "C" const char *cb_last_error_string(void) { return g_err; }
 extern "C" int cb_version(void) { return 100; }
 unsigned long long g_cb_launches = 0;
+int g_cb_pdl = 1;          // programmatic dependent launch for the kernels that support it (common.cuh)
+extern "C" int cb_set_pdl(int on)
+{
+    if (on == 0 || on == 1) g_cb_pdl = on;
+    return g_cb_pdl;
+}
 extern "C" unsigned long long cb_launch_count(void) { return g_cb_launches; }
 
 // ---------------------------------------------------------------------------------------------

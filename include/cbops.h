@@ -411,6 +411,11 @@ void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, cons
                                         const float *weight, const int *idx, const float *grad_output,
                                         float *grad_input, float *grad_position, float *grad_weight);
 
+/* tuning knob: 1 (default) = kernels that support it are launched with programmatic stream serialization (their set-up
+ * overlaps the tail of the previous kernel; they wait for it with griddepcontrol.wait before touching memory); 0 = ordinary
+ * launches.  Returns the setting in force. */
+int cb_set_pdl(int on);
+
 /* ------------------------------------------------------------------------------------------------
  * segmentation cross-entropy      replaces nn.CrossEntropyLoss(ignore_index)(output, target) of
  *                                 pytorch/model/pointtransformer_seg.py:15-25 (mean over the rows whose target != ignore_index)
