@@ -13,10 +13,11 @@ WGRAD_FORK = _os.environ.get("CB_WGRAD_FORK", "1") != "0"   # weight gradients o
                                                             # backward (linear_ops.wgrad_fork); CB_WGRAD_FORK=0 keeps them in line
 
 
-def _backward(loss):
+def _backward(loss, fork=True):
     """loss.sum().backward() as the reference's iteration does it (pytorch/tool/train.py:322-324), with the weight-gradient
-    kernels of the linear layers forked to a side stream and joined before anyone reads the gradients."""
-    if WGRAD_FORK and loss.is_cuda:
+    kernels of the linear layers forked to a side stream and joined before anyone reads the gradients.  fork=False under
+    torch's DistributedDataParallel: its gradient hooks read every gradient the moment autograd hands it over."""
+    if WGRAD_FORK and fork and loss.is_cuda:
         from .linear_ops import wgrad_fork
         with wgrad_fork():
             loss.sum().backward()
@@ -85,7 +86,7 @@ class TrainStep:
             self.prefetch_geometry(next_batch)
         out, stages = self.net(batch, levels)
         loss = self.criterion(out, batch["point_labels"], stages)
-        _backward(loss)
+        _backward(loss, fork=self.net is self.model)
         if update:
             self.opt.step()
         return loss.detach()
