@@ -411,6 +411,11 @@ void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, cons
                                         const float *weight, const int *idx, const float *grad_output,
                                         float *grad_input, float *grad_position, float *grad_weight);
 
+/* developer hook (tools/debug_fps.py): copies the cycle / bucket counters of the cluster FPS kernel to out8 (touched buckets,
+ * iterations, cycles of warp 0: total / refresh / exchange, max buckets per warp-iteration, ...), clears them, and arms
+ * (enable = 1) or disarms (0) the counting. */
+int cb_debug_fps(int enable, unsigned long long *out8);
+
 /* tuning knob: 1 (default) = kernels that support it are launched with programmatic stream serialization (their set-up
  * overlaps the tail of the previous kernel; they wait for it with griddepcontrol.wait before touching memory); 0 = ordinary
  * launches.  Returns the setting in force. */
