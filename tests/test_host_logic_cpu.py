@@ -178,3 +178,29 @@ def test_reference_constructor_signatures():
     plain = {k: v for k, v in cfg_dict.items() if k not in ("contrast", "multi")}
     m2 = model.pointtransformer_seg_repro(c=6, k=13, config=plain)           # origin_4gpu.yaml: no heads, plain classifier
     assert m2.head is None and m2.cls is not None and model.Loss(plain).contrast_head is None
+
+
+def test_cpu_tensors_take_torch_paths_and_the_wgrad_fork_is_opt_in():
+    """Host logic around the CUDA-only kernels: on CPU tensors the drop-in wrappers fall through to torch (the KERNELS have no
+    CPU fallback, the nn.Module-level wrappers stay usable for state_dict / shape work), and the weight-gradient fork is off
+    unless engine._backward turns it on."""
+    import torch
+    from contrastboundary_b200 import linear_ops, model
+    assert linear_ops._fork["on"] is False and not linear_ops._fork["used"]
+    with linear_ops.wgrad_fork():
+        assert linear_ops._fork["on"] is True
+    assert linear_ops._fork["on"] is False
+    torch.manual_seed(0)
+    x = torch.randn(17, 8, requires_grad=True)
+    lin = linear_ops.Linear(8, 5)
+    ref = torch.nn.functional.linear(x, lin.weight, lin.bias)
+    got = lin(x)
+    assert torch.equal(got, ref)
+    got.sum().backward()
+    assert lin.weight.grad is not None and x.grad is not None
+    logits = torch.randn(11, 13, requires_grad=True)
+    target = torch.randint(0, 13, (11,))
+    target[3] = 255
+    a = model.cross_entropy(logits, target, 255)
+    b = torch.nn.functional.cross_entropy(logits, target, ignore_index=255)
+    assert torch.equal(a, b)
