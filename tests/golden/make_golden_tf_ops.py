@@ -1,0 +1,74 @@
+"""Golden vectors for the TF tree's ConvNet operators, produced by EXECUTING the reference's own source
+(/root/reference/tensorflow/models/local_aggregation_operators.py + basic_operators.py + utils.py, unmodified) on the NumPy
+stand-in for the TF-1 API in tf_numpy_shim.py (TensorFlow is not installable in the build container).
+
+    python tests/golden/make_golden_tf_ops.py        -> tests/golden/tf_ops_ref.npz
+
+This pins row a13 (AdaptiveWeight, adapt.yaml) against reference code that actually ran, instead of restatements only:
+the oracle restatements (oracle/tf_model.py, oracle/tf_convnet_np.py) are checked against these vectors on the CPU
+(tests/test_convnet_cpu.py) and the CUDA kernels against the same vectors on the GPU (tests/test_convnet_gpu.py)."""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("CB_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def load_reference_models():
+    """the reference's tensorflow/models/*.py as package `refmodels`, with `tensorflow` := the NumPy shim; the package's own
+    __init__ (which pulls in the whole model zoo) is not executed"""
+    import tf_numpy_shim as shim
+    sys.modules["tensorflow"] = shim
+    pkg = types.ModuleType("refmodels")
+    pkg.__path__ = [os.path.join(REF, "tensorflow", "models")]
+    sys.modules["refmodels"] = pkg
+    lao = importlib.import_module("refmodels.local_aggregation_operators")
+    return shim, lao
+
+
+def scene(n, seed):
+    from contrastboundary_b200 import synthetic
+    return synthetic.make_scene(n, seed)[0].astype(np.float64)
+
+
+def main():
+    import oracle
+    shim, lao = load_reference_models()
+    out = {}
+    cfg = types.SimpleNamespace(adaptive_weight=types.SimpleNamespace(          # config/s3dis/adapt.yaml:19-26
+        local_input_feature="dp", reduction="mean", shared_channels=1, fc_num=1, weight_softmax=False, output_conv=False))
+    rng = np.random.default_rng(7)
+    cases = {"self": (1200, 1200, 0.12, 24), "pool": (1200, 350, 0.14, 72)}
+    for name, (n0, n, radius, fdim) in cases.items():
+        sup = scene(n0, 11).astype(np.float32)
+        qry = sup if name == "self" else sup[rng.choice(n0, n, replace=False)]
+        lens_s, lens_q = np.array([n0], np.int32), np.array([len(qry)], np.int32)
+        nb = oracle.batch_neighbors(qry, sup, lens_q, lens_s, radius).astype(np.int64)      # shadow index = n0 (reference C++ semantics)
+        nb = nb[:, :26]                                                                       # neighborhood_limits[0] of the shipped config
+        feat = rng.standard_normal((n0, fdim))
+        shim.reset(seed=3)
+        res = lao.AdaptiveWeight(cfg, qry.astype(np.float64), sup.astype(np.float64), nb, feat, scope="aw", radius=radius, out_fdim=fdim,
+                                 is_training=True, init="xavier", weight_decay=0, activation_fn="relu", bn=True, bn_momentum=0.98, bn_eps=1e-3)
+        v, taps = shim.variables(), shim.taps()
+        out[f"aw/{name}/query"], out[f"aw/{name}/support"], out[f"aw/{name}/neighbors"] = qry, sup, nb.astype(np.int32)
+        out[f"aw/{name}/features"], out[f"aw/{name}/radius"] = feat, np.float64(radius)
+        out[f"aw/{name}/fc_weight"] = v["aw/fc_1/weights"]                # (3, fdim): TF kernels are (in, out)
+        out[f"aw/{name}/fc_bias"] = v["aw/fc_1/biases"]
+        out[f"aw/{name}/bn_gamma"], out[f"aw/{name}/bn_beta"] = v["aw/pool_bn/gamma"], v["aw/pool_bn/beta"]
+        out[f"aw/{name}/aggregated"] = taps["aw/pool_bn/input"]           # what enters pool_bn: the aggregation itself
+        out[f"aw/{name}/output"] = res                                    # relu(pool_bn(aggregated))
+        print(name, "neighbors", nb.shape, "shadow fraction %.2f" % float((nb == n0).mean()), "output", res.shape)
+    np.savez_compressed(os.path.join(HERE, "tf_ops_ref.npz"), **out)
+    print("wrote tests/golden/tf_ops_ref.npz", sum(a.nbytes for a in out.values()) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

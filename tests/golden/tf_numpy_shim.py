@@ -1,0 +1,236 @@
+"""A NumPy stand-in for the small part of the TensorFlow-1 API that the reference's ConvNet operators use, so that the
+reference's OWN source files (tensorflow/models/local_aggregation_operators.py, basic_operators.py, ...) can be imported and
+EXECUTED here, where TensorFlow is not installable, to produce golden vectors (tests/golden/make_golden_tf_ops.py).
+
+Test infrastructure only.  Every function is the eager NumPy meaning of the TF-1 op of the same name (graph mode is not
+modelled: the reference's functions are straight-line tensor code); variables live in a dictionary keyed by their
+variable-scope path, created by the initializer the reference asks for from a seeded generator.  Tensors are float64 /
+int64 NumPy arrays, so the goldens carry no float32 rounding of their own."""
+import contextlib
+import types
+
+import numpy as np
+
+__version__ = "1.15.0-numpy-shim"
+float32, float16, float64, int32, int64, bool = np.float64, np.float64, np.float64, np.int64, np.int64, np.bool_
+
+
+class _State:
+    scope = []
+    variables = {}
+    taps = {}              # name -> last input of a named layer (e.g. the tensor entering 'pool_bn')
+    rng = np.random.default_rng(0)
+    collections = {}
+
+
+def reset(seed=0):
+    _State.scope, _State.variables, _State.taps, _State.collections = [], {}, {}, {}
+    _State.rng = np.random.default_rng(seed)
+
+
+def variables():
+    return _State.variables
+
+
+def taps():
+    return _State.taps
+
+
+@contextlib.contextmanager
+def variable_scope(name_or_scope, *args, **kwargs):
+    pushed = isinstance(name_or_scope, str) and name_or_scope != ""
+    if pushed:
+        _State.scope.append(name_or_scope)
+    try:
+        yield "/".join(_State.scope)
+    finally:
+        if pushed:
+            _State.scope.pop()
+
+
+name_scope = variable_scope
+
+
+@contextlib.contextmanager
+def device(_):
+    yield
+
+
+def _path(name):
+    return "/".join(_State.scope + [name])
+
+
+def get_variable(name, shape=None, initializer=None, dtype=None, trainable=True, **kwargs):
+    key = _path(name)
+    if key not in _State.variables:
+        shape = tuple(int(s) for s in shape)
+        _State.variables[key] = np.asarray(initializer(shape), dtype=np.float64).reshape(shape)
+    return _State.variables[key]
+
+
+# ---- initializers (values only matter in that they are generic: the tests read the variables back) -------------------
+def glorot_uniform_initializer(**_):
+    def init(shape):
+        fan_in, fan_out = (shape[0], shape[-1]) if len(shape) > 1 else (shape[0], shape[0])
+        lim = np.sqrt(6.0 / (fan_in + fan_out))
+        return _State.rng.uniform(-lim, lim, shape)
+    return init
+
+
+def truncated_normal_initializer(stddev=1.0, **_):
+    return lambda shape: np.clip(_State.rng.normal(0, stddev, shape), -2 * stddev, 2 * stddev)
+
+
+def constant_initializer(value=0.0, **_):
+    # a generic (non-zero) value around the requested constant: a zero bias would hide a missing bias term
+    return lambda shape: np.full(shape, float(value)) + 0.1 * _State.rng.standard_normal(shape)
+
+
+def zeros_initializer(**_):
+    return lambda shape: 0.1 * _State.rng.standard_normal(shape)
+
+
+def ones_initializer(**_):
+    return lambda shape: 1.0 + 0.1 * _State.rng.standard_normal(shape)
+
+
+def _variance_scaling_initializer(factor=2.0, mode="FAN_IN", uniform=False, **_):
+    def init(shape):
+        fan_in = shape[0] if len(shape) > 1 else shape[0]
+        return _State.rng.normal(0, np.sqrt(factor / fan_in), shape)
+    return init
+
+
+contrib = types.SimpleNamespace(layers=types.SimpleNamespace(variance_scaling_initializer=_variance_scaling_initializer))
+
+
+# ---- tensor ops ----------------------------------------------------------------------------------------------------------
+def shape(x):
+    return np.shape(x)
+
+
+def concat(values, axis=0, **_):
+    return np.concatenate([np.asarray(v) for v in values], axis=axis)
+
+
+def zeros_like(x, dtype=None, **_):
+    return np.zeros_like(x, dtype=dtype)
+
+
+def ones_like(x, dtype=None, **_):
+    return np.ones_like(x, dtype=dtype)
+
+
+def zeros(shape, dtype=np.float64, **_):
+    return np.zeros(shape, dtype=dtype)
+
+
+def ones(shape, dtype=np.float64, **_):
+    return np.ones(shape, dtype=dtype)
+
+
+def constant(value, dtype=None, **_):
+    return np.asarray(value, dtype=dtype)
+
+
+def gather(params, indices, axis=0, **_):
+    return np.take(np.asarray(params), np.asarray(indices).astype(np.int64), axis=axis)
+
+
+def expand_dims(x, axis, **_):
+    return np.expand_dims(x, axis)
+
+
+def squeeze(x, axis=None, **_):
+    return np.squeeze(x, axis=axis)
+
+
+def tile(x, multiples, **_):
+    return np.tile(x, [int(m) for m in multiples])
+
+
+def reshape(x, shape, **_):
+    return np.reshape(x, [int(s) for s in shape])
+
+
+def transpose(x, perm=None, **_):
+    return np.transpose(x, perm)
+
+
+def cast(x, dtype, **_):
+    return np.asarray(x).astype(dtype)
+
+
+sqrt, square, exp, log, abs, maximum, minimum = np.sqrt, np.square, np.exp, np.log, np.abs, np.maximum, np.minimum
+multiply, add, subtract, divide = np.multiply, np.add, np.subtract, np.divide
+less, greater, greater_equal, less_equal, equal, logical_and, logical_or, logical_not = (
+    np.less, np.greater, np.greater_equal, np.less_equal, np.equal, np.logical_and, np.logical_or, np.logical_not)
+
+
+def where(cond, x=None, y=None, **_):
+    return np.where(cond, x, y)
+
+
+def reduce_sum(x, axis=None, keepdims=False, **_):
+    return np.sum(x, axis=axis, keepdims=keepdims)
+
+
+def reduce_max(x, axis=None, keepdims=False, **_):
+    return np.max(x, axis=axis, keepdims=keepdims)
+
+
+def reduce_mean(x, axis=None, keepdims=False, **_):
+    return np.mean(x, axis=axis, keepdims=keepdims)
+
+
+def matmul(a, b, **_):
+    return np.matmul(a, b)
+
+
+def tensordot(a, b, axes, **_):
+    return np.tensordot(a, b, axes)
+
+
+def add_to_collection(name, value):
+    _State.collections.setdefault(name, []).append(value)
+
+
+def _relu(x, **_):
+    return np.maximum(x, 0)
+
+
+def _leaky_relu(x, alpha=0.2, **_):
+    return np.where(x > 0, x, alpha * x)
+
+
+def _softmax(x, axis=-1, **_):
+    e = np.exp(x - np.max(x, axis=axis, keepdims=True))
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def _l2_loss(x, **_):
+    return 0.5 * np.sum(np.square(x))
+
+
+nn = types.SimpleNamespace(relu=_relu, leaky_relu=_leaky_relu, softmax=_softmax, l2_loss=_l2_loss)
+
+
+def _batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, training=False, trainable=True, name=None, fused=None, **_):
+    """tf.layers.batch_normalization: statistics over every axis but the last; biased variance in training"""
+    x = np.asarray(inputs, dtype=np.float64)
+    c = x.shape[-1]
+    with variable_scope(name or "batch_normalization"):
+        _State.taps[_path("input")] = x
+        gamma = get_variable("gamma", [c], ones_initializer())
+        beta = get_variable("beta", [c], zeros_initializer())
+        mm = get_variable("moving_mean", [c], zeros_initializer())
+        mv = get_variable("moving_variance", [c], lambda s: 1.0 + 0.1 * _State.rng.random(s))
+    red = tuple(range(x.ndim - 1))
+    if training:
+        mean, var = x.mean(axis=red), x.var(axis=red)
+    else:
+        mean, var = mm, mv
+    return (x - mean) / np.sqrt(var + epsilon) * gamma + beta
+
+
+layers = types.SimpleNamespace(batch_normalization=_batch_normalization)

@@ -26,6 +26,28 @@ def test_adaptive_weight_restatements_agree():
     assert np.abs(a - y).max() < 1e-6          # tf_model.py counts the neighbours in float32 (cnt + 1e-5), as TF does
 
 
+def test_adaptive_weight_restatements_match_executed_reference_source():
+    """tests/golden/tf_ops_ref.npz comes from EXECUTING the reference's own AdaptiveWeight source
+    (tensorflow/models/local_aggregation_operators.py:316-500, adapt.yaml) on a NumPy stand-in for the TF-1 API
+    (tests/golden/make_golden_tf_ops.py): both restatements reproduce the aggregation (what enters pool_bn) and the
+    operator's output relu(pool_bn(.)) — row a13 is pinned by reference code that ran, not only by reading it."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    for name in ("self", "pool"):
+        k = lambda s: g[f"aw/{name}/{s}"]
+        q, sup, idx, feat = k("query").astype(np.float64), k("support").astype(np.float64), k("neighbors").astype(np.int64), k("features")
+        w, b, radius = k("fc_weight").T.copy(), k("fc_bias"), float(k("radius"))      # TF kernel (3, c) -> (c, 3)
+        assert (idx == len(sup)).any() and (idx < len(sup)).all(1).any()              # shadow entries and full rows both occur
+        agg = T.adaptive_weight(torch.from_numpy(q), torch.from_numpy(sup), torch.from_numpy(idx), torch.from_numpy(feat),
+                                torch.from_numpy(w), torch.from_numpy(b), radius).numpy()
+        assert np.abs(agg - k("aggregated")).max() < 1e-6 * np.abs(k("aggregated")).max()     # tf_model.py counts in float32
+        c = feat.shape[1]
+        P = {"x.fc_1.weight": w, "x.fc_1.bias": b, "x.pool_bn.weight": k("bn_gamma"), "x.pool_bn.bias": k("bn_beta")}
+        out = R.adaptive_weight(P, "x", q, sup, idx, feat, radius, 1e-3)
+        assert out.shape == (len(q), c)
+        assert np.abs(out - k("output")).max() < 1e-10 * max(1.0, np.abs(k("output")).max())
+
+
 def test_contrast_loss_restatements_agree():
     rng = np.random.default_rng(1)
     n, k, d = 400, 20, 72

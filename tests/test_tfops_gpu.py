@@ -119,6 +119,28 @@ def test_adaptive_weight_matches_restatement():
             assert float((a - r).abs().max()) <= 2e-5 * float(r.abs().max()) + 1e-7
 
 
+def test_adaptive_weight_matches_executed_reference_source():
+    """a13 against tests/golden/tf_ops_ref.npz: vectors produced by EXECUTING the reference's own AdaptiveWeight source
+    (tensorflow/models/local_aggregation_operators.py:316-500, adapt.yaml) on a NumPy stand-in for the TF-1 API
+    (tests/golden/make_golden_tf_ops.py) — the CUDA kernel reproduces the aggregation that enters pool_bn, and the module-level
+    relu(pool_bn(.)) reproduces the operator's output."""
+    import os
+    from contrastboundary_b200 import tf_model
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tf_ops_ref.npz"))
+    for name in ("self", "pool"):
+        k = lambda s: g[f"aw/{name}/{s}"]
+        t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+        q, sup, feat = t32(k("query")), t32(k("support")), t32(k("features"))
+        nb = torch.from_numpy(k("neighbors").astype(np.int32)).cuda()
+        w, b = t32(k("fc_weight").T), t32(k("fc_bias"))                          # TF kernel (3, c) -> (c, 3)
+        agg = tf_model.adaptive_weight(q, sup, nb, feat, w, b, float(k("radius")))
+        ref = torch.from_numpy(k("aggregated")).cuda()
+        assert float((agg.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+        y = torch.relu(torch.nn.functional.batch_norm(agg, None, None, t32(k("bn_gamma")), t32(k("bn_beta")), True, 0.0, 1e-3))
+        out = torch.from_numpy(k("output")).cuda()
+        assert float((y.double() - out).abs().max()) <= 1e-4 * max(1.0, float(out.abs().max()))
+
+
 def test_tf_contrast_loss_matches_restatement():
     """a14 (parity unpinned, same caveat)"""
     from contrastboundary_b200 import tf_model
