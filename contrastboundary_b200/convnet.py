@@ -370,6 +370,49 @@ def input_features(points, colors, in_features_dim=5):
     raise NotImplementedError(in_features_dim)
 
 
+# ------------------------------------------------------------------------------------------------
+# TensorFlow checkpoint names -> this module's state_dict
+# ------------------------------------------------------------------------------------------------
+def tf_variable_to_state_dict(name):
+    """('model/resnet_backbone/res2_bottleneck0/conv2/local_aggregation/fc_1/weights') ->
+    ('resnet_backbone.res.1.bottleneck0.conv2.fc_1.weight', transpose?)  or None for variables this module does not hold
+    (optimizer slots, the global step).  TF kernels are stored (in, out); nn.Linear weights (out, in): transpose = True."""
+    import re
+    parts = [p for p in name.split(":")[0].split("/") if p not in ("model", "conv1d_1x1", "local_aggregation", "local_aggreagtion")]
+    if not parts or parts[0] not in ("resnet_backbone", "resnet_scene_segmentation_head"):
+        return None
+    out = [parts[0]]
+    for p_ in parts[1:-1]:
+        m = re.fullmatch(r"res(\d+)_(strided_bottleneck|bottleneck\d+)", p_)
+        out += ["res", str(int(m.group(1)) - 1), m.group(2)] if m else [p_]
+    leaf, parent = parts[-1], (parts[-2] if len(parts) > 1 else "")
+    is_bn = parent in ("bn", "pool_bn")
+    if is_bn:
+        key = {"gamma": "weight", "beta": "bias", "moving_mean": "running_mean", "moving_variance": "running_var"}.get(leaf)
+        return None if key is None else (".".join(out + [key]), False)
+    if parent == "fc_1":
+        return {"weights": (".".join(out + ["weight"]), True), "biases": (".".join(out + ["bias"]), False)}.get(leaf)
+    return {"weights": (".".join(out + ["weights", "weight"]), True), "biases": (".".join(out + ["weights", "bias"]), False)}.get(leaf)
+
+
+def load_tf_variables(model, variables, strict=False):
+    """variables: {TF variable name: array} (e.g. read from a reference checkpoint).  Copies every variable that maps onto
+    `model` (ConvNetSeg); returns the list of TF names that were not used."""
+    sd = model.state_dict()
+    unused = []
+    with torch.no_grad():
+        for name, value in variables.items():
+            m = tf_variable_to_state_dict(name)
+            if m is None or m[0] not in sd:
+                unused.append(name)
+                continue
+            t = torch.as_tensor(value, dtype=sd[m[0]].dtype)
+            sd[m[0]].copy_(t.t() if m[1] else t)
+    if strict and unused:
+        raise KeyError("TF variables without a counterpart: %s" % unused[:8])
+    return unused
+
+
 class ConvNetTrainStep:
     """one training iteration of the TF trainer (utils/trainer.py): pyramid (the reference builds it on tf.data CPU workers) ->
     forward -> loss -> backward -> global-norm clip -> Momentum SGD."""

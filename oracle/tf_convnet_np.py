@@ -146,15 +146,12 @@ def contrast_loss(feat, neighbors, cls, temperature, weight):
     return float((-np.log(pos / (pos + neg) + eps)).mean() * weight)
 
 
-def forward(P, inp, cfg):
-    """P: {name: float64 array}; inp: pyramid dict of NumPy arrays; cfg: contrastboundary_b200.convnet.ConvNetConfig-like
-    -> (logits (n0, ncls), loss vector [xen, cbl_0..cbl_4], latents)"""
-    P = {k: np.asarray(v, F64) for k, v in P.items()}
+def backbone(P, inp, cfg):
+    """resnet_backbone (backbone/resnet.py:307-420): input conv, simple block, per level [strided bottleneck +] depth x
+    bottleneck -> list of the num_layers stage features.  P / inp as float64."""
     eps = cfg.bn_eps
-    f = cfg.first_features_dim
     r = cfg.first_subsampling_dl * cfg.density_parameter                        # build_models.py:186
-    pts = [np.asarray(p, F64) for p in inp["points"]]
-    inp = dict(inp, points=pts)
+    pts = inp["points"]
     x = conv1d_1x1(P, "resnet_backbone.res1_input_conv", np.asarray(inp["features"], F64), eps)
     x = adaptive_weight(P, "resnet_backbone.res1_simple_block", pts[0], pts[0], inp["neighbors"][0], x, r, eps)
     feats = []
@@ -165,7 +162,13 @@ def forward(P, inp, cfg):
         for i in range(cfg.depth):
             x = bottleneck(P, pre + f".bottleneck{i}", inp, l, x, r * 2 ** l, False, eps)
         feats.append(x)
-    # seg head (seg_head.py:58-95)
+    return feats
+
+
+def seg_head_features(P, inp, feats, cfg):
+    """resnet_scene_segmentation_head with sep_head (heads/seg_head.py:58-95): nearest upsampling + concat + 1x1 conv,
+    -> [F_up[0] (finest) .. F_up[3], feats[4]]"""
+    eps = cfg.bn_eps
     f_up = []
     x = feats[4]
     for j in range(4):
@@ -173,7 +176,20 @@ def forward(P, inp, cfg):
         x = closest(x, inp["upsamples"][lvl][:, 0])
         x = conv1d_1x1(P, f"resnet_scene_segmentation_head.up_conv{j}", np.concatenate([x, feats[lvl - 1]], 1), eps)
         f_up.append(x)
-    f_out = list(reversed(f_up)) + [feats[4]]
+    return list(reversed(f_up)) + [feats[4]]
+
+
+def forward(P, inp, cfg):
+    """P: {name: float64 array}; inp: pyramid dict of NumPy arrays; cfg: contrastboundary_b200.convnet.ConvNetConfig-like
+    -> (logits (n0, ncls), loss vector [xen, cbl_0..cbl_4], latents)"""
+    P = {k: np.asarray(v, F64) for k, v in P.items()}
+    eps = cfg.bn_eps
+    f = cfg.first_features_dim
+    r = cfg.first_subsampling_dl * cfg.density_parameter                        # build_models.py:186
+    pts = [np.asarray(p, F64) for p in inp["points"]]
+    inp = dict(inp, points=pts)
+    feats = backbone(P, inp, cfg)
+    f_out = seg_head_features(P, inp, feats, cfg)
     # multiscale head
     up_idx0, cls = head_geometry({k: ([np.asarray(a) for a in v] if isinstance(v, (list, tuple)) else np.asarray(v)) for k, v in inp.items()
                                   if k in ("points", "batches_len", "point_labels", "upsamples", "pools")}, cfg.r_sample, cfg.num_classes)

@@ -34,6 +34,26 @@ def load_reference_models():
     return shim, lao
 
 
+def pyramid(points, lens, dl, density, limits):
+    """the reference's input pyramid (tensorflow/datasets/base.py:767-842) composed from the CPU oracle of its C++ operators"""
+    import oracle
+    pts, lens = points.astype(np.float32), np.asarray(lens, np.int32)
+    r = dl * density / 2.0
+    nl = len(limits)
+    P, NB, PO, UP = [None] * nl, [None] * nl, [None] * nl, [np.zeros((0, 1), np.int32)] + [None] * (nl - 1)
+    for l in range(nl - 1):
+        NB[l] = oracle.batch_neighbors(pts, pts, lens, lens, r)[:, :limits[l]]
+        pool_pts, pool_lens = oracle.batch_grid_subsampling(pts, lens, 2 * dl)
+        PO[l] = oracle.batch_neighbors(pool_pts, pts, pool_lens, lens, r)[:, :limits[l]]
+        UP[l + 1] = oracle.batch_neighbors(pts, pool_pts, lens, pool_lens, 2 * r)[:, :limits[l]]
+        P[l] = pts
+        pts, lens, r, dl = pool_pts, pool_lens, 2 * r, 2 * dl
+    P[nl - 1] = pts
+    NB[nl - 1] = oracle.batch_neighbors(pts, pts, lens, lens, r)[:, :limits[nl - 1]]
+    PO[nl - 1] = np.zeros((0, 1), np.int32)
+    return {"points": P, "neighbors": NB, "pools": PO, "upsamples": UP}
+
+
 def scene(n, seed):
     from contrastboundary_b200 import synthetic
     return synthetic.make_scene(n, seed)[0].astype(np.float64)
@@ -46,7 +66,7 @@ def main():
     cfg = types.SimpleNamespace(adaptive_weight=types.SimpleNamespace(          # config/s3dis/adapt.yaml:19-26
         local_input_feature="dp", reduction="mean", shared_channels=1, fc_num=1, weight_softmax=False, output_conv=False))
     rng = np.random.default_rng(7)
-    cases = {"self": (1200, 1200, 0.12, 24), "pool": (1200, 350, 0.14, 72)}
+    cases = {"self": (800, 800, 0.14, 24), "pool": (600, 200, 0.12, 72)}
     for name, (n0, n, radius, fdim) in cases.items():
         sup = scene(n0, 11).astype(np.float32)
         qry = sup if name == "self" else sup[rng.choice(n0, n, replace=False)]
@@ -66,6 +86,34 @@ def main():
         out[f"aw/{name}/aggregated"] = taps["aw/pool_bn/input"]           # what enters pool_bn: the aggregation itself
         out[f"aw/{name}/output"] = res                                    # relu(pool_bn(aggregated))
         print(name, "neighbors", nb.shape, "shadow fraction %.2f" % float((nb == n0).mean()), "output", res.shape)
+    # ---- the backbone and the segmentation head: backbone/resnet.py:307-420 + heads/seg_head.py:31-110, executed -----------------------
+    resnet = importlib.import_module("refmodels.backbone.resnet")
+    seg = importlib.import_module("refmodels.heads.seg_head")
+    fdim, dl, density, limits = 4, 0.04, 5.0, [12, 14, 16, 16, 14]
+    cfg2 = types.SimpleNamespace(adaptive_weight=cfg.adaptive_weight, local_aggreagtion="adaptive_weight", sep_head=True, arch_up="", num_layers=5,
+                                 num_classes=13)
+    pts = np.concatenate([scene(900, 21), scene(700, 22) + np.array([30.0, 0, 0])]).astype(np.float32)
+    pyr = pyramid(pts, [900, 700], dl, density, limits)
+    feat_in = rng.standard_normal((len(pts), 5))
+    inputs = {k: [np.asarray(a, np.float64) if k == "points" else np.asarray(a, np.int64) for a in v] for k, v in pyr.items()}
+    shim.reset(seed=5)
+    F = resnet.resnet_backbone(cfg2, inputs, feat_in, base_radius=dl * density, base_fdim=fdim, bottleneck_ratio=2, depth=1, is_training=True,
+                               init="xavier", weight_decay=0, activation_fn="relu", bn=True, bn_momentum=0.98, bn_eps=1e-3)
+    F_up, head = seg.resnet_scene_segmentation_head(cfg2, inputs, F, base_fdim=fdim, is_training=True, init="xavier", weight_decay=0,
+                                                    activation_fn="relu", bn=True, bn_momentum=0.98, bn_eps=1e-3)
+    assert head is None and len(F) == 5 and len(F_up) == 4
+    for k, v in pyr.items():
+        for l, a in enumerate(v):
+            out[f"net/{k}/{l}"] = a
+    out["net/features"] = feat_in
+    out["net/config"] = np.array([fdim, dl, density, 2, 1], np.float64)      # first_features_dim, dl, density, bottleneck_ratio, depth
+    for l in range(5):
+        out[f"net/F/{l}"] = F[l]
+    for l in range(4):
+        out[f"net/F_up/{l}"] = F_up[l]
+    for name, value in shim.variables().items():
+        out["net/var/" + name] = value
+    print("backbone + seg head: level sizes", [len(p) for p in pyr["points"]], "variables", len(shim.variables()))
     np.savez_compressed(os.path.join(HERE, "tf_ops_ref.npz"), **out)
     print("wrote tests/golden/tf_ops_ref.npz", sum(a.nbytes for a in out.values()) // 1024, "KiB")
 

@@ -179,6 +179,10 @@ def reduce_max(x, axis=None, keepdims=False, **_):
     return np.max(x, axis=axis, keepdims=keepdims)
 
 
+def reduce_min(x, axis=None, keepdims=False, **_):
+    return np.min(x, axis=axis, keepdims=keepdims)
+
+
 def reduce_mean(x, axis=None, keepdims=False, **_):
     return np.mean(x, axis=axis, keepdims=keepdims)
 

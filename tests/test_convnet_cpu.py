@@ -48,6 +48,42 @@ def test_adaptive_weight_restatements_match_executed_reference_source():
         assert np.abs(out - k("output")).max() < 1e-10 * max(1.0, np.abs(k("output")).max())
 
 
+def test_backbone_and_seg_head_restatement_match_executed_reference_source():
+    """The reference's resnet_backbone (backbone/resnet.py:307-420: input conv, simple block, strided / plain bottlenecks with
+    AdaptiveWeight, ind_max_pool shortcuts) and resnet_scene_segmentation_head (heads/seg_head.py:31-110), EXECUTED on the NumPy
+    TF stand-in over a 5-level pyramid built by the CPU oracle of the reference's C++ operators: the float64 restatement that
+    the CUDA network is tested against (oracle/tf_convnet_np.py, tests/test_convnet_gpu.py) reproduces every stage feature.
+    The TF variable names go through the product's checkpoint-name converter (convnet.tf_variable_to_state_dict)."""
+    import os
+    import types
+    from contrastboundary_b200 import convnet
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    fdim, dl, density, ratio, depth = g["net/config"]
+    cfg = types.SimpleNamespace(bn_eps=1e-3, first_features_dim=int(fdim), first_subsampling_dl=float(dl), density_parameter=float(density),
+                                num_layers=5, depth=int(depth))
+    P, used = {}, 0
+    for key in g.files:
+        if not key.startswith("net/var/"):
+            continue
+        m = convnet.tf_variable_to_state_dict(key[len("net/var/"):])
+        assert m is not None, key
+        P[m[0]] = g[key].T.copy() if m[1] else g[key]
+        used += 1
+    assert used == 200 and "resnet_backbone.res.1.strided_bottleneck.conv2.fc_1.weight" in P
+    ref_keys = set(convnet.ConvNetSeg(convnet.ConvNetConfig()).state_dict().keys())
+    assert {k for k in P if "res.0.bottleneck0" in k or "up_conv" in k or "res1_" in k} <= ref_keys      # same names as the product's modules
+    inp = {k: [g[f"net/{k}/{l}"].astype(np.float64 if k == "points" else np.int64) for l in range(5)] for k in ("points", "neighbors", "pools", "upsamples")}
+    inp["features"] = g["net/features"]
+    feats = R.backbone(P, inp, cfg)
+    f_out = R.seg_head_features(P, inp, feats, cfg)
+    for l in range(5):
+        ref = g[f"net/F/{l}"]
+        assert feats[l].shape == ref.shape and np.abs(feats[l] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), l
+    for l in range(4):
+        ref = g[f"net/F_up/{l}"]
+        assert np.abs(f_out[l] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), l
+
+
 def test_contrast_loss_restatements_agree():
     rng = np.random.default_rng(1)
     n, k, d = 400, 20, 72
