@@ -99,7 +99,8 @@ def _pyramid_level(seed=3):
 
 
 def test_adaptive_weight_matches_restatement():
-    """a13 (parity unpinned: TF cannot run here; the checker is oracle/tf_model.py, a line-by-line restatement)"""
+    """a13 forward + backward against oracle/tf_model.py, a line-by-line restatement that is itself pinned by the executed
+    reference source (tests/test_convnet_cpu.py); the forward is also compared with that golden directly, below"""
     from contrastboundary_b200 import tf_model
     from oracle import tf_model as otf
     pts, nb = _pyramid_level()
