@@ -41,17 +41,19 @@ def pyramid(points, lens, dl, density, limits):
     r = dl * density / 2.0
     nl = len(limits)
     P, NB, PO, UP = [None] * nl, [None] * nl, [None] * nl, [np.zeros((0, 1), np.int32)] + [None] * (nl - 1)
+    LENS = [None] * nl
     for l in range(nl - 1):
+        LENS[l] = lens
         NB[l] = oracle.batch_neighbors(pts, pts, lens, lens, r)[:, :limits[l]]
         pool_pts, pool_lens = oracle.batch_grid_subsampling(pts, lens, 2 * dl)
         PO[l] = oracle.batch_neighbors(pool_pts, pts, pool_lens, lens, r)[:, :limits[l]]
         UP[l + 1] = oracle.batch_neighbors(pts, pool_pts, lens, pool_lens, 2 * r)[:, :limits[l]]
         P[l] = pts
         pts, lens, r, dl = pool_pts, pool_lens, 2 * r, 2 * dl
-    P[nl - 1] = pts
+    P[nl - 1], LENS[nl - 1] = pts, lens
     NB[nl - 1] = oracle.batch_neighbors(pts, pts, lens, lens, r)[:, :limits[nl - 1]]
     PO[nl - 1] = np.zeros((0, 1), np.int32)
-    return {"points": P, "neighbors": NB, "pools": PO, "upsamples": UP}
+    return {"points": P, "neighbors": NB, "pools": PO, "upsamples": UP, "batches_len": LENS}
 
 
 def scene(n, seed):
@@ -96,6 +98,7 @@ def main():
     pyr = pyramid(pts, [900, 700], dl, density, limits)
     feat_in = rng.standard_normal((len(pts), 5))
     inputs = {k: [np.asarray(a, np.float64) if k == "points" else np.asarray(a, np.int64) for a in v] for k, v in pyr.items()}
+    lens0 = [900, 700]
     shim.reset(seed=5)
     F = resnet.resnet_backbone(cfg2, inputs, feat_in, base_radius=dl * density, base_fdim=fdim, bottleneck_ratio=2, depth=1, is_training=True,
                                init="xavier", weight_decay=0, activation_fn="relu", bn=True, bn_momentum=0.98, bn_eps=1e-3)
@@ -114,6 +117,41 @@ def main():
     for name, value in shim.variables().items():
         out["net/var/" + name] = value
     print("backbone + seg head: level sizes", [len(p) for p in pyr["points"]], "variables", len(shim.variables()))
+
+    # ---- a14: the contrast head (heads/head.py:462-807) on the same pyramid: label sampling ('label'), hard sub-scene labels
+    #      (get_scene_label 'max': pools for stage 1, a radius search among the level-0 points beyond), soft-NN on l2 distances --------------
+    from contrastboundary_b200 import synthetic
+    import oracle
+    head = importlib.import_module("refmodels.heads.head")
+    labels0 = np.concatenate([synthetic.make_scene(900, 21)[2], synthetic.make_scene(700, 22)[2]]).astype(np.int64)
+    r_sample = [dl * density * 2 ** i / 2.0 * 1.5 for i in range(4)]          # any radii work: they are inputs of both sides
+
+    def radius_search(queries, supports, q_len, s_len, radius, device=None):   # what ops.get_tf_func('radius') wraps: the reference's C++
+        return oracle.batch_neighbors(np.asarray(queries, np.float32), np.asarray(supports, np.float32), np.asarray(q_len, np.int32),
+                                      np.asarray(s_len, np.int32), float(radius)).astype(np.int64)
+    sys.modules["ops"] = types.SimpleNamespace(get_tf_func=lambda name: radius_search)
+    d = 32
+    latents = [rng.standard_normal((len(p), d)) for p in pyr["points"]]
+    class GraphTensor(np.ndarray):          # TF-1 graph tensors compare by identity (head.py:146 asserts `pts_from == pts_to`)
+        def __eq__(self, other):
+            return self is other
+        __hash__ = None
+    stage = [{"p_out": inputs["points"][i].view(GraphTensor), "latent": latents[i], "f_out": latents[i]} for i in range(5)]
+    cinputs = {"neighbors": inputs["neighbors"], "point_labels": labels0, "points": inputs["points"], "stage_list": {"up": stage, "down": stage},
+               "sample_idx": {"down": inputs["pools"], "up": inputs["upsamples"]}, "batches_len": [np.asarray(x, np.int64) for x in pyr["batches_len"]],
+               "_glb": {}}
+    ccfg = types.SimpleNamespace(search="radius", sample="grid", ignored_labels=[], num_classes=13, num_layers=5, r_sample=r_sample, debug=False)
+    hcfg = types.SimpleNamespace(sample="label", dist="l2", margin="", mask="", contrast_aug="", weight=0.1)
+    out["cbl/point_labels"], out["cbl/r_sample"] = labels0, np.asarray(r_sample)
+    for i in range(5):
+        samples = head.contrast_head.sample_labels(cinputs, "up", i, "label", "latent", ccfg, name=f"up{i}/sample")
+        res = head.contrast_head.contrast(latents[i], (*samples, "up", i), "softnn", cinputs, hcfg, ccfg, name=f"up{i}/softnn")
+        scene_lab = head.get_scene_label(cinputs, "up", i, "latent", ccfg, reduction="max", extend=False, infer="")
+        out[f"cbl/latent/{i}"] = latents[i]
+        out[f"cbl/batches_len/{i}"] = np.asarray(pyr["batches_len"][i], np.int32)
+        out[f"cbl/loss/{i}"] = np.float64(res["loss"])
+        out[f"cbl/scene_label/{i}"] = labels0 if scene_lab is None else np.asarray(scene_lab).reshape(-1).astype(np.int64)
+        print("contrast head stage", i, "loss", float(res["loss"]), "points with pos and neg:", int(np.asarray(res["logits"]).shape[0]))
     np.savez_compressed(os.path.join(HERE, "tf_ops_ref.npz"), **out)
     print("wrote tests/golden/tf_ops_ref.npz", sum(a.nbytes for a in out.values()) // 1024, "KiB")
 

@@ -133,8 +133,63 @@ def constant(value, dtype=None, **_):
     return np.asarray(value, dtype=dtype)
 
 
-def gather(params, indices, axis=0, **_):
+Tensor = np.ndarray
+
+
+def TensorShape(dims):
+    return tuple(dims)
+
+
+def gather(params, indices, axis=0, batch_dims=0, **_):
+    assert batch_dims == 0
     return np.take(np.asarray(params), np.asarray(indices).astype(np.int64), axis=axis)
+
+
+def one_hot(indices, depth, axis=-1, dtype=np.float64, **_):
+    idx = np.asarray(indices).astype(np.int64)
+    out = (idx[..., None] == np.arange(int(depth))).astype(dtype)        # out-of-range (e.g. -1) -> all zeros, as TF
+    assert axis in (-1, idx.ndim)
+    return out
+
+
+def argmax(x, axis=None, **_):
+    return np.argmax(x, axis=axis)                                        # first maximum, as TF
+
+
+def boolean_mask(tensor, mask, name=None, axis=None, **_):
+    tensor, mask = np.asarray(tensor), np.asarray(mask).astype(np.bool_)
+    return tensor[mask]
+
+
+def reduce_any(x, axis=None, keepdims=False, **_):
+    return np.any(x, axis=axis, keepdims=keepdims)
+
+
+def reduce_all(x, axis=None, keepdims=False, **_):
+    return np.all(x, axis=axis, keepdims=keepdims)
+
+
+def cond(pred, true_fn=None, false_fn=None, name=None, **_):
+    return true_fn() if np.asarray(pred).all() else false_fn()
+
+
+def stack(values, axis=0, **_):
+    return np.stack(values, axis=axis)
+
+
+def stop_gradient(x, **_):
+    return x
+
+
+not_equal, pow = np.not_equal, np.power
+
+
+def _xlogy(x, y):
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    return np.where(x == 0, 0.0, x * np.log(np.where(x == 0, 1.0, y)))
+
+
+math = types.SimpleNamespace(xlogy=_xlogy, log=np.log, exp=np.exp)
 
 
 def expand_dims(x, axis, **_):
@@ -216,7 +271,11 @@ def _l2_loss(x, **_):
     return 0.5 * np.sum(np.square(x))
 
 
-nn = types.SimpleNamespace(relu=_relu, leaky_relu=_leaky_relu, softmax=_softmax, l2_loss=_l2_loss)
+def _l2_normalize(x, axis=-1, epsilon=1e-12, **_):
+    return x / np.sqrt(np.maximum(np.sum(np.square(x), axis=axis, keepdims=True), epsilon))
+
+
+nn = types.SimpleNamespace(relu=_relu, leaky_relu=_leaky_relu, softmax=_softmax, l2_loss=_l2_loss, l2_normalize=_l2_normalize)
 
 
 def _batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, training=False, trainable=True, name=None, fused=None, **_):

@@ -85,6 +85,30 @@ def test_backbone_and_seg_head_restatement_match_executed_reference_source():
         assert np.abs(f_out[l] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), l
 
 
+def test_contrast_head_restatements_match_executed_reference_source():
+    """a14: the reference's contrast head (heads/head.py:462-807 — sample_labels 'label', collect_labels / get_scene_label 'max',
+    solve_samples_mask, calc_dist 'l2', soft-NN) EXECUTED on the NumPy TF stand-in at every stage of a 5-level pyramid; its
+    cross-stage radius search is served by the CPU oracle of the reference's C++ neighbour operator.  The restatements
+    reproduce the hard sub-scene labels exactly and the loss of every stage (including the stages where no point has both a
+    positive and a negative neighbour: loss 0)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    inp = {k: [g[f"net/{k}/{l}"] for l in range(5)] for k in ("points", "neighbors", "pools", "upsamples")}
+    inp["batches_len"] = [g[f"cbl/batches_len/{l}"] for l in range(5)]
+    inp["point_labels"] = g["cbl/point_labels"]
+    _, cls = R.head_geometry(inp, [float(r) for r in g["cbl/r_sample"]], 13)
+    nonzero = 0
+    for i in range(5):
+        ref_lab = g[f"cbl/scene_label/{i}"]
+        assert np.array_equal(np.asarray(cls[i]).astype(np.int64), ref_lab), f"hard sub-scene labels, stage {i}"
+        feat, nb, ref = g[f"cbl/latent/{i}"], inp["neighbors"][i].astype(np.int64), float(g[f"cbl/loss/{i}"])
+        a = R.contrast_loss(feat, nb, np.asarray(cls[i]), None, 0.1)
+        b = float(T.contrast_loss(torch.from_numpy(feat), torch.from_numpy(nb), torch.from_numpy(np.asarray(cls[i]).astype(np.int64)), 1.0, 0.1))
+        assert abs(a - ref) < 1e-10 * max(1.0, abs(ref)) and abs(b - ref) < 1e-10 * max(1.0, abs(ref)), (i, a, b, ref)
+        nonzero += ref > 0
+    assert nonzero >= 3
+
+
 def test_contrast_loss_restatements_agree():
     rng = np.random.default_rng(1)
     n, k, d = 400, 20, 72

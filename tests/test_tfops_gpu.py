@@ -162,6 +162,36 @@ def test_tf_contrast_loss_matches_restatement():
         assert float((res[1][1] - res[0][1]).abs().max()) <= 1e-4 * float(res[0][1].abs().max())
 
 
+def test_tf_contrast_head_matches_executed_reference_source():
+    """a14 against tests/golden/tf_ops_ref.npz: the reference's contrast head (heads/head.py:462-807) EXECUTED on the NumPy TF
+    stand-in at every stage of a 5-level pyramid (tests/golden/make_golden_tf_ops.py): the CUDA label votes reproduce its hard
+    sub-scene labels exactly, the CUDA soft-NN loss reproduces its loss at every stage (incl. the stages whose loss is 0)."""
+    from contrastboundary_b200 import convnet, tf_model
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tf_ops_ref.npz"))
+    pts = [torch.from_numpy(g[f"net/points/{l}"].astype(np.float32)).cuda() for l in range(5)]
+    lens = [torch.from_numpy(g[f"cbl/batches_len/{l}"].astype(np.int32)).cuda() for l in range(5)]
+    nbs = [torch.from_numpy(g[f"net/neighbors/{l}"].astype(np.int32)).cuda() for l in range(5)]
+    pools0 = torch.from_numpy(g["net/pools/0"].astype(np.int32)).cuda()
+    labels = torch.from_numpy(g["cbl/point_labels"].astype(np.int64)).cuda()
+    r_sample = [float(r) for r in g["cbl/r_sample"]]
+    nonzero = 0
+    for i in range(5):
+        ref_lab = g[f"cbl/scene_label/{i}"]
+        if i == 0:
+            cls = labels.to(torch.int32)
+        elif i == 1:
+            cls = convnet.label_vote_idx(pools0, labels, 13, pts[0].shape[0])
+        else:
+            cls = convnet.label_vote_radius(pts[i], pts[0], lens[i], lens[0], r_sample[i - 1], labels, 13)
+        assert np.array_equal(cls.cpu().numpy().astype(np.int64), ref_lab), f"hard sub-scene labels, stage {i}"
+        feat = torch.from_numpy(g[f"cbl/latent/{i}"].astype(np.float32)).cuda()
+        ref = float(g[f"cbl/loss/{i}"])
+        loss = float(tf_model.tf_contrast_loss(feat, nbs[i], cls, 1.0, 0.1))
+        assert abs(loss - ref) <= 1e-4 * max(abs(ref), 1e-3), (i, loss, ref)
+        nonzero += ref > 0
+    assert nonzero >= 3
+
+
 def test_segmentation_inputs_radius_pyramid():
     """the whole 5-level input pyramid (datasets/base.py:767-842) built on the device vs the same
     composition of the CPU oracle operators, level by level"""
