@@ -1,10 +1,10 @@
 """oracle/tf_model.py — TEST INFRASTRUCTURE.  Plain-torch restatement of the TF tree's AdaptiveWeight
 aggregation (tensorflow/models/local_aggregation_operators.py:351-471, adapt.yaml config) and contrast_head
 soft-NN loss (tensorflow/models/heads/head.py:180-195,641-662,725-807).  TensorFlow cannot be imported in the
-build container.  adaptive_weight IS pinned: tests/golden/tf_ops_ref.npz holds vectors from the reference's own
-AdaptiveWeight source executed on a NumPy stand-in of the TF-1 API (tests/golden/make_golden_tf_ops.py,
-tests/test_convnet_cpu.py).  contrast_loss is not ("parity unpinned" for row a14): it follows the
-cited lines op by op and must agree with the second restatement in oracle/tf_convnet_np.py."""
+build container.  Both functions are pinned under a stand-in runtime: tests/golden/tf_ops_ref.npz holds vectors from the
+reference's own AdaptiveWeight and contrast_head source executed on a NumPy stand-in of the TF-1 API
+(tests/golden/make_golden_tf_ops.py, tests/test_convnet_cpu.py); both also must agree with the second, independently
+written restatement in oracle/tf_convnet_np.py."""
 import torch
 
 _EPS = 1e-12

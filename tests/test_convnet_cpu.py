@@ -1,7 +1,7 @@
 """The two independently written restatements of the TF tree's a13 / a14 operators (oracle/tf_model.py in torch,
-oracle/tf_convnet_np.py in NumPy float64) must agree with each other, and — for AdaptiveWeight, the resnet backbone and the
-segmentation head — with vectors produced by executing the reference's own TF source on a NumPy stand-in of the TF-1 API
-(tests/golden/make_golden_tf_ops.py).  The contrast head stays "parity unpinned" (DESIGN.md)."""
+oracle/tf_convnet_np.py in NumPy float64) must agree with each other, and — for AdaptiveWeight, the resnet backbone, the
+segmentation head and the contrast head — with vectors produced by executing the reference's own TF source on a NumPy
+stand-in of the TF-1 API (tests/golden/make_golden_tf_ops.py)."""
 import numpy as np
 import torch
 

@@ -143,7 +143,8 @@ def test_adaptive_weight_matches_executed_reference_source():
 
 
 def test_tf_contrast_loss_matches_restatement():
-    """a14 (parity unpinned, same caveat)"""
+    """a14 forward + backward against oracle/tf_model.py, a restatement that is itself pinned by the executed reference source
+    (tests/test_convnet_cpu.py); the forward is also compared with that golden directly, below"""
     from contrastboundary_b200 import tf_model
     from oracle import tf_model as otf
     pts, nb = _pyramid_level()
