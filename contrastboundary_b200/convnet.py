@@ -380,6 +380,16 @@ def tf_variable_to_state_dict(name):
     ('resnet_backbone.res.1.bottleneck0.conv2.fc_1.weight', transpose?)  or None for variables this module does not hold
     (optimizer slots, the global step).  TF kernels are stored (in, out); nn.Linear weights (out, in): transpose = True."""
     import re
+    bn_leaf = {"gamma": "weight", "beta": "bias", "moving_mean": "running_mean", "moving_variance": "running_var"}
+    # the multi-scale head (heads/head.py:338-425): .../main/up{i}/mlp_0/{weights, batch_normalization/*}, .../main/linear/{weights, bias}
+    m = re.search(r"(?:^|/)main/up(\d+)/mlp_0/(weights|batch_normalization/(\w+))$", name.split(":")[0])
+    if m:
+        if m.group(2) == "weights":
+            return "multiscale.mlp.%s.weights.weight" % m.group(1), True
+        return ("multiscale.mlp.%s.bn.%s" % (m.group(1), bn_leaf[m.group(3)]), False) if m.group(3) in bn_leaf else None
+    m = re.search(r"(?:^|/)main/linear/(weights|bias)$", name.split(":")[0])
+    if m:
+        return ("multiscale.linear.weight", True) if m.group(1) == "weights" else ("multiscale.linear.bias", False)
     parts = [p for p in name.split(":")[0].split("/") if p not in ("model", "conv1d_1x1", "local_aggregation", "local_aggreagtion")]
     if not parts or parts[0] not in ("resnet_backbone", "resnet_scene_segmentation_head"):
         return None

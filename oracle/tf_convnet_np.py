@@ -179,6 +179,20 @@ def seg_head_features(P, inp, feats, cfg):
     return list(reversed(f_up)) + [feats[4]]
 
 
+def multiscale_head(P, f_out, up_idx0, labels, cfg):
+    """multiscale_head '||Ua-concat-latent' (heads/head.py:338-425): latent_i = relu(bn(f_out_i W_i)) (mlps_by_ops '1mlp', :268-273),
+    nearest upsampling of every latent to U0 (a level-0 point without a level-i point in range gathers a zero row), concat, linear
+    classifier (:279-282), mean sparse softmax cross-entropy (:200-214) -> (logits, latents, loss)"""
+    eps = cfg.bn_eps
+    latents = [conv1d_1x1(P, f"multiscale.mlp.{i}", f_out[i], eps) for i in range(cfg.num_layers)]
+    cols = [latents[0]] + [closest(latents[i], up_idx0[i]) for i in range(1, cfg.num_layers)]
+    logits = np.concatenate(cols, 1) @ P["multiscale.linear.weight"].T + P["multiscale.linear.bias"]
+    labels = np.asarray(labels).astype(np.int64)
+    z = logits - logits.max(1, keepdims=True)
+    logp = z - np.log(np.exp(z).sum(1, keepdims=True))
+    return logits, latents, float(-logp[np.arange(len(labels)), labels].mean())
+
+
 def forward(P, inp, cfg):
     """P: {name: float64 array}; inp: pyramid dict of NumPy arrays; cfg: contrastboundary_b200.convnet.ConvNetConfig-like
     -> (logits (n0, ncls), loss vector [xen, cbl_0..cbl_4], latents)"""
@@ -193,13 +207,8 @@ def forward(P, inp, cfg):
     # multiscale head
     up_idx0, cls = head_geometry({k: ([np.asarray(a) for a in v] if isinstance(v, (list, tuple)) else np.asarray(v)) for k, v in inp.items()
                                   if k in ("points", "batches_len", "point_labels", "upsamples", "pools")}, cfg.r_sample, cfg.num_classes)
-    latents = [conv1d_1x1(P, f"multiscale.mlp.{i}", f_out[i], eps) for i in range(cfg.num_layers)]
-    cols = [latents[0]] + [closest(latents[i], up_idx0[i]) for i in range(1, cfg.num_layers)]
-    logits = np.concatenate(cols, 1) @ P["multiscale.linear.weight"].T + P["multiscale.linear.bias"]
-    labels = np.asarray(inp["point_labels"]).astype(np.int64)
-    z = logits - logits.max(1, keepdims=True)
-    logp = z - np.log(np.exp(z).sum(1, keepdims=True))
-    losses = [float(-logp[np.arange(len(labels)), labels].mean())]
+    logits, latents, xen = multiscale_head(P, f_out, up_idx0, np.asarray(inp["point_labels"]), cfg)
+    losses = [xen]
     if cfg.contrast:
         for i in range(cfg.num_layers):
             losses.append(contrast_loss(latents[i], np.asarray(inp["neighbors"][i]), np.asarray(cls[i]), cfg.contrast_temperature,

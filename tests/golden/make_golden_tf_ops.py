@@ -152,6 +152,40 @@ def main():
         out[f"cbl/loss/{i}"] = np.float64(res["loss"])
         out[f"cbl/scene_label/{i}"] = labels0 if scene_lab is None else np.asarray(scene_lab).reshape(-1).astype(np.int64)
         print("contrast head stage", i, "loss", float(res["loss"]), "points with pos and neg:", int(np.asarray(res["logits"]).shape[0]))
+
+    # ---- the multi-scale head '||Ua-concat-latent' (heads/head.py:338-460) with the reference's OWN head-config object
+    #      (config/head.py: multiscale_1) on the executed backbone's features: latent_i = mlp(f_out_i), nearest upsampling to U0,
+    #      concat, linear classifier, sparse softmax cross-entropy --------------------------------------------------------------------------
+    cpkg = types.ModuleType("refconfig")
+    cpkg.__path__ = [os.path.join(REF, "tensorflow", "config")]
+    sys.modules["refconfig"] = cpkg
+    hc = importlib.import_module("refconfig.head")
+    mcfg = hc.main_dict["multiscale_1"]
+    assert mcfg._ops == "||Ua-concat-latent" and hc.contrast_dict["contrast_0"]._ops == "softnn|latent|label|l2||w.1|Ua"
+
+    class GlobalConfig:                      # config/base.py: a missing attribute reads as ''
+        def __getattr__(self, name):
+            return ""
+    gc = GlobalConfig()
+    gc.__dict__.update(num_layers=5, num_classes=13, first_features_dim=fdim, init="xavier", weight_decay=0, bn_momentum=0.99, bn_eps=1e-6,
+                       activation="relu", search="radius", sample="grid", ignored_labels=[], debug=False,
+                       r_sample=[0.6 * dl * 2 ** (i + 1) for i in range(4)])   # config/s3dis.py:87, shrunk so that some
+    #                                                   level-0 points find NO level-i point in range (the zero-row gather path)
+    f_out = [F_up[0], F_up[1], F_up[2], F_up[3], F[4]]
+    mstage = [{"p_out": stage[i]["p_out"], "f_out": f_out[i]} for i in range(5)]
+    minputs = dict(cinputs, stage_list={"up": mstage, "down": mstage}, _glb={})
+    shim.reset(seed=9)
+    with shim.variable_scope("multi"):
+        hd = head.multiscale_head()(minputs, mcfg, gc, True)
+    out["multi/logits"], out["multi/loss"] = hd["logits"]["seg"], np.float64(hd["loss"]["seg"])
+    out["multi/r_sample"] = np.asarray(gc.r_sample)
+    for i in range(5):
+        out[f"multi/latent/{i}"] = mstage[i]["latent"]
+    for name, value in shim.variables().items():
+        out["multi/var/" + name] = value
+    shadow = {k: int((np.asarray(v) == len(pyr["points"][int(k.split("-")[0][-1])])).sum()) for k, v in minputs["_glb"].items() if "sample_neighbor" in k}
+    print("multi-scale head: loss", float(hd["loss"]["seg"]), "logits", hd["logits"]["seg"].shape, "variables", sorted(shim.variables())[:4], "...",
+          "level-0 points without a level-i point in range:", shadow)
     np.savez_compressed(os.path.join(HERE, "tf_ops_ref.npz"), **out)
     print("wrote tests/golden/tf_ops_ref.npz", sum(a.nbytes for a in out.values()) // 1024, "KiB")
 

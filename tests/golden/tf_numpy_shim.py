@@ -101,6 +101,12 @@ def _variance_scaling_initializer(factor=2.0, mode="FAN_IN", uniform=False, **_)
     return init
 
 
+def _vs(scale=1.0, **_):
+    return _variance_scaling_initializer(factor=scale)
+
+
+initializers = types.SimpleNamespace(glorot_uniform=glorot_uniform_initializer, glorot_normal=glorot_uniform_initializer,
+                                     variance_scaling=_vs, zeros=zeros_initializer, ones=ones_initializer)
 contrib = types.SimpleNamespace(layers=types.SimpleNamespace(variance_scaling_initializer=_variance_scaling_initializer))
 
 
@@ -141,8 +147,16 @@ def TensorShape(dims):
 
 
 def gather(params, indices, axis=0, batch_dims=0, **_):
-    assert batch_dims == 0
-    return np.take(np.asarray(params), np.asarray(indices).astype(np.int64), axis=axis)
+    """tf.gather, GPU-kernel semantics for an out-of-range index: the output row is zero (the CPU kernel raises).  The
+    reference relies on it: multiscale_head gathers with the one-past-the-end shadow index of a radius search that found
+    nothing (heads/head.py:455-458), and it trains on GPU."""
+    assert batch_dims == 0 and axis == 0
+    params, idx = np.asarray(params), np.asarray(indices).astype(np.int64)
+    n = params.shape[0]
+    assert idx.min() >= 0 and idx.max() <= n, "only the one-past-the-end shadow index is expected out of range"
+    if idx.max() < n:
+        return params[idx]
+    return np.concatenate([params, np.zeros_like(params[:1])], 0)[idx]
 
 
 def one_hot(indices, depth, axis=-1, dtype=np.float64, **_):
@@ -275,7 +289,14 @@ def _l2_normalize(x, axis=-1, epsilon=1e-12, **_):
     return x / np.sqrt(np.maximum(np.sum(np.square(x), axis=axis, keepdims=True), epsilon))
 
 
-nn = types.SimpleNamespace(relu=_relu, leaky_relu=_leaky_relu, softmax=_softmax, l2_loss=_l2_loss, l2_normalize=_l2_normalize)
+def _sparse_xent(labels=None, logits=None, name=None, **_):
+    z = logits - logits.max(axis=-1, keepdims=True)
+    logp = z - np.log(np.exp(z).sum(axis=-1, keepdims=True))
+    return -logp[np.arange(logp.shape[0]), np.asarray(labels).astype(np.int64)]
+
+
+nn = types.SimpleNamespace(relu=_relu, leaky_relu=_leaky_relu, softmax=_softmax, l2_loss=_l2_loss, l2_normalize=_l2_normalize,
+                           sparse_softmax_cross_entropy_with_logits=_sparse_xent)
 
 
 def _batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, training=False, trainable=True, name=None, fused=None, **_):

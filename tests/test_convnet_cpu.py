@@ -85,6 +85,39 @@ def test_backbone_and_seg_head_restatement_match_executed_reference_source():
         assert np.abs(f_out[l] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), l
 
 
+def test_multiscale_head_restatement_matches_executed_reference_source():
+    """The reference's multiscale_head (heads/head.py:338-460) EXECUTED on the NumPy TF stand-in with the reference's own
+    head-config object (config/head.py multiscale_1 = '||Ua-concat-latent') on the executed backbone's features: per-stage latent
+    MLP, nearest upsampling to the input points through the cross-stage radius search (some input points find no coarse point
+    in range and gather the zero row), concat, linear classifier, mean sparse softmax cross-entropy.  The restatement
+    reproduces latents, logits and loss; the variable names go through the product's checkpoint-name converter."""
+    import os
+    import types
+    from contrastboundary_b200 import convnet
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    P = {}
+    for key in g.files:
+        if key.startswith("multi/var/"):
+            m = convnet.tf_variable_to_state_dict(key[len("multi/var/"):])
+            assert m is not None, key
+            P[m[0]] = g[key].T.copy() if m[1] else g[key]
+    ref_keys = set(convnet.ConvNetSeg(convnet.ConvNetConfig()).state_dict().keys())
+    assert len(P) == 5 * 5 + 2 and set(P) <= ref_keys
+    inp = {k: [g[f"net/{k}/{l}"] for l in range(5)] for k in ("points", "upsamples", "pools")}
+    inp["batches_len"] = [g[f"cbl/batches_len/{l}"] for l in range(5)]
+    inp["point_labels"] = g["cbl/point_labels"]
+    up_idx0, _ = R.head_geometry(inp, [float(r) for r in g["multi/r_sample"]], 13)
+    assert sum(int((up_idx0[i] == len(inp["points"][i])).sum()) for i in range(2, 5)) > 50          # the zero-row path is exercised
+    f_out = [g[f"net/F_up/{l}"] for l in range(4)] + [g["net/F/4"]]
+    cfg = types.SimpleNamespace(bn_eps=1e-6, num_layers=5)
+    logits, latents, xen = R.multiscale_head(P, f_out, up_idx0, inp["point_labels"], cfg)
+    for i in range(5):
+        ref = g[f"multi/latent/{i}"]
+        assert np.abs(latents[i] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), i
+    assert np.abs(logits - g["multi/logits"]).max() < 1e-9 * np.abs(g["multi/logits"]).max()
+    assert abs(xen - float(g["multi/loss"])) < 1e-12 * float(g["multi/loss"]) + 1e-12
+
+
 def test_contrast_head_restatements_match_executed_reference_source():
     """a14: the reference's contrast head (heads/head.py:462-807 — sample_labels 'label', collect_labels / get_scene_label 'max',
     solve_samples_mask, calc_dist 'l2', soft-NN) EXECUTED on the NumPy TF stand-in at every stage of a 5-level pyramid; its
