@@ -17,9 +17,9 @@ TensorFlow is not part of this stack (it is not installable here): variable scop
 (`resnet_backbone.res2_strided_bottleneck.conv2.local_aggregation.fc_1` ...), kernels are stored (out, in) as torch does.
 
 PARITY: no TensorFlow in the build container or on the GPU box.  AdaptiveWeight, the resnet backbone, the segmentation
-head and the contrast head (hard sub-scene labels, soft-NN loss) are pinned by vectors from the reference's own TF source
-executed on a NumPy stand-in of the TF-1 API (tests/golden/make_golden_tf_ops.py -> tf_ops_ref.npz); the multi-scale head,
-the composition of the loss vector and the gradients are checked against two independent restatements of the reference source — oracle/tf_model.py (operators, torch) and oracle/tf_convnet_np.py (the
+head, the multi-scale head + cross-entropy and the contrast head (hard sub-scene labels, soft-NN loss) are pinned by vectors
+from the reference's own TF source executed on a NumPy stand-in of the TF-1 API (tests/golden/make_golden_tf_ops.py ->
+tf_ops_ref.npz); the gradients are checked against two independent restatements of the reference source — oracle/tf_model.py (operators, torch) and oracle/tf_convnet_np.py (the
 whole network and loss, NumPy float64) — plus a finite-difference check of the gradients against the float64 restatement
 (tests/test_convnet_gpu.py).
 """
