@@ -117,6 +117,14 @@ def main():
     for name, value in shim.variables().items():
         out["net/var/" + name] = value
     print("backbone + seg head: level sizes", [len(p) for p in pyr["points"]], "variables", len(shim.variables()))
+    # which variables carry an L2 weight loss when weight_decay > 0 (basic_operators.py:126-129,371-379): the same code once more
+    shim.reset(seed=5)
+    F2 = resnet.resnet_backbone(cfg2, inputs, feat_in, base_radius=dl * density, base_fdim=fdim, bottleneck_ratio=2, depth=1, is_training=True,
+                                init="xavier", weight_decay=1e-3, activation_fn="relu", bn=True, bn_momentum=0.98, bn_eps=1e-3)
+    seg.resnet_scene_segmentation_head(cfg2, inputs, F2, base_fdim=fdim, is_training=True, init="xavier", weight_decay=1e-3,
+                                       activation_fn="relu", bn=True, bn_momentum=0.98, bn_eps=1e-3)
+    assert all(np.array_equal(a, b) for a, b in zip(F, F2))
+    l2_names = list(shim.taps()["l2_loss_variables"])
 
     # ---- a14: the contrast head (heads/head.py:462-807) on the same pyramid: label sampling ('label'), hard sub-scene labels
     #      (get_scene_label 'max': pools for stage 1, a radius search among the level-0 points beyond), soft-NN on l2 distances --------------
@@ -167,7 +175,7 @@ def main():
         def __getattr__(self, name):
             return ""
     gc = GlobalConfig()
-    gc.__dict__.update(num_layers=5, num_classes=13, first_features_dim=fdim, init="xavier", weight_decay=0, bn_momentum=0.99, bn_eps=1e-6,
+    gc.__dict__.update(num_layers=5, num_classes=13, first_features_dim=fdim, init="xavier", weight_decay=1e-3, bn_momentum=0.99, bn_eps=1e-6,
                        activation="relu", search="radius", sample="grid", ignored_labels=[], debug=False,
                        r_sample=[0.6 * dl * 2 ** (i + 1) for i in range(4)])   # config/s3dis.py:87, shrunk so that some
     #                                                   level-0 points find NO level-i point in range (the zero-row gather path)
@@ -183,6 +191,8 @@ def main():
         out[f"multi/latent/{i}"] = mstage[i]["latent"]
     for name, value in shim.variables().items():
         out["multi/var/" + name] = value
+    l2_names += list(shim.taps()["l2_loss_variables"])
+    out["l2_loss_variables"] = np.array(sorted(l2_names))
     shadow = {k: int((np.asarray(v) == len(pyr["points"][int(k.split("-")[0][-1])])).sum()) for k, v in minputs["_glb"].items() if "sample_neighbor" in k}
     print("multi-scale head: loss", float(hd["loss"]["seg"]), "logits", hd["logits"]["seg"].shape, "variables", sorted(shim.variables())[:4], "...",
           "level-0 points without a level-i point in range:", shadow)

@@ -231,7 +231,11 @@ def cast(x, dtype, **_):
 
 
 sqrt, square, exp, log, abs, maximum, minimum = np.sqrt, np.square, np.exp, np.log, np.abs, np.maximum, np.minimum
-multiply, add, subtract, divide = np.multiply, np.add, np.subtract, np.divide
+def multiply(x, y, name=None):
+    return np.multiply(x, y)
+
+
+add, subtract, divide = np.add, np.subtract, np.divide
 less, greater, greater_equal, less_equal, equal, logical_and, logical_or, logical_not = (
     np.less, np.greater, np.greater_equal, np.less_equal, np.equal, np.logical_and, np.logical_or, np.logical_not)
 
@@ -282,6 +286,9 @@ def _softmax(x, axis=-1, **_):
 
 
 def _l2_loss(x, **_):
+    for name, v in _State.variables.items():            # remember WHICH variables the reference regularises
+        if v is x:
+            _State.taps.setdefault("l2_loss_variables", []).append(name)
     return 0.5 * np.sum(np.square(x))
 
 

@@ -118,6 +118,31 @@ def test_multiscale_head_restatement_matches_executed_reference_source():
     assert abs(xen - float(g["multi/loss"])) < 1e-12 * float(g["multi/loss"]) + 1e-12
 
 
+def test_weight_decay_set_matches_executed_reference_source():
+    """Which variables the reference puts an L2 weight loss on (recorded while its source ran with weight_decay > 0:
+    basic_operators.py:126-129,371-379) == the parameters ConvNetSeg.decay_parameters() hands to the optimiser's weight decay
+    (l2_loss = sum(w^2) / 2, so d/dw = weight_decay * w: the same update)."""
+    import os
+    from contrastboundary_b200 import convnet
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    l2 = set(str(n) for n in g["l2_loss_variables"])
+    names = [k[len("net/var/"):] for k in g.files if k.startswith("net/var/")] + [k[len("multi/var/"):] for k in g.files if k.startswith("multi/var/")]
+    assert len(l2) == 34 and l2 <= set(names)
+    model = convnet.ConvNetSeg(convnet.ConvNetConfig())
+    decay, rest = model.decay_parameters()
+    decay_ids = {id(p) for p in decay}
+    param_names = {n: id(p) for n, p in model.named_parameters()}
+    checked = 0
+    for tf_name in names:
+        key, _ = convnet.tf_variable_to_state_dict(tf_name)
+        if key not in param_names:                      # running statistics are buffers, not parameters
+            assert key.endswith(("running_mean", "running_var")), key
+            continue
+        assert (param_names[key] in decay_ids) == (tf_name in l2), (tf_name, key)
+        checked += 1
+    assert checked > 120
+
+
 def test_contrast_head_restatements_match_executed_reference_source():
     """a14: the reference's contrast head (heads/head.py:462-807 — sample_labels 'label', collect_labels / get_scene_label 'max',
     solve_samples_mask, calc_dist 'l2', soft-NN) EXECUTED on the NumPy TF stand-in at every stage of a 5-level pyramid; its
