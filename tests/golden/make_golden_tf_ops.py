@@ -1,12 +1,25 @@
-"""Golden vectors for the TF tree's ConvNet operators, produced by EXECUTING the reference's own source
-(/root/reference/tensorflow/models/local_aggregation_operators.py + basic_operators.py + utils.py, unmodified) on the NumPy
-stand-in for the TF-1 API in tf_numpy_shim.py (TensorFlow is not installable in the build container).
+"""Golden vectors for the TF tree's ConvNet (BASELINE config 3), produced by EXECUTING the reference's own source files,
+unmodified, from /root/reference — TensorFlow itself is not installable in the build container, so `tensorflow` is the NumPy
+stand-in of the TF-1 API in tf_numpy_shim.py (eager meaning of every op the files call, float64, variables in a scope-keyed
+dictionary):
+
+    tensorflow/models/local_aggregation_operators.py   AdaptiveWeight (config/s3dis/adapt.yaml)                      row a13
+    tensorflow/models/basic_operators.py, utils.py      conv1d_1x1, batch_norm, ind_max_pool, ind_closest_pool, dense_layer, mlps, ...
+    tensorflow/models/backbone/resnet.py                resnet_backbone (input conv, simple block, strided / plain bottlenecks)
+    tensorflow/models/heads/seg_head.py                 resnet_scene_segmentation_head (sep_head)
+    tensorflow/models/heads/head.py                     multiscale_head ('||Ua-concat-latent') + cross-entropy,
+                                                        contrast_head (label sampling, hard sub-scene labels, soft-NN)       row a14
+    tensorflow/config/head.py                           the reference's own head-config objects (multiscale_1, contrast_0)
+
+The 5-level input pyramid and the heads' cross-stage radius searches come from the CPU oracle of the reference's C++ operators
+(oracle/, itself pinned against the reference's compiled C++).
 
     python tests/golden/make_golden_tf_ops.py        -> tests/golden/tf_ops_ref.npz
 
-This pins row a13 (AdaptiveWeight, adapt.yaml) against reference code that actually ran, instead of restatements only:
-the oracle restatements (oracle/tf_model.py, oracle/tf_convnet_np.py) are checked against these vectors on the CPU
-(tests/test_convnet_cpu.py) and the CUDA kernels against the same vectors on the GPU (tests/test_convnet_gpu.py)."""
+Consumers: tests/test_convnet_cpu.py (both restatements == these vectors; the set of L2-regularised variables ==
+ConvNetSeg.decay_parameters(); TF variable names through convnet.tf_variable_to_state_dict) and tests/test_tfops_gpu.py (the CUDA
+AdaptiveWeight kernel, label votes and soft-NN loss == these vectors); the CUDA network is tested against the restatement
+(tests/test_convnet_gpu.py)."""
 import importlib
 import os
 import sys
