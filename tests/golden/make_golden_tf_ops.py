@@ -209,6 +209,36 @@ def main():
     shadow = {k: int((np.asarray(v) == len(pyr["points"][int(k.split("-")[0][-1])])).sum()) for k, v in minputs["_glb"].items() if "sample_neighbor" in k}
     print("multi-scale head: loss", float(hd["loss"]["seg"]), "logits", hd["logits"]["seg"].shape, "variables", sorted(shim.variables())[:4], "...",
           "level-0 points without a level-i point in range:", shadow)
+    # ---- the WHOLE model: the reference's own builder (models/build_models.py SceneSegModel), driven by its own config object
+    #      (config/s3dis.py Conv '|multi-Ua-concat-latent|contrast-Ua-softnn-latent-label-l2-w.1' + config/s3dis/adapt.yaml), on the
+    #      same pyramid: backbone -> seg head -> build_head (load_config + apply_head_ops for both heads) -> build_loss -----------------------
+    cwd = os.getcwd()
+    os.chdir(os.path.join(REF, "tensorflow"))          # the reference resolves 'config/s3dis/adapt.yaml' relative to its tree
+    sys.path.insert(0, os.path.join(REF, "tensorflow"))
+    sys.modules["termcolor"] = types.SimpleNamespace(colored=lambda s_, *a, **k: s_)       # utils/logger.py colours its prints
+    try:
+        import config as refcfg
+        import models as refmodels_full
+        rcfg = refcfg.Config(refcfg.load_config(dataset_name="s3dis", cfg_name="conv_multi-Ua-concat-latent_contrast-Ua-softnn-latent-label-l2-w.1"))
+        assert rcfg.arch_out == ["multi-Ua-concat-latent", "contrast-Ua-softnn-latent-label-l2-w.1"] and rcfg.depth == 1 and rcfg.bn_eps == 1e-6
+        rcfg.update({"first_features_dim": 4}, exclude=[])                                 # 72 in adapt.yaml: smaller vectors, same code
+        finputs = {"points": [np.asarray(p, np.float64).view(GraphTensor) for p in pyr["points"]],
+                   "neighbors": inputs["neighbors"], "pools": inputs["pools"], "upsamples": inputs["upsamples"],
+                   "batches_len": [np.asarray(x, np.int64) for x in pyr["batches_len"]], "features": feat_in, "point_labels": labels0,
+                   "in_batches": None, "out_batches": None}
+        shim.reset(seed=13)
+        model = refmodels_full.SceneSegModel(finputs, True, rcfg, scope=None, verbose=False)
+    finally:
+        os.chdir(cwd)
+    out["full/config"] = np.array([rcfg.first_features_dim, rcfg.first_subsampling_dl, rcfg.density_parameter, rcfg.bottleneck_ratio, rcfg.depth,
+                                   rcfg.bn_eps, rcfg.weight_decay, rcfg.num_classes], np.float64)
+    out["full/r_sample"] = np.asarray(rcfg.r_sample, np.float64)
+    out["full/logits"] = model.head_dict["result"]["seg"]["logits"]
+    for k_, v_ in model.loss_dict.items():
+        out["full/loss/" + k_] = np.float64(v_)
+    for name, value in shim.variables().items():
+        out["full/var/" + name] = value
+    print("whole model:", {k_: round(float(v_), 6) for k_, v_ in model.loss_dict.items()}, "variables", len(shim.variables()))
     np.savez_compressed(os.path.join(HERE, "tf_ops_ref.npz"), **out)
     print("wrote tests/golden/tf_ops_ref.npz", sum(a.nbytes for a in out.values()) // 1024, "KiB")
 

@@ -272,6 +272,21 @@ def add_to_collection(name, value):
     _State.collections.setdefault(name, []).append(value)
 
 
+def get_collection(name, scope=None):
+    assert scope is None
+    return list(_State.collections.get(name, []))
+
+
+def add_n(inputs, name=None):
+    out = 0.0
+    for v in inputs:
+        out = out + v
+    return out
+
+
+accumulate_n = add_n
+
+
 def _relu(x, **_):
     return np.maximum(x, 0)
 

@@ -118,6 +118,45 @@ def test_multiscale_head_restatement_matches_executed_reference_source():
     assert abs(xen - float(g["multi/loss"])) < 1e-12 * float(g["multi/loss"]) + 1e-12
 
 
+def test_whole_network_restatement_matches_executed_reference_model():
+    """The reference's OWN builder — models/build_models.py SceneSegModel with its own config object (config/s3dis.py Conv
+    '|multi-Ua-concat-latent|contrast-Ua-softnn-latent-label-l2-w.1' + config/s3dis/adapt.yaml; only first_features_dim is
+    reduced) — EXECUTED end to end on the NumPy TF stand-in: backbone, segmentation head, build_head (its load_config +
+    apply_head_ops for both heads), build_loss.  The float64 restatement that the CUDA network is tested against
+    (oracle/tf_convnet_np.forward) reproduces the logits, every entry of the loss dictionary, the L2 term and the total."""
+    import os
+    import types
+    from contrastboundary_b200 import convnet
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    fdim, dl, density, ratio, depth, eps, wd, ncls = g["full/config"]
+    assert (ratio, depth, eps, wd, ncls) == (2, 1, 1e-6, 1e-3, 13)                     # adapt.yaml / s3dis.py values reached the model
+    P, l2 = {}, 0.0
+    decay_rule = lambda k: k.endswith("weights.weight") or k.endswith("linear.weight")     # ConvNetSeg.decay_parameters()
+    for key in g.files:
+        if key.startswith("full/var/"):
+            m = convnet.tf_variable_to_state_dict(key[len("full/var/"):])
+            assert m is not None, key
+            P[m[0]] = g[key].T.copy() if m[1] else g[key]
+            if decay_rule(m[0]):
+                l2 += wd * 0.5 * float((g[key] ** 2).sum())
+    cfg = types.SimpleNamespace(bn_eps=float(eps), first_features_dim=int(fdim), first_subsampling_dl=float(dl), density_parameter=float(density),
+                                num_layers=5, depth=int(depth), r_sample=[float(r) for r in g["full/r_sample"]], num_classes=int(ncls),
+                                contrast=True, contrast_temperature=None, contrast_weight=0.1)
+    inp = {k: [g[f"net/{k}/{l}"].astype(np.float64 if k == "points" else np.int64) for l in range(5)] for k in ("points", "neighbors", "pools", "upsamples")}
+    inp["batches_len"] = [g[f"cbl/batches_len/{l}"] for l in range(5)]
+    inp["point_labels"], inp["features"] = g["cbl/point_labels"], g["net/features"]
+    logits, losses, latents, _ = R.forward(P, inp, cfg)
+    ref = g["full/logits"]
+    assert np.abs(logits - ref).max() < 1e-8 * np.abs(ref).max()
+    names = ["seg"] + [f"softnn-up{i}" for i in range(5)]
+    for v, n in zip(losses, names):
+        r = float(g["full/loss/" + n])
+        assert abs(v - r) < 1e-9 * max(1.0, abs(r)), (n, v, r)
+    assert sum(float(g["full/loss/" + n]) > 0 for n in names) >= 5
+    assert abs(l2 - float(g["full/loss/l2_loss"])) < 1e-12 * float(g["full/loss/l2_loss"])   # the optimiser's weight-decay set, as an L2 loss
+    assert abs(losses.sum() + l2 - float(g["full/loss/loss"])) < 1e-9 * float(g["full/loss/loss"])
+
+
 def test_weight_decay_set_matches_executed_reference_source():
     """Which variables the reference puts an L2 weight loss on (recorded while its source ran with weight_decay > 0:
     basic_operators.py:126-129,371-379) == the parameters ConvNetSeg.decay_parameters() hands to the optimiser's weight decay
