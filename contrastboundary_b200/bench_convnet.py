@@ -160,11 +160,12 @@ def run(args, Clocks, root, cpu_baseline_fn=None):
                    "ms_pyramid": 1e3 * t_pyr / args.steps, "ms_network_fwd_bwd_update": 1e3 * t_net / args.steps,
                    "level_points": [int(p.shape[0]) for p in inputs["points"]],
                    "l2": "per-step working set exceeds the 126 MB L2; no explicit flush"},
-        "parity": "forward pinned under a stand-in runtime: TensorFlow is not installable here. AdaptiveWeight, the resnet backbone, the "
-                  "segmentation head, the multi-scale head + cross-entropy and the contrast head (hard sub-scene labels + soft-NN loss) "
-                  "are checked against vectors from the reference's own TF source executed on a NumPy stand-in of the TF-1 API "
-                  "(tests/golden/make_golden_tf_ops.py); gradients against float64 finite differences of that forward and two "
-                  "independent restatements (oracle/tf_model.py, oracle/tf_convnet_np.py)",
+        "parity": "forward pinned under a stand-in runtime: TensorFlow is not installable here, so the reference's own TF source - its "
+                  "operators, and its whole SceneSegModel builder with its own config object + adapt.yaml - is executed on a NumPy "
+                  "stand-in of the TF-1 API (tests/golden/make_golden_tf_ops.py). Directly against those vectors: the CUDA AdaptiveWeight "
+                  "kernel, label votes and soft-NN loss; transitively (CUDA network = float64 restatement on the GPU, restatement = "
+                  "executed reference on the CPU): logits, every loss entry, the L2 term. Gradients: float64 finite differences of "
+                  "that forward and two independent restatements (oracle/tf_model.py, oracle/tf_convnet_np.py)",
         "e2e": {"value": pts * args.steps / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 24,
                 "ms_per_step": 1e3 * t_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk,
