@@ -230,6 +230,25 @@ def main():
         model = refmodels_full.SceneSegModel(finputs, True, rcfg, scope=None, verbose=False)
     finally:
         os.chdir(cwd)
+    # ---- the input pyramid itself: datasets/base.py Dataset.tf_segmentation_inputs_radius (:767-842) executed, its two custom ops
+    #      (ops.get_tf_func 'grid' / 'radius') served by the CPU oracle of the reference's C++ -------------------------------------------------
+    def batch_subsampling(points, lens_, sampleDl=0.1, **_):
+        p_, l_ = oracle.batch_grid_subsampling(np.asarray(points, np.float32), np.asarray(lens_, np.int32), float(sampleDl))
+        return p_, l_
+    sys.modules["ops"] = types.SimpleNamespace(get_tf_func=lambda name, verbose=False: {"grid": batch_subsampling, "radius": radius_search}[name])
+    sys.modules.pop("datasets", None)
+    base = importlib.import_module("datasets.base")
+    ds = object.__new__(base.Dataset)
+    ds.config, ds.verbose, ds.neighborhood_limits = rcfg, False, limits
+    binds = np.repeat(np.arange(2), lens0)
+    ref_pyr = ds.tf_segmentation_inputs_radius(pts, feat_in, labels0, np.asarray(lens0, np.int32), binds)
+    for key in ("points", "neighbors", "pools", "upsamples", "batches_len"):
+        for l in range(5):
+            assert np.array_equal(np.asarray(ref_pyr[key][l]), np.asarray(pyr[key][l])), (key, l)     # == the arrays stored as net/*
+    out["pyr/in_batches"], out["pyr/out_batches"] = np.asarray(ref_pyr["in_batches"]), np.asarray(ref_pyr["out_batches"])
+    out["pyr/batch_weights"] = np.asarray(ref_pyr["batch_weights"], np.float64)
+    print("pyramid: datasets/base.py == the oracle composition at all 5 levels; in_batches", out["pyr/in_batches"].shape, "out_batches",
+          out["pyr/out_batches"].shape)
     out["full/config"] = np.array([rcfg.first_features_dim, rcfg.first_subsampling_dl, rcfg.density_parameter, rcfg.bottleneck_ratio, rcfg.depth,
                                    rcfg.bn_eps, rcfg.weight_decay, rcfg.num_classes], np.float64)
     out["full/r_sample"] = np.asarray(rcfg.r_sample, np.float64)

@@ -187,6 +187,26 @@ def cond(pred, true_fn=None, false_fn=None, name=None, **_):
     return true_fn() if np.asarray(pred).all() else false_fn()
 
 
+def while_loop(cond, body, loop_vars, shape_invariants=None, name=None, **_):
+    vars_ = list(loop_vars)
+    while np.asarray(cond(*vars_)).all():
+        vars_ = list(body(*vars_))
+    return vars_
+
+
+def map_fn(fn, elems, dtype=None, **_):
+    return np.stack([fn(e) for e in elems])
+
+
+def range(start, limit=None, delta=1, dtype=None, **_):          # noqa: A001  (tf.range)
+    return np.arange(start, limit, delta) if limit is not None else np.arange(start)
+
+
+def pad(tensor, paddings, mode="CONSTANT", constant_values=0, **_):
+    assert mode == "CONSTANT"
+    return np.pad(np.asarray(tensor), [(int(a), int(b)) for a, b in paddings], constant_values=constant_values)
+
+
 def stack(values, axis=0, **_):
     return np.stack(values, axis=axis)
 

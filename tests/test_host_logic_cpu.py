@@ -31,6 +31,23 @@ def test_stack_batch_inds_matches_reference_semantics():
     assert np.array_equal(c, np.array([[0, 1], [2, 3]], np.int32))
 
 
+def test_pyramid_host_logic_matches_executed_reference_source():
+    """The reference's input-pyramid builder (tensorflow/datasets/base.py:694-737,767-842), EXECUTED on the NumPy TF stand-in with its
+    two custom ops served by the CPU oracle of the reference's C++ (tests/golden/make_golden_tf_ops.py): the golden script asserts
+    that its five levels ARE the arrays stored as net/* (the oracle composition that tf_pyramid.segmentation_inputs_radius is
+    tested against on the GPU); here the product's host-side pieces reproduce its batch index matrices and batch weights."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    lens0, lens4 = g["cbl/batches_len/0"], g["cbl/batches_len/4"]
+    a = tf_pyramid.stack_batch_inds(torch.from_numpy(lens0.astype(np.int32))).numpy()
+    b = tf_pyramid.stack_batch_inds(torch.from_numpy(lens4.astype(np.int32))).numpy()
+    assert np.array_equal(a, g["pyr/in_batches"]) and np.array_equal(b, g["pyr/out_batches"])
+    inds = np.repeat(np.arange(len(lens0)), lens0)
+    w = (lens0.min().astype(np.float32) / lens0.astype(np.float32))[inds]                   # tf_pyramid.py:52-53 (base.py:776-779)
+    assert np.allclose(w, g["pyr/batch_weights"], rtol=1e-6, atol=0)
+    assert sum(len(g[f"net/points/{l}"]) for l in range(5)) == 2183 and g["net/upsamples/0"].shape == (0, 1) and g["net/pools/4"].shape == (0, 1)
+
+
 def test_batchnorm_wrapper_is_a_drop_in_on_cpu():
     """linear_ops.BatchNorm1d / bn_act: same parameters, buffers, state_dict and results as nn.BatchNorm1d (+ add + relu)"""
     torch.manual_seed(0)
