@@ -298,3 +298,41 @@ def test_convnet_modules_match_float64_restatement_and_finite_differences(monkey
         fd = (lp - lm) / (2 * eps)
         an = sum(float((params[n].grad.numpy() * d[n]).sum()) for n in names)
         assert abs(fd - an) <= 2e-3 * abs(fd), (gname, fd, an)
+
+
+def test_product_modules_loaded_from_the_executed_reference_model(monkeypatch):
+    """The PRODUCT's modules (convnet.ConvNetSeg / ConvNetLoss; libcbops operators swapped for plain-torch twins because CUDA is
+    absent here; float64) with the variables of the reference's own executed SceneSegModel loaded through
+    convnet.load_tf_variables (TF names -> state_dict keys, (in, out) kernels transposed): same logits, same loss entries as
+    the reference model produced (tests/golden/tf_ops_ref.npz 'full/*')."""
+    import os
+    from contrastboundary_b200 import convnet, linear_ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_ops_ref.npz"))
+    fdim, dl, density, ratio, depth, eps, wd, ncls = g["full/config"]
+    cfg = convnet.ConvNetConfig(first_features_dim=int(fdim), depth=int(depth), bottleneck_ratio=int(ratio), first_subsampling_dl=float(dl),
+                                density_parameter=float(density), bn_eps=float(eps), weight_decay=float(wd), num_classes=int(ncls))
+    assert np.allclose(cfg.r_sample, g["full/r_sample"])
+    monkeypatch.setattr(convnet, "adaptive_weight", lambda q, s, nb, f, w, b, r: T.adaptive_weight(q, s, nb, f, w, b, r))
+    monkeypatch.setattr(convnet, "ind_max_pool", lambda x, inds: torch.cat([x, x.min(0, keepdim=True)[0].detach()], 0)[inds.long()].max(1)[0])
+    monkeypatch.setattr(convnet, "tf_contrast_loss", lambda f, nb, c, t, w: T.contrast_loss(f, nb, c.long(), t, w))
+    monkeypatch.setattr(linear_ops, "FUSED_BN", False)
+    model = convnet.ConvNetSeg(cfg).double().train()
+    variables = {k[len("full/var/"):]: g[k] for k in g.files if k.startswith("full/var/")}
+    unused = convnet.load_tf_variables(model, variables)
+    assert unused == [], unused
+    trainable = {n for n, _ in model.named_parameters()}
+    loaded = {convnet.tf_variable_to_state_dict(n)[0] for n in variables}
+    assert trainable <= loaded                                       # every parameter of the product came from a reference variable
+    as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double() if a.dtype.kind == "f" else torch.from_numpy(np.ascontiguousarray(a))
+    inp = {k: [as_t(g[f"net/{k}/{l}"]) for l in range(5)] for k in ("points", "neighbors", "pools", "upsamples")}
+    inp["batches_len"] = [as_t(g[f"cbl/batches_len/{l}"]) for l in range(5)]
+    inp["point_labels"], inp["features"] = as_t(g["cbl/point_labels"]), as_t(g["net/features"])
+    np_inp = {k: ([a.numpy() for a in v] if isinstance(v, list) else v.numpy()) for k, v in inp.items()}
+    up0, cls = R.head_geometry(np_inp, cfg.r_sample, cfg.num_classes)
+    geo = {"up_idx0": [None] + [torch.from_numpy(u) for u in up0[1:]], "cls": [torch.from_numpy(np.asarray(c)).int() for c in cls]}
+    logits, sl = model(inp, geo)
+    loss = convnet.ConvNetLoss(cfg)(logits, inp["point_labels"], sl).detach().numpy()
+    ref = g["full/logits"]
+    assert np.abs(logits.detach().numpy() - ref).max() < 1e-6 * np.abs(ref).max()          # 1e-6: the float32 neighbour count of tf_model.py
+    names = ["seg"] + [f"softnn-up{i}" for i in range(5)]
+    np.testing.assert_allclose(loss, [float(g["full/loss/" + n]) for n in names], rtol=1e-6, atol=1e-12)
