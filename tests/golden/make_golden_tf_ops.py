@@ -258,6 +258,36 @@ def main():
     for name, value in shim.variables().items():
         out["full/var/" + name] = value
     print("whole model:", {k_: round(float(v_), 6) for k_, v_ in model.loss_dict.items()}, "variables", len(shim.variables()))
+
+    # ---- gradients of the executed model by central differences (the stand-in has no autodiff): directional derivatives of the sum of
+    #      the head losses (the loss vector the product back-propagates; the L2 term lives in its optimiser) along seeded directions ----------
+    import zlib
+    base_vars = {k_: v_.copy() for k_, v_ in shim.variables().items()}
+    groups = {"kernels": lambda n: n.endswith("/weights") and "/fc_1/" not in n, "fc_1": lambda n: "/fc_1/" in n,
+              "batch_norm": lambda n: n.endswith(("/gamma", "/beta"))}
+
+    def head_loss(values):
+        os.chdir(os.path.join(REF, "tensorflow"))
+        try:
+            shim.reset(seed=13)
+            shim.preset(values)
+            m_ = refmodels_full.SceneSegModel(dict(finputs), True, rcfg, scope=None, verbose=False)
+        finally:
+            os.chdir(cwd)
+        return float(m_.loss_dict["loss"]) - float(m_.loss_dict["l2_loss"])
+    assert abs(head_loss(base_vars) - (float(model.loss_dict["loss"]) - float(model.loss_dict["l2_loss"]))) < 1e-12
+    for gname, sel in groups.items():
+        names = sorted(n for n in base_vars if sel(n))
+        direction = {n: np.random.default_rng(zlib.crc32(n.encode())).standard_normal(base_vars[n].shape) for n in names}
+        scale = np.sqrt(sum(float((base_vars[n] ** 2).sum()) for n in names)) / np.sqrt(sum(float((d_ ** 2).sum()) for d_ in direction.values()))
+        vals = []
+        for rel in (2e-7, 2e-8, 2e-9):           # a ladder: the loss is piecewise smooth (ReLU kinks), small steps see fewer kinks
+            h = rel * scale
+            lp = head_loss({**base_vars, **{n: base_vars[n] + h * direction[n] for n in names}})
+            lm = head_loss({**base_vars, **{n: base_vars[n] - h * direction[n] for n in names}})
+            vals.append((lp - lm) / (2 * h))
+        out[f"full/dd/{gname}"] = np.asarray(vals, np.float64)
+        print("directional derivative", gname, len(names), "variables, steps 2e-7 / 2e-8 / 2e-9:", vals)
     np.savez_compressed(os.path.join(HERE, "tf_ops_ref.npz"), **out)
     print("wrote tests/golden/tf_ops_ref.npz", sum(a.nbytes for a in out.values()) // 1024, "KiB")
 

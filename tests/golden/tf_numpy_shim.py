@@ -32,6 +32,11 @@ def variables():
     return _State.variables
 
 
+def preset(values):
+    """start the next run from given variable values (get_variable returns an existing entry instead of initialising one)"""
+    _State.variables = {k: np.array(v, dtype=np.float64) for k, v in values.items()}
+
+
 def taps():
     return _State.taps
 

@@ -331,8 +331,24 @@ def test_product_modules_loaded_from_the_executed_reference_model(monkeypatch):
     up0, cls = R.head_geometry(np_inp, cfg.r_sample, cfg.num_classes)
     geo = {"up_idx0": [None] + [torch.from_numpy(u) for u in up0[1:]], "cls": [torch.from_numpy(np.asarray(c)).int() for c in cls]}
     logits, sl = model(inp, geo)
-    loss = convnet.ConvNetLoss(cfg)(logits, inp["point_labels"], sl).detach().numpy()
     ref = g["full/logits"]
     assert np.abs(logits.detach().numpy() - ref).max() < 1e-6 * np.abs(ref).max()          # 1e-6: the float32 neighbour count of tf_model.py
     names = ["seg"] + [f"softnn-up{i}" for i in range(5)]
-    np.testing.assert_allclose(loss, [float(g["full/loss/" + n]) for n in names], rtol=1e-6, atol=1e-12)
+    loss_t = convnet.ConvNetLoss(cfg)(logits, inp["point_labels"], sl)
+    np.testing.assert_allclose(loss_t.detach().numpy(), [float(g["full/loss/" + n]) for n in names], rtol=1e-6, atol=1e-12)
+    # backward: autograd through the product's modules == central differences of the EXECUTED reference model (the golden script
+    # re-ran the reference's builder at +-h along directions seeded by the TF variable names; a ladder of steps, because the loss is
+    # only piecewise smooth)
+    import zlib
+    loss_t.sum().backward()
+    params = dict(model.named_parameters())
+    groups = {"kernels": lambda n: n.endswith("/weights") and "/fc_1/" not in n, "fc_1": lambda n: "/fc_1/" in n,
+              "batch_norm": lambda n: n.endswith(("/gamma", "/beta"))}
+    for gname, sel in groups.items():
+        an = 0.0
+        for tf_name in sorted(n for n in variables if sel(n)):
+            key, transpose = convnet.tf_variable_to_state_dict(tf_name)
+            d = np.random.default_rng(zlib.crc32(tf_name.encode())).standard_normal(variables[tf_name].shape)
+            an += float((params[key].grad.numpy() * (d.T if transpose else d)).sum())
+        ladder = g[f"full/dd/{gname}"]
+        assert min(abs(an - fd) / abs(fd) for fd in ladder) < 2e-3, (gname, an, ladder)
